@@ -1,0 +1,284 @@
+"""Thin numpy-facing wrapper around the C ABI (one `Context` = one asgfem_ctx = one GPU, one refinement level).
+
+Everything is converted to exactly what a Julia caller would pass: 1-based Int64/Int32 index arrays,
+column-major matrices, flat `entries` vectors in the reference layout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+LEGENDRE, HERMITE = 0, 1
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.asgfem_create(C.byref(h), device)
+        if rc != 0:
+            raise _lib.AsgfemError(rc, self.lib.asgfem_last_error(None).decode())
+        self.h = h
+        self.n = 0
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.asgfem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise _lib.AsgfemError(rc, self.lib.asgfem_last_error(self.h).decode())
+
+    # ---- stochastic discretisation ---------------------------------------------------------------
+    def set_multiindices(self, family, multi_indices):
+        mi = _i64(np.asarray(multi_indices))  # (N, M) C-order == M x N column-major
+        self.N, self.Mlen = mi.shape
+        self._ck(self.lib.asgfem_set_multiindices(self.h, family, self.N, self.Mlen, _ptr(mi)))
+
+    def coupling_csc(self):
+        """G as (colptr, rowval, nzval), 1-based, of shape (M*N) x N (TensorizedBasis.G.cscmatrix)."""
+        nnz = C.c_int64()
+        self._ck(self.lib.asgfem_get_coupling_nnz(self.h, C.byref(nnz)))
+        colptr = np.zeros(self.N + 1, dtype=np.int64)
+        rowval = np.zeros(nnz.value, dtype=np.int64)
+        nzval = np.zeros(nnz.value)
+        self._ck(self.lib.asgfem_get_coupling_csc(self.h, _ptr(colptr), _ptr(rowval), _ptr(nzval)))
+        return colptr, rowval, nzval
+
+    def neighbours(self):
+        plus = np.zeros((self.N, self.Mlen), dtype=np.int64)
+        minus = np.zeros((self.N, self.Mlen), dtype=np.int64)
+        self._ck(self.lib.asgfem_get_neighbours(self.h, _ptr(plus), _ptr(minus)))
+        return plus.T.copy(), minus.T.copy()  # M x N like the Julia matrices
+
+    # ---- matrices --------------------------------------------------------------------------------
+    def set_pattern_csc(self, n, colptr, rowval):
+        self.n = int(n)
+        colptr, rowval = _i64(colptr), _i64(rowval)
+        self._ck(self.lib.asgfem_set_pattern_csc(self.h, n, _ptr(colptr), _ptr(rowval)))
+
+    def set_num_stiffness(self, M):
+        self._ck(self.lib.asgfem_set_num_stiffness(self.h, M))
+
+    def set_stiffness(self, m, nzval):
+        nzval = _f64(nzval)
+        self._ck(self.lib.asgfem_set_stiffness(self.h, m, _ptr(nzval)))
+
+    def set_stiffness_csc(self, m, colptr, rowval, nzval):
+        colptr, rowval, nzval = _i64(colptr), _i64(rowval), _f64(nzval)
+        self._ck(self.lib.asgfem_set_stiffness_csc(self.h, m, _ptr(colptr), _ptr(rowval), _ptr(nzval)))
+
+    def pattern_csc(self):
+        nnz = C.c_int64()
+        self._ck(self.lib.asgfem_get_pattern_nnz(self.h, C.byref(nnz)))
+        colptr = np.zeros(self.n + 1, dtype=np.int64)
+        rowval = np.zeros(nnz.value, dtype=np.int64)
+        self._ck(self.lib.asgfem_get_pattern_csc(self.h, _ptr(colptr), _ptr(rowval)))
+        return colptr, rowval
+
+    def get_stiffness(self, m):
+        nnz = C.c_int64()
+        self._ck(self.lib.asgfem_get_pattern_nnz(self.h, C.byref(nnz)))
+        v = np.zeros(nnz.value)
+        self._ck(self.lib.asgfem_get_stiffness(self.h, m, _ptr(v)))
+        return v
+
+    def set_bdofs(self, bdofs_1based):
+        b = _i64(bdofs_1based)
+        self._ck(self.lib.asgfem_set_bdofs(self.h, len(b), _ptr(b)))
+
+    # ---- mesh / space / coefficient ----------------------------------------------------------------
+    def set_mesh(self, coords_2xn, cellnodes_3xnc_1based):
+        """coords: (nnodes, 2) C-order == 2 x nnodes column-major; cellnodes: (ncells, 3), 1-based Int32."""
+        co = _f64(coords_2xn)
+        cn = _i32(cellnodes_3xnc_1based)
+        self._ck(self.lib.asgfem_set_mesh(self.h, co.shape[0], cn.shape[0], _ptr(co), _ptr(cn)))
+
+    def set_space(self, order, ndofs, celldofs_1based):
+        cd = _i32(celldofs_1based)  # (ncells, ndofs4cell) C-order == ndofs4cell x ncells column-major
+        self._ck(self.lib.asgfem_set_space(self.h, order, ndofs, cd.shape[1], _ptr(cd)))
+        self.n = int(ndofs)
+
+    def set_coefficient_cosinus(self, mean, decay_factors, b1, b2):
+        d, b1, b2 = _f64(decay_factors), _i64(b1), _i64(b2)
+        self._ck(self.lib.asgfem_set_coefficient_cosinus(self.h, len(d), float(mean), _ptr(d), _ptr(b1), _ptr(b2)))
+
+    def assemble_stiffness(self, M, xref, w):
+        xref, w = _f64(xref), _f64(w)  # xref (nq, 2) C-order == 2 x nq column-major
+        self._ck(self.lib.asgfem_assemble_stiffness(self.h, M, len(w), _ptr(xref), _ptr(w)))
+
+    # ---- vectors ---------------------------------------------------------------------------------
+    def vec_alloc(self, nslots):
+        self._ck(self.lib.asgfem_vec_alloc(self.h, nslots))
+
+    def vec_upload(self, slot, host):
+        host = _f64(host)
+        assert host.size == self.n * self.N, "host vector must have n*N entries (reference layout)"
+        self._ck(self.lib.asgfem_vec_upload(self.h, slot, _ptr(host)))
+
+    def vec_download(self, slot, out=None):
+        out = np.empty(self.n * self.N) if out is None else out
+        self._ck(self.lib.asgfem_vec_download(self.h, slot, _ptr(out)))
+        return out
+
+    def vec_zero(self, slot):
+        self._ck(self.lib.asgfem_vec_zero(self.h, slot))
+
+    def vec_fill_random(self, slot, seed=20240):
+        self._ck(self.lib.asgfem_vec_fill_random(self.h, slot, seed))
+
+    def vec_dot(self, a, b):
+        out = C.c_double()
+        self._ck(self.lib.asgfem_vec_dot(self.h, a, b, C.byref(out)))
+        return out.value
+
+    def vec_dot_owned(self, a, b):
+        out = C.c_double()
+        self._ck(self.lib.asgfem_vec_dot_owned(self.h, a, b, C.byref(out)))
+        return out.value
+
+    def vec_axpy(self, alpha, x, y):
+        self._ck(self.lib.asgfem_vec_axpy(self.h, alpha, x, y))
+
+    # ---- operator / preconditioner / solver ----------------------------------------------------------
+    def set_apply_variant(self, v):
+        self._ck(self.lib.asgfem_set_apply_variant(self.h, v))
+
+    def apply(self, sx, sy):
+        self._ck(self.lib.asgfem_apply(self.h, sx, sy))
+
+    def last_apply_ms(self):
+        out = C.c_double()
+        self._ck(self.lib.asgfem_last_apply_ms(self.h, C.byref(out)))
+        return out.value
+
+    def apply_host(self, x, out=None):
+        x = _f64(x)
+        out = np.empty_like(x) if out is None else out
+        self._ck(self.lib.asgfem_apply_host(self.h, _ptr(x), _ptr(out)))
+        return out
+
+    def apply_host_ptr(self, x_ptr, y_ptr):
+        """Raw host pointers (e.g. pinned torch tensors) - used by bench.py's end-to-end leg."""
+        self._ck(self.lib.asgfem_apply_host(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)))
+
+    def precond_setup(self):
+        self._ck(self.lib.asgfem_precond_setup(self.h))
+
+    def precond_apply(self, sr, sz):
+        self._ck(self.lib.asgfem_precond_apply(self.h, sr, sz))
+
+    def precond_apply_host(self, b, out=None):
+        b = _f64(b)
+        out = np.empty_like(b) if out is None else out
+        self._ck(self.lib.asgfem_precond_apply_host(self.h, _ptr(b), _ptr(out)))
+        return out
+
+    def pcg(self, b0, slot_x, atol=1e-14, rtol=1e-14, itmax=0):
+        b0 = _f64(b0)
+        st = _lib.Stats()
+        self._ck(self.lib.asgfem_pcg(self.h, _ptr(b0), slot_x, atol, rtol, itmax, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
+
+    def solve_primal_host(self, sol, b0, atol=1e-14, rtol=1e-14, itmax=0):
+        assert sol.dtype == np.float64 and sol.flags.c_contiguous
+        b0 = _f64(b0)
+        st = _lib.Stats()
+        self._ck(self.lib.asgfem_solve_primal_host(self.h, _ptr(sol), _ptr(b0), atol, rtol, itmax, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
+
+    # ---- estimator -------------------------------------------------------------------------------
+    def estimate_poisson_primal(self, slot_u, mi_ext, xref, w, sf, wf, ncells, f_at_qp=None):
+        mi = _i64(np.asarray(mi_ext))
+        N_ext, M_ext = mi.shape
+        xref, w, sf, wf = _f64(xref), _f64(w), _f64(sf), _f64(wf)
+        fq = None if f_at_qp is None else _f64(f_at_qp)
+        eta4cell = np.zeros((N_ext, ncells))  # C-order (N_ext, ncells) == ncells x N_ext column-major
+        eta4modes = np.zeros(N_ext)
+        self._ck(self.lib.asgfem_estimate_poisson_primal(
+            self.h, slot_u, N_ext, M_ext, _ptr(mi), len(w), _ptr(xref), _ptr(w), _ptr(fq), len(wf), _ptr(sf),
+            _ptr(wf), _ptr(eta4cell), _ptr(eta4modes)))
+        return eta4modes, eta4cell.T  # view as ncells x N_ext
+
+    # ---- multi-GPU helpers -----------------------------------------------------------------------
+    def set_owned_rows(self, n_owned):
+        self._ck(self.lib.asgfem_set_owned_rows(self.h, n_owned))
+
+    def vec_device_ptr(self, slot):
+        p, ld = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.asgfem_vec_device_ptr(self.h, slot, C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+    def pack_rows(self, slot, rows_1based, dbuf_ptr):
+        r = _i64(rows_1based)
+        self._ck(self.lib.asgfem_pack_rows(self.h, slot, len(r), _ptr(r), C.c_void_p(dbuf_ptr)))
+
+    def unpack_rows(self, slot, rows_1based, dbuf_ptr):
+        r = _i64(rows_1based)
+        self._ck(self.lib.asgfem_unpack_rows(self.h, slot, len(r), _ptr(r), C.c_void_p(dbuf_ptr)))
+
+
+# ---- context-free index helpers ------------------------------------------------------------------
+def coupling_weights(family, maxdeg):
+    lib = _lib.load()
+    gp = np.zeros(maxdeg + 1)
+    gm = np.zeros(maxdeg + 1)
+    rc = lib.asgfem_coupling_weights(family, maxdeg, _ptr(gp), _ptr(gm))
+    if rc:
+        raise _lib.AsgfemError(rc, "asgfem_coupling_weights")
+    return gp, gm
+
+
+def add_boundary_modes(multi_indices, p_extension=1, tail_extension=(10, 2)):
+    lib = _lib.load()
+    mi = _i64(np.asarray(multi_indices))
+    N, M = mi.shape
+    Next, Mext = C.c_int64(), C.c_int64()
+    rc = lib.asgfem_add_boundary_modes(N, M, _ptr(mi), p_extension, tail_extension[0], tail_extension[1],
+                                       C.byref(Next), C.byref(Mext), None, 0)
+    if rc:
+        raise _lib.AsgfemError(rc, "asgfem_add_boundary_modes")
+    out = np.zeros((Next.value, Mext.value), dtype=np.int64)
+    rc = lib.asgfem_add_boundary_modes(N, M, _ptr(mi), p_extension, tail_extension[0], tail_extension[1],
+                                       C.byref(Next), C.byref(Mext), _ptr(out), out.size)
+    if rc:
+        raise _lib.AsgfemError(rc, "asgfem_add_boundary_modes")
+    return out
+
+
+def classify_modes(mi_ext, n_active):
+    """Returns (inactive_else, inactive_bnd, inactive_bnd2, active_bnd, active_int) as 1-based index lists."""
+    lib = _lib.load()
+    mi = _i64(np.asarray(mi_ext))
+    cls = np.zeros(mi.shape[0], dtype=np.int32)
+    rc = lib.asgfem_classify_modes(mi.shape[0], mi.shape[1], _ptr(mi), n_active, _ptr(cls))
+    if rc:
+        raise _lib.AsgfemError(rc, "asgfem_classify_modes")
+    return tuple((np.where(cls == c)[0] + 1).tolist() for c in range(5))

@@ -1,0 +1,323 @@
+// Host-side sparse Cholesky of the Dirichlet-reduced mean stiffness matrix K_0.
+//
+// Replaces `lu(A0.cscmatrix)` of MyPreconditionerPrimal (src/modelproblems/solvers_poisson_primal.jl:30-44):
+// the reference pins boundary dofs with a 1e60 diagonal and hands the matrix to UMFPACK; here the boundary
+// rows/columns are removed (the result on those rows is defined as exactly 0) and the remaining SPD matrix is
+// factorised as P K P^T = L L^T once per refinement level:
+//   1. fill-reducing ordering: graph nested dissection with BFS level-set separators (no METIS in the image),
+//   2. elimination tree + column counts by row-subtree traversal,
+//   3. up-looking numeric factorisation.
+// The factor is returned row-wise (strictly lower part + inverse diagonal) for the device triangular solves.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "common.h"
+
+namespace asgfem {
+
+namespace {
+
+struct Graph {
+    int32_t n;
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> adj;
+};
+
+// BFS restricted to nodes with tag[node] == id; returns the level structure in `out` (concatenated), level starts in lv
+int32_t bfs(const Graph& g, int32_t start, const std::vector<int32_t>& tag, int32_t id, std::vector<int32_t>& dist,
+            std::vector<int32_t>& out, std::vector<int32_t>& lv) {
+    out.clear();
+    lv.clear();
+    out.push_back(start);
+    dist[start] = 0;
+    lv.push_back(0);
+    size_t head = 0;
+    int32_t cur = 0;
+    while (head < out.size()) {
+        int32_t u = out[head];
+        if (dist[u] != cur) {
+            cur = dist[u];
+            lv.push_back((int32_t)head);
+        }
+        ++head;
+        for (int64_t p = g.ptr[u]; p < g.ptr[u + 1]; ++p) {
+            int32_t v = g.adj[p];
+            if (tag[v] == id && dist[v] < 0) {
+                dist[v] = cur + 1;
+                out.push_back(v);
+            }
+        }
+    }
+    lv.push_back((int32_t)out.size());
+    return (int32_t)out.size();
+}
+
+// nested dissection ordering; returns perm (elimination order -> node)
+void nested_dissection(const Graph& g, std::vector<int32_t>& perm) {
+    const int32_t n = g.n;
+    const int32_t LEAF = 24;
+    perm.assign((size_t)n, -1);
+    std::vector<int32_t> tag((size_t)n, 0), dist((size_t)n, -1), bfsout, lv, tmp;
+    struct Task {
+        std::vector<int32_t> nodes;
+        int32_t lo;  // this set occupies perm[lo, lo + nodes.size())
+    };
+    std::vector<Task> stack;
+    {
+        Task t;
+        t.nodes.resize((size_t)n);
+        std::iota(t.nodes.begin(), t.nodes.end(), 0);
+        t.lo = 0;
+        stack.push_back(std::move(t));
+    }
+    int32_t next_id = 1;
+    while (!stack.empty()) {
+        Task t = std::move(stack.back());
+        stack.pop_back();
+        const int32_t sz = (int32_t)t.nodes.size();
+        if (sz == 0) continue;
+        if (sz <= LEAF) {
+            for (int32_t k = 0; k < sz; ++k) perm[t.lo + k] = t.nodes[k];
+            continue;
+        }
+        const int32_t id = next_id++;
+        for (int32_t v : t.nodes) {
+            tag[v] = id;
+            dist[v] = -1;
+        }
+        // connected component of the first node
+        int32_t cnt = bfs(g, t.nodes[0], tag, id, dist, bfsout, lv);
+        if (cnt < sz) {  // disconnected: split off the component, no separator needed
+            Task a, b;
+            a.nodes = bfsout;
+            for (int32_t v : a.nodes) tag[v] = -id;
+            for (int32_t v : t.nodes)
+                if (tag[v] == id) b.nodes.push_back(v);
+            a.lo = t.lo;
+            b.lo = t.lo + (int32_t)a.nodes.size();
+            stack.push_back(std::move(a));
+            stack.push_back(std::move(b));
+            continue;
+        }
+        // pseudo-peripheral start: two more sweeps from the farthest node
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            int32_t far = bfsout.back();
+            for (int32_t v : t.nodes) dist[v] = -1;
+            bfs(g, far, tag, id, dist, bfsout, lv);
+        }
+        int32_t nlev = (int32_t)lv.size() - 1;
+        if (nlev < 3) {  // (nearly) complete graph: no useful separator
+            for (int32_t k = 0; k < sz; ++k) perm[t.lo + k] = t.nodes[k];
+            continue;
+        }
+        // separator = the level whose removal balances the two sides best
+        int32_t best = 1;
+        int64_t bestcost = INT64_MAX;
+        for (int32_t l = 1; l < nlev - 1; ++l) {
+            int64_t a = lv[l], s = lv[l + 1] - lv[l], b = sz - lv[l + 1];
+            int64_t cost = std::llabs(a - b) + 4 * s;  // balance + separator size
+            if (cost < bestcost) {
+                bestcost = cost;
+                best = l;
+            }
+        }
+        Task a, b;
+        a.nodes.assign(bfsout.begin(), bfsout.begin() + lv[best]);
+        b.nodes.assign(bfsout.begin() + lv[best + 1], bfsout.end());
+        int32_t nsep = lv[best + 1] - lv[best];
+        a.lo = t.lo;
+        b.lo = t.lo + (int32_t)a.nodes.size();
+        int32_t seplo = b.lo + (int32_t)b.nodes.size();
+        for (int32_t k = 0; k < nsep; ++k) perm[seplo + k] = bfsout[lv[best] + k];
+        stack.push_back(std::move(a));
+        stack.push_back(std::move(b));
+    }
+}
+
+}  // namespace
+
+int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,
+                     const uint8_t* is_boundary, CholFactor& F, std::string& err) {
+    // ---- reduced numbering -----------------------------------------------------------------------
+    std::vector<int32_t> red((size_t)n_full, -1), full;
+    for (int64_t i = 0; i < n_full; ++i)
+        if (!is_boundary[i]) {
+            red[i] = (int32_t)full.size();
+            full.push_back((int32_t)i);
+        }
+    const int32_t n = (int32_t)full.size();
+    F.n = n;
+    F.perm.clear();
+    F.Lp.assign(1, 0);
+    F.Li.clear();
+    F.Lx.clear();
+    F.dinv.clear();
+    if (n == 0) return 0;
+
+    Graph g;
+    g.n = n;
+    g.ptr.assign((size_t)n + 1, 0);
+    for (int32_t r = 0; r < n; ++r) {
+        int64_t i = full[r];
+        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
+            if (red[col[p]] >= 0 && col[p] != i) g.ptr[r + 1]++;
+    }
+    for (int32_t r = 0; r < n; ++r) g.ptr[r + 1] += g.ptr[r];
+    g.adj.resize((size_t)g.ptr[n]);
+    for (int32_t r = 0; r < n; ++r) {
+        int64_t i = full[r], q = g.ptr[r];
+        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
+            if (red[col[p]] >= 0 && col[p] != i) g.adj[q++] = red[col[p]];
+    }
+
+    std::vector<int32_t> perm;
+    nested_dissection(g, perm);
+    std::vector<int32_t> iperm((size_t)n);
+    for (int32_t k = 0; k < n; ++k) {
+        if (perm[k] < 0) {
+            err = "internal error: incomplete ordering";
+            return ASGFEM_ENUMERIC;
+        }
+        iperm[perm[k]] = k;
+    }
+
+    // ---- permuted upper triangle by columns: C = P A P^T, column k holds rows i <= k ----------------
+    std::vector<int64_t> Cp((size_t)n + 1, 0);
+    for (int32_t k = 0; k < n; ++k) {
+        int64_t i = full[perm[k]];
+        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+            int32_t rj = red[col[p]];
+            if (rj >= 0 && iperm[rj] <= k) Cp[k + 1]++;
+        }
+    }
+    for (int32_t k = 0; k < n; ++k) Cp[k + 1] += Cp[k];
+    std::vector<int32_t> Ci((size_t)Cp[n]);
+    std::vector<double> Cx((size_t)Cp[n]);
+    for (int32_t k = 0; k < n; ++k) {
+        int64_t i = full[perm[k]], q = Cp[k];
+        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+            int32_t rj = red[col[p]];
+            if (rj >= 0 && iperm[rj] <= k) {
+                Ci[q] = iperm[rj];
+                Cx[q] = val[p];  // A symmetric: A[i, j] used as C[j', k]
+                ++q;
+            }
+        }
+    }
+
+    // ---- elimination tree (Liu) ---------------------------------------------------------------------
+    std::vector<int32_t> parent((size_t)n, -1), anc((size_t)n, -1);
+    for (int32_t k = 0; k < n; ++k)
+        for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+            int32_t i = Ci[p];
+            while (i != -1 && i < k) {
+                int32_t nxt = anc[i];
+                anc[i] = k;
+                if (nxt == -1) parent[i] = k;
+                i = nxt;
+            }
+        }
+
+    // ---- row patterns by row-subtree traversal (ereach); pass 1 counts, pass 2 factorises ------------
+    std::vector<int32_t> flag((size_t)n, -1), stack((size_t)n), rowlen((size_t)n, 0);
+    std::vector<int64_t> colcount((size_t)n, 1);  // diagonal
+    auto ereach = [&](int32_t k, int32_t& top) {
+        top = n;
+        flag[k] = k;
+        for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+            int32_t i = Ci[p];
+            if (i > k) continue;
+            int32_t len = 0;
+            for (; flag[i] != k; i = parent[i]) {
+                stack[len++] = i;
+                flag[i] = k;
+            }
+            while (len > 0) stack[--top] = stack[--len];
+        }
+    };
+    int64_t lnz = 0;
+    for (int32_t k = 0; k < n; ++k) {
+        int32_t top;
+        ereach(k, top);
+        rowlen[k] = n - top;
+        lnz += n - top;
+        for (int32_t q = top; q < n; ++q) colcount[stack[q]]++;
+    }
+    // column storage for the numeric phase (diagonal first), row storage for the output
+    std::vector<int64_t> Lcp((size_t)n + 1, 0);
+    for (int32_t j = 0; j < n; ++j) Lcp[j + 1] = Lcp[j] + colcount[j];
+    std::vector<int32_t> Lci;
+    std::vector<double> Lcx;
+    try {
+        Lci.resize((size_t)Lcp[n]);
+        Lcx.resize((size_t)Lcp[n]);
+        F.Lp.assign((size_t)n + 1, 0);
+        for (int32_t k = 0; k < n; ++k) F.Lp[k + 1] = F.Lp[k] + rowlen[k];
+        F.Li.resize((size_t)lnz);
+        F.Lx.resize((size_t)lnz);
+        F.dinv.resize((size_t)n);
+    } catch (const std::bad_alloc&) {
+        err = "out of host memory for the Cholesky factor";
+        return ASGFEM_ENOMEM;
+    }
+    std::vector<int64_t> cnext(Lcp.begin(), Lcp.end() - 1);
+    std::vector<double> x((size_t)n, 0.0);
+    std::fill(flag.begin(), flag.end(), -1);
+    for (int32_t k = 0; k < n; ++k) {
+        int32_t top;
+        ereach(k, top);
+        double d = 0.0;
+        for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+            if (Ci[p] == k)
+                d += Cx[p];
+            else
+                x[Ci[p]] += Cx[p];
+        }
+        int64_t rp = F.Lp[k];
+        for (int32_t q = top; q < n; ++q) {
+            int32_t j = stack[q];
+            double lkj = x[j] / Lcx[Lcp[j]];
+            x[j] = 0.0;
+            for (int64_t p = Lcp[j] + 1; p < cnext[j]; ++p) x[Lci[p]] -= Lcx[p] * lkj;
+            d -= lkj * lkj;
+            int64_t at = cnext[j]++;
+            Lci[at] = k;
+            Lcx[at] = lkj;
+            F.Li[rp] = j;
+            F.Lx[rp] = lkj;
+            ++rp;
+        }
+        if (!(d > 0.0) || !std::isfinite(d)) {
+            err = "K_0 restricted to the interior dofs is not positive definite (pivot " + std::to_string(k) + ")";
+            return ASGFEM_ENUMERIC;
+        }
+        double lkk = std::sqrt(d);
+        int64_t at = cnext[k]++;
+        Lci[at] = k;
+        Lcx[at] = lkk;
+        F.dinv[k] = 1.0 / lkk;
+        // rows of L in the output are sorted by column for coalesced/monotone access
+        // (ereach order is topological, not sorted)
+    }
+    for (int32_t k = 0; k < n; ++k) {
+        int64_t a = F.Lp[k], b = F.Lp[k + 1];
+        // sort (Li, Lx) of the row by column index
+        std::vector<std::pair<int32_t, double>> tmp;
+        tmp.reserve((size_t)(b - a));
+        for (int64_t p = a; p < b; ++p) tmp.push_back({F.Li[p], F.Lx[p]});
+        std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, double>& u, const std::pair<int32_t, double>& v) {
+            return u.first < v.first;
+        });
+        for (int64_t p = a; p < b; ++p) {
+            F.Li[p] = tmp[p - a].first;
+            F.Lx[p] = tmp[p - a].second;
+        }
+    }
+    F.perm.resize((size_t)n);
+    for (int32_t k = 0; k < n; ++k) F.perm[k] = full[perm[k]];
+    return 0;
+}
+
+}  // namespace asgfem

@@ -1,0 +1,184 @@
+// Internal definitions shared by the translation units of libasgfem_cuda.so.
+// Product code: nothing in here may depend on oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/asgfem.h"
+
+namespace asgfem {
+
+// ---- multi-index machinery (index.cpp) ---------------------------------------------------------
+struct MultiIndexSet {
+    int64_t N = 0, M = 0;
+    std::vector<int64_t> mi;     // N x M row-major (mode j = mi[j*M..])
+    std::vector<int64_t> plus;   // M x N column-major as in the ABI: plus[m + M*j], 1-based, 0 absent
+    std::vector<int64_t> minus;
+    void build_neighbours();
+    int64_t maxdeg() const;
+};
+uint64_t hash_mi(const int64_t* v, int64_t M);
+void coupling_weights(int family, int64_t maxdeg, std::vector<double>& gp, std::vector<double>& gm);
+
+// neighbour lists per mode in the summation order of mul! (nu ascending, then direction ascending)
+struct Coupling {
+    std::vector<int32_t> ptr;  // N+1
+    std::vector<int32_t> m;    // direction 1..M (0 is the mean term, not stored)
+    std::vector<int32_t> nu;   // source mode (0-based)
+    std::vector<double> g;
+};
+void build_coupling(const MultiIndexSet& S, int family, Coupling& C);
+
+// ---- sparse Cholesky of the Dirichlet-reduced K_0 (chol.cpp) -----------------------------------
+struct CholFactor {
+    int64_t n = 0;                 // reduced dimension
+    std::vector<int32_t> perm;     // perm[k] = original (full) row id of the k-th eliminated unknown
+    std::vector<int64_t> Lp;       // CSR of L (strictly lower part), rows in elimination order
+    std::vector<int32_t> Li;
+    std::vector<double> Lx;
+    std::vector<double> dinv;      // 1 / L_kk
+};
+// A: full n_full x n_full CSR (rowptr int64, col int32), keep[i] != 0 for interior rows. Returns 0 or ASGFEM_E*.
+int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,
+                     const uint8_t* is_boundary, CholFactor& F, std::string& err);
+
+// ---- device-side plans --------------------------------------------------------------------------
+struct ApplyPlan;    // apply.cu
+struct PrecondPlan;  // sptrsv.cu
+struct EstimatePlan;
+
+}  // namespace asgfem
+
+struct asgfem_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // pattern (CSR, 0-based) and the permutation from the caller's CSC order
+    int64_t n = 0, nnz = 0;
+    int64_t n_owned = -1;  // rows written by apply (multi-GPU); -1 = all
+    std::vector<int64_t> h_rowptr;
+    std::vector<int32_t> h_col;
+    std::vector<int64_t> h_csc_colptr;  // caller's CSC (0-based) for get_pattern / set_stiffness
+    std::vector<int32_t> h_csc_row;
+    std::vector<int64_t> h_csc2csr;     // position in CSR of CSC entry p
+    int64_t* d_rowptr = nullptr;
+    int32_t* d_col = nullptr;
+    int32_t M = -1;          // number of KLE matrices beyond the mean (K_0..K_M)
+    double* d_vals = nullptr;  // (M+1) x nnz, CSR order
+    std::vector<uint8_t> h_bmask;
+    uint8_t* d_bmask = nullptr;
+    std::vector<int64_t> h_bdofs;
+
+    // stochastic discretisation
+    int family = 0;
+    asgfem::MultiIndexSet mis;
+    asgfem::Coupling coup;
+    std::vector<double> gp, gm;
+    int32_t* d_cptr = nullptr;
+    int32_t* d_cm = nullptr;
+    int32_t* d_cnu = nullptr;
+    double* d_cg = nullptr;
+    int64_t N = 0, ld = 0;  // device vectors are row-major n x ld, ld = N rounded up to a multiple of 16
+
+    // vectors
+    std::vector<double*> slots;
+    double* d_stage = nullptr;  // staging for layout conversion
+    size_t stage_bytes = 0;
+    double* d_partial = nullptr;  // reduction scratch
+    size_t partial_elems = 0;
+
+    // mesh / space / coefficient (device assembly + estimator)
+    int64_t nnodes = 0, ncells = 0;
+    std::vector<double> h_coords;
+    std::vector<int32_t> h_cellnodes;  // 0-based, 3 x ncells
+    double* d_coords = nullptr;
+    int32_t* d_cellnodes = nullptr;
+    int32_t order = 0, ndofs4cell = 0;
+    int64_t ndofs_space = 0;
+    std::vector<int32_t> h_celldofs;  // 0-based
+    int32_t* d_celldofs = nullptr;
+    int64_t maxm = 0;
+    double mean = 0;
+    std::vector<double> h_decay;
+    std::vector<int64_t> h_b1, h_b2;
+    double* d_decay = nullptr;
+    int32_t* d_b1 = nullptr;
+    int32_t* d_b2 = nullptr;
+
+    // kernels
+    int apply_variant = 0;
+    double last_apply_ms = 0;
+    asgfem::ApplyPlan* plan = nullptr;
+    asgfem::PrecondPlan* precond = nullptr;
+};
+
+namespace asgfem {
+
+inline int fail(asgfem_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define ASG_CUDA(ctx, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            return asgfem::fail((ctx), _e == cudaErrorMemoryAllocation ? ASGFEM_ENOMEM : ASGFEM_ECUDA,  \
+                                std::string(#call) + ": " + cudaGetErrorString(_e));                    \
+        }                                                                                               \
+    } while (0)
+
+#define ASG_CHECK(ctx, cond, code, msg)                       \
+    do {                                                      \
+        if (!(cond)) return asgfem::fail((ctx), (code), (msg)); \
+    } while (0)
+
+template <class T>
+int dev_upload(asgfem_ctx* ctx, T** dptr, const std::vector<T>& h) {
+    if (*dptr) {
+        cudaFree(*dptr);
+        *dptr = nullptr;
+    }
+    size_t bytes = sizeof(T) * (h.empty() ? 1 : h.size());
+    ASG_CUDA(ctx, cudaMalloc((void**)dptr, bytes));
+    if (!h.empty()) ASG_CUDA(ctx, cudaMemcpyAsync(*dptr, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// apply.cu
+int apply_build_plan(asgfem_ctx* ctx);
+void apply_free_plan(asgfem_ctx* ctx);
+int apply_launch(asgfem_ctx* ctx, const double* x, double* y);
+// vecops.cu
+int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
+int vec_to_host_layout(asgfem_ctx* ctx, const double* dvec, double* host);
+int vec_dot(asgfem_ctx* ctx, const double* a, const double* b, int64_t nrows, double* out);
+int vec_fill_random(asgfem_ctx* ctx, double* d, uint64_t seed);
+int vec_axpy(asgfem_ctx* ctx, double alpha, const double* x, double* y);
+int vec_xpay(asgfem_ctx* ctx, const double* x, double beta, double* y);  // y = x + beta*y
+int vec_mask_rows(asgfem_ctx* ctx, double* x);                            // zero boundary rows
+int vec_pack_rows(asgfem_ctx* ctx, const double* v, int64_t nrows, const int64_t* d_rows, double* buf);
+int vec_unpack_rows(asgfem_ctx* ctx, double* v, int64_t nrows, const int64_t* d_rows, const double* buf);
+// sptrsv.cu
+int precond_setup(asgfem_ctx* ctx);
+void precond_free(asgfem_ctx* ctx);
+int precond_apply(asgfem_ctx* ctx, const double* r, double* z);
+// pcg.cu
+int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, double rtol, int64_t itmax,
+              asgfem_stats* stats);
+// assemble.cu
+int assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w);
+// estimate.cu
+int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
+                            int32_t nq, const double* xref, const double* w, const double* f_at_qp, int32_t nqf,
+                            const double* sf, const double* wf, double* eta4cell, double* eta4modes);
+
+}  // namespace asgfem

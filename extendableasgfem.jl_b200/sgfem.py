@@ -1,0 +1,148 @@
+"""Host-side mirror of the reference's operator interface for the solve path, same names and argument meaning:
+
+* TensorizedBasis        src/tensorizedbasis.jl:28-34 (multi_indices, nmodes, G)
+* SGFEVector             src/sgfevector.jl:18-27 (flat `entries`, block view per mode via sol[j])
+* solve_primal           solve_primal!(sol, A0, Am, b0, G, nmodes, bfac; atol, rtol)
+                         src/modelproblems/solvers_poisson_primal.jl:130-169
+* solve                  solve!(PoissonProblemPrimal, sol, C; rhs, ...)   src/modelproblems/poisson_primal.jl:38-81
+* mul / ldiv             LinearAlgebra.mul! (:86-124) / ldiv! (:46-78) on host vectors
+* estimate               estimate(PoissonProblemPrimal, sol, C; rhs, bonus_quadorder, tail_extension)
+                         src/estimate.jl:260-418
+
+All arithmetic runs in libasgfem_cuda.so; nothing here computes on the CPU except index bookkeeping.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import context as _ctx
+from . import grids as _grids
+from . import multiindices as _mi
+
+LegendrePolynomials = _ctx.LEGENDRE
+HermitePolynomials = _ctx.HERMITE
+
+
+class TensorizedBasis:
+    def __init__(self, OBT, multi_indices, ctx: _ctx.Context | None = None):
+        self.OBT = OBT
+        self.multi_indices = [list(m) for m in multi_indices]
+        _mi.prepare_multi_indices(self.multi_indices)
+        self.nmodes = len(self.multi_indices)
+        self.ctx = ctx or _ctx.Context()
+        self.ctx.set_multiindices(OBT, np.array(self.multi_indices, dtype=np.int64))
+        self._G = None
+
+    def maxlength_multiindices(self):
+        return len(self.multi_indices[0])
+
+    @property
+    def G(self):
+        """(M*N) x N CSC exactly like TensorizedBasis.G.cscmatrix (built by the native library)."""
+        if self._G is None:
+            colptr, rowval, nzval = self.ctx.coupling_csc()
+            M = self.maxlength_multiindices()
+            self._G = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(M * self.nmodes, self.nmodes))
+        return self._G
+
+    def get_coupling_coefficient(self, m, j, k):  # 1-based like tensorizedbasis.jl:74
+        return self.G[(m - 1) * self.nmodes + j - 1, k - 1]
+
+
+class SGFEVector:
+    def __init__(self, FES: _grids.FESpace, TB: TensorizedBasis):
+        self.FES_space = FES
+        self.TB = TB
+        self.entries = np.zeros(FES.ndofs * TB.nmodes)
+
+    def __getitem__(self, j):  # 1-based mode id -> block view (sgfevector.jl:118)
+        n = self.FES_space.ndofs
+        return self.entries[(j - 1) * n: j * n]
+
+    def __len__(self):
+        return len(self.entries)
+
+
+def _install_matrices(ctx, A0, Am):
+    """A0, Am: scipy sparse matrices as a Julia caller holds FEMatrix.entries.cscmatrix."""
+    mats = [sp.csc_matrix(A0)] + [sp.csc_matrix(A) for A in Am]
+    n = mats[0].shape[0]
+    union = mats[0].copy()
+    union.data = np.ones_like(union.data)
+    for A in mats[1:]:
+        B = A.copy()
+        B.data = np.ones_like(B.data)
+        union = union + B
+    union = sp.csc_matrix(union)
+    union.sort_indices()
+    ctx.set_pattern_csc(n, union.indptr.astype(np.int64) + 1, union.indices.astype(np.int64) + 1)
+    ctx.set_num_stiffness(len(Am))
+    for m, A in enumerate(mats):
+        A.sort_indices()
+        ctx.set_stiffness_csc(m, A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1, A.data)
+
+
+def solve_primal(sol: SGFEVector, A0, Am, b0, G=None, nmodes=None, bfac=1, atol=1.0e-14, rtol=1.0e-14,
+                 itmax=0, return_stats=False):
+    """Drop-in for solve_primal!: overwrites sol.entries, returns bdofs (1-based, first-occurrence order)."""
+    ctx = sol.TB.ctx
+    _install_matrices(ctx, A0, Am)
+    bdofs = sol.FES_space.bdofs + 1
+    ctx.set_bdofs(bdofs)
+    stats = ctx.solve_primal_host(sol.entries, np.asarray(b0, dtype=np.float64), atol, rtol, itmax)
+    return (bdofs, stats) if return_stats else bdofs
+
+
+def setup_device_problem(sol: SGFEVector, C, bonus_quadorder_a=2):
+    """Device-side part of solve!: mesh/space/coefficient upload and assembly of K_0..K_M on the device."""
+    ctx, FES = sol.TB.ctx, sol.FES_space
+    g = FES.grid
+    ctx.set_mesh(g.coords, g.cellnodes + 1)
+    ctx.set_space(FES.order, FES.ndofs, FES.celldofs + 1)
+    ctx.set_coefficient_cosinus(C.mean_value, C.decay_factors, C.b1, C.b2)
+    xref, w = _grids.quadrature_rule(2 * (FES.order - 1) + bonus_quadorder_a)
+    ctx.assemble_stiffness(sol.TB.maxlength_multiindices(), xref, w)
+    ctx.set_bdofs(FES.bdofs + 1)
+
+
+def solve(sol: SGFEVector, C, rhs=None, bonus_quadorder_a=2, bonus_quadorder_f=0, atol=1.0e-14, rtol=1.0e-14,
+          itmax=0, return_stats=False):
+    """solve!(PoissonProblemPrimal, sol, C; rhs, ...) with K_m assembled on the device."""
+    setup_device_problem(sol, C, bonus_quadorder_a)
+    b0 = sol.FES_space.rhs(rhs, bonus_quadorder_f)
+    stats = sol.TB.ctx.solve_primal_host(sol.entries, b0, atol, rtol, itmax)
+    bdofs = sol.FES_space.bdofs + 1
+    return (bdofs, stats) if return_stats else bdofs
+
+
+def mul(ctx: _ctx.Context, x):
+    """mul!(Ax, S, x) on host vectors in the reference layout."""
+    return ctx.apply_host(x)
+
+
+def ldiv(ctx: _ctx.Context, b):
+    """ldiv!(y, P, b) on host vectors in the reference layout."""
+    return ctx.precond_apply_host(b)
+
+
+def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10, 2)):
+    """Returns (eta4modes, eta4cell, multi_indices_extended) like estimate.jl:417.  Requires the device problem
+    (setup_device_problem / solve) so that mesh, space and coefficient are resident."""
+    ctx, FES = sol.TB.ctx, sol.FES_space
+    g = FES.grid
+    mi_ext = _mi.add_boundary_modes(sol.TB.multi_indices, tail_extension=tail_extension)
+    quadorder = 2 * (FES.order - 1) + bonus_quadorder
+    xref, w = _grids.quadrature_rule(quadorder)
+    sf, wf = _grids.quadrature_rule_1d(quadorder)
+    fq = None
+    if rhs is not None:
+        c = g.cellnodes
+        x1, x2, x3 = g.coords[c[:, 0]], g.coords[c[:, 1]], g.coords[c[:, 2]]
+        xq = x1[:, None, :] + xref[None, :, 0:1] * (x2 - x1)[:, None, :] + xref[None, :, 1:2] * (x3 - x1)[:, None, :]
+        fq = rhs(xq[:, :, 0], xq[:, :, 1])  # (ncells, nq) C-order == nq x ncells column-major
+    ctx.vec_alloc(max(1, 1))
+    ctx.vec_upload(0, sol.entries)
+    eta4modes, eta4cell = ctx.estimate_poisson_primal(0, np.array(mi_ext, dtype=np.int64), xref, w, sf, wf,
+                                                      g.ncells, fq)
+    return eta4modes, eta4cell, mi_ext

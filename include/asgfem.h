@@ -1,0 +1,187 @@
+/* libasgfem_cuda.so - C ABI of the B200-native SGFE solve hot path.
+ *
+ * Drop-in boundary for ExtendableASGFEM.jl v1.0.1 (pure Julia, no FFI of its own): every entry
+ * point below replaces the Julia seam cited next to it (paths relative to the reference repo).
+ * The Julia-side binding a maintainer would add (ccall stubs overriding solve_primal!/mul!/ldiv!/
+ * estimate) is shown in INTEGRATION.md and shipped as julia/ASGFEMCuda.jl.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative ASGFEM_E* code otherwise; nothing throws or
+ *    aborts across the boundary; asgfem_last_error(ctx) holds the message of the last failure
+ *  - host pointers are borrowed for the duration of the call only; the library owns all device memory
+ *  - indices cross the boundary exactly as Julia holds them: 1-based, Int64 (Int32 where the
+ *    reference stores Int32, i.e. ExtendableGrid{Float64,Int32} adjacencies)
+ *  - vectors cross the boundary in the reference layout: flat length n*N, block mu contiguous
+ *    (column-major n x N, src/sgfevector.jl:97-101); the device layout is private
+ *  - all calls are synchronous (they return after the stream has drained); a context is not
+ *    thread-safe; one context per (GPU, refinement level)
+ *  - there is NO CPU fallback: every compute entry point fails with ASGFEM_ECUDA if no device is usable
+ */
+#ifndef ASGFEM_H
+#define ASGFEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct asgfem_ctx asgfem_ctx;
+
+enum {
+    ASGFEM_OK = 0,
+    ASGFEM_EINVAL = -1,  /* bad argument / inconsistent sizes / index out of range */
+    ASGFEM_ESTATE = -2,  /* call order violated (e.g. apply before set_multiindices)  */
+    ASGFEM_ECUDA = -3,   /* CUDA runtime error (message in asgfem_last_error)         */
+    ASGFEM_ENOMEM = -4,  /* host or device allocation failed                          */
+    ASGFEM_ENUMERIC = -5 /* factorisation broke down (matrix not SPD on interior dofs) */
+};
+
+enum { ASGFEM_LEGENDRE = 0, ASGFEM_HERMITE = 1 }; /* src/orthogonal_polynomials/{Legendre_uniform,Hermite_normal}.jl */
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+int asgfem_create(asgfem_ctx** out, int device);
+int asgfem_destroy(asgfem_ctx* ctx);
+const char* asgfem_last_error(const asgfem_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+const char* asgfem_version(void);
+
+/* ---- (a2) recurrence coefficients --------------------------------------------------------------
+ * g+(k) = 1/b, g-(k) = c/b of normalise_recurrence_coefficients(OBT, k), k = 0..maxdeg
+ * (src/orthogonal_polynomials/orthogonal_polynomials.jl:211-221 as used at src/tensorizedbasis.jl:202-211). */
+int asgfem_coupling_weights(int32_t family, int64_t maxdeg, double* gplus, double* gminus);
+
+/* ---- (a3, a4) multi-indices, coupling matrix G, neighbour tables -------------------------------
+ * mi: M x N column-major (mode j = mi[j*M .. j*M+M-1]), already padded to equal length
+ * (prepare_multi_indices!, src/mopcontrol.jl:29-37).  Replaces get_tensor_multiplication_with_ym
+ * (src/tensorizedbasis.jl:193-218) and get_neighbours (src/estimate.jl:1-22). */
+int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t N, int64_t M, const int64_t* mi);
+int asgfem_get_coupling_nnz(asgfem_ctx* ctx, int64_t* nnz);
+/* G as the flushed (M*N) x N CSC of TensorizedBasis.G: colptr[N+1], rowval[nnz], nzval[nnz], 1-based, rows sorted */
+int asgfem_get_coupling_csc(asgfem_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval);
+/* PLUS/MINUS as M x N column-major Int64, 1-based mode ids, 0 = absent */
+int asgfem_get_neighbours(asgfem_ctx* ctx, int64_t* plus, int64_t* minus);
+
+/* ---- (a10, a13) host index machinery (no context, integer only) -------------------------------
+ * add_boundary_modes (src/mopcontrol.jl:60-132) incl. its quirks, without the sleep(1) of :74.
+ * Call with out == NULL to query N_ext / M_ext; out is M_ext x N_ext column-major. */
+int asgfem_add_boundary_modes(int64_t N, int64_t M, const int64_t* mi, int64_t p_extension, int64_t tail1,
+                              int64_t tail2, int64_t* N_ext, int64_t* M_ext, int64_t* out, int64_t out_capacity);
+/* classify_modes (src/mopcontrol.jl:168-241): cls[j] = 0 inactive_else, 1 inactive_bnd, 2 inactive_bnd2,
+ * 3 active_bnd, 4 active_int; the first N_active modes of mi_ext are the active set (scripts/poisson.jl:341) */
+int asgfem_classify_modes(int64_t N_ext, int64_t M, const int64_t* mi_ext, int64_t N_active, int32_t* cls);
+
+/* ---- (a6) stiffness matrices K_0..K_M in one shared pattern ------------------------------------
+ * Host-assembled path (parity with the Julia FEMatrix objects of src/modelproblems/poisson_primal.jl:56-63):
+ * pattern = Julia CSC (colptr[n+1], rowval[nnz]) 1-based, structurally symmetric; nzval on that pattern.
+ * set_stiffness_csc accepts a matrix with its own (sub-)pattern, e.g. when ExtendableSparse dropped exact zeros. */
+int asgfem_set_pattern_csc(asgfem_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval);
+int asgfem_set_num_stiffness(asgfem_ctx* ctx, int32_t M); /* allocates K_0..K_M (zero) */
+int asgfem_set_stiffness(asgfem_ctx* ctx, int32_t m, const double* nzval);
+int asgfem_set_stiffness_csc(asgfem_ctx* ctx, int32_t m, const int64_t* colptr, const int64_t* rowval,
+                             const double* nzval);
+int asgfem_get_stiffness(asgfem_ctx* ctx, int32_t m, double* nzval); /* on the shared pattern (CSC order) */
+int asgfem_get_pattern_nnz(asgfem_ctx* ctx, int64_t* nnz);
+int asgfem_get_pattern_csc(asgfem_ctx* ctx, int64_t* colptr, int64_t* rowval);
+/* boundary dofs (1-based) as returned by solve_primal! (src/modelproblems/solvers_poisson_primal.jl:136-142) */
+int asgfem_set_bdofs(asgfem_ctx* ctx, int64_t nb, const int64_t* bdofs);
+
+/* ---- (a5, a6) device assembly from the KLE modes -----------------------------------------------
+ * Mesh and space as ExtendableGrids/ExtendableFEMBase hold them: coords 2 x nnodes (Float64),
+ * cellnodes 3 x ncells (Int32, 1-based), celldofs ndofs4cell x ncells (Int32, 1-based) = FES[CellDofs].
+ * order = 1 (H1Pk{1,2,1}) or 2 (H1Pk{1,2,2}). */
+int asgfem_set_mesh(asgfem_ctx* ctx, int64_t nnodes, int64_t ncells, const double* coords, const int32_t* cellnodes);
+int asgfem_set_space(asgfem_ctx* ctx, int32_t order, int64_t ndofs, int32_t ndofs4cell, const int32_t* celldofs);
+/* StochasticCoefficientCosinus fields (src/coefficients/cosinus.jl:11-17): a_0 = mean,
+ * a_m(x) = decay_factors[m] cos(pi b1[m] x1) cos(pi b2[m] x2) (get_am!, cosinus.jl:58-65) */
+int asgfem_set_coefficient_cosinus(asgfem_ctx* ctx, int64_t maxm, double mean, const double* decay_factors,
+                                   const int64_t* b1, const int64_t* b2);
+/* K_m[i,j] = sum_T |T| sum_q w[q] a_m(x_q) grad(phi_j).grad(phi_i), m = 0..M, with the caller's quadrature
+ * rule (xref 2 x nq reference coordinates, w sums to 1) - the arithmetic of
+ * BilinearOperator(get_am_x(m,C),[grad(1)],[grad(1)]) (src/coefficients/coefficients.jl:147-153).
+ * Builds the shared pattern from celldofs if none was set. */
+int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w);
+
+/* ---- (a1) SGFEVector storage --------------------------------------------------------------------
+ * Device-resident n x N fp64 blocks addressed by slot id (src/sgfevector.jl:18-27, entries 86-106).
+ * Slots 0..nslots-1 are user slots; the PCG driver allocates its own work vectors. */
+int asgfem_vec_alloc(asgfem_ctx* ctx, int32_t nslots);
+int asgfem_vec_upload(asgfem_ctx* ctx, int32_t slot, const double* host);   /* host: n*N, reference layout */
+int asgfem_vec_download(asgfem_ctx* ctx, int32_t slot, double* host);
+int asgfem_vec_zero(asgfem_ctx* ctx, int32_t slot);
+/* x[i + n*mu] = 2*u01(splitmix64(seed ^ (i + n*mu))) - 1, generated on the device (bench inputs) */
+int asgfem_vec_fill_random(asgfem_ctx* ctx, int32_t slot, uint64_t seed);
+int asgfem_vec_dot(asgfem_ctx* ctx, int32_t slot_a, int32_t slot_b, double* out);
+int asgfem_vec_axpy(asgfem_ctx* ctx, double alpha, int32_t slot_x, int32_t slot_y); /* y += alpha x */
+
+/* ---- (a7) operator ------------------------------------------------------------------------------
+ * Y = sum_m (G_m (x) K_m) X with the rows of bdofs zeroed: LinearAlgebra.mul!(Ax, S::MySystemPrimal, x)
+ * (src/modelproblems/solvers_poisson_primal.jl:86-124).  Columns at bdofs take part exactly as in the
+ * reference (X is not masked). */
+int asgfem_apply(asgfem_ctx* ctx, int32_t slot_x, int32_t slot_y);
+int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax); /* host vectors, reference layout */
+/* selects the kernel: 0 = automatic, 1 = reference-order gather kernel, 2 = tiled shared-memory kernel */
+int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant);
+/* duration of the last asgfem_apply kernel(s) in milliseconds, from CUDA events on the library's stream */
+int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms);
+
+/* ---- (a8) mean-based preconditioner -------------------------------------------------------------
+ * setup: MyPreconditionerPrimal (solvers_poisson_primal.jl:30-44): K_0 with the boundary dofs pinned,
+ * factorised once on the host (sparse Cholesky, nested dissection), uploaded as level-scheduled
+ * triangular factors.  apply: ldiv!(y, P, b) (:46-78) for all N blocks at once; y may alias b.
+ * Boundary rows of the result are exactly 0 (the reference leaves O(1e-60) there). */
+int asgfem_precond_setup(asgfem_ctx* ctx);
+int asgfem_precond_apply(asgfem_ctx* ctx, int32_t slot_r, int32_t slot_z);
+int asgfem_precond_apply_host(asgfem_ctx* ctx, const double* b, double* y);
+
+/* ---- (a9) Krylov driver -------------------------------------------------------------------------
+ * solve_primal! (solvers_poisson_primal.jl:130-169) with PCG in place of Krylov.gmres:
+ * rhs b[:,1] = x0[:,1] + b0 ... exactly lines 149-155 (b = deepcopy(sol); b[1] += b0; b[m][bdofs] = 0),
+ * warm start from the slot content, stop when sqrt(r.z) <= atol + rtol*sqrt(r0.z0). */
+typedef struct asgfem_stats {
+    int64_t niter;
+    int32_t solved;
+    int32_t _pad;
+    double rz0;          /* sqrt(r0.z0) */
+    double rzk;          /* sqrt(rk.zk) at exit */
+    double residual;     /* ||A x - b||_2 after the solve (the reference's "solver residual", :165-167) */
+    double ms_setup;     /* rhs + initial residual */
+    double ms_iterations;
+    double ms_apply;     /* accumulated operator time   */
+    double ms_precond;   /* accumulated preconditioner time */
+} asgfem_stats;
+int asgfem_pcg(asgfem_ctx* ctx, const double* b0, int32_t slot_x, double atol, double rtol, int64_t itmax,
+               asgfem_stats* stats);
+/* whole seam on host vectors: sol (n*N, in: warm start, out: solution), b0 (n) */
+int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const double* b0, double atol, double rtol,
+                             int64_t itmax, asgfem_stats* stats);
+
+/* ---- (a11, a12) residual error estimator -------------------------------------------------------
+ * estimate(::Type{PoissonProblemPrimal}, sol, C; rhs, bonus_quadorder, tail_extension) (src/estimate.jl:260-418)
+ * for the solution in slot_u.  Needs set_mesh/set_space/set_coefficient_cosinus and the ACTIVE multi-indices
+ * (set_multiindices).  mi_ext: M_ext x N_ext column-major extended set (active modes first,
+ * asgfem_add_boundary_modes).  Cell rule (xref 2 x nq, w) and face rule (sf nqf points on [0,1], wf) are
+ * the caller's QuadratureRule tables of order 2(order-1)+bonus_quadorder (:286-287); f_at_qp is the rhs at the
+ * cell quadrature points (nq x ncells column-major; NULL = f == 1).  Outputs: eta4cell ncells x N_ext
+ * column-major, eta4modes N_ext (the Julia return values of :417). */
+int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,
+                                   const int64_t* mi_ext, int32_t nq, const double* xref, const double* w,
+                                   const double* f_at_qp, int32_t nqf, const double* sf, const double* wf,
+                                   double* eta4cell, double* eta4modes);
+
+/* ---- (e) row-sharded multi-GPU operation --------------------------------------------------------
+ * One context per rank/GPU.  The context holds the LOCAL rows of every K_m with local column ids:
+ * columns 0..n_owned-1 are the owned dofs, n_owned..n_local-1 the halo dofs (owned by neighbours).
+ * Vectors have n_local rows; only owned rows are written by apply.  The host layer (torch.distributed /
+ * NCCL) exchanges halo rows between the pack/unpack calls and all-reduces the partial dots. */
+int asgfem_set_owned_rows(asgfem_ctx* ctx, int64_t n_owned);
+/* device pointer to the private (row-major n_local x ldN) storage of a slot, and its leading dimension */
+int asgfem_vec_device_ptr(asgfem_ctx* ctx, int32_t slot, void** dptr, int64_t* ld);
+/* gather rows[0..nrows) (1-based local ids) of a slot into a dense device buffer (nrows x N) / scatter back */
+int asgfem_pack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t* rows, void* dbuf);
+int asgfem_unpack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t* rows, const void* dbuf);
+int asgfem_vec_dot_owned(asgfem_ctx* ctx, int32_t slot_a, int32_t slot_b, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASGFEM_H */
