@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the SGFE operator hot path (BASELINE.json metric: "SGFE matvec GDoF/s (dofs x modes)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N = 1 workload (BASELINE.json configs[3]): synthetic 1024 x 1024 structured P1 mesh (n = 1,048,576 dofs),
+cosinus KLE with M = 20 terms assembled on the device, first 2000 graded-lex Legendre multi-indices.
+One step = one application  Y = sum_m (G_m (x) K_m) X  to a device-resident n x N fp64 block.
+N > 1: weak scaling - every rank owns a 1024 x 1024 strip of a 1024 x (1024 N) mesh, halo rows are exchanged
+with torch.distributed (NCCL) every step, no other collective on the data path.
+
+`--impl reference` times the reference algorithm (oracle/cpu_ref.c, a C restatement of mul! - Julia is not
+installed in this image) on the host cores, on a bounded column sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX = 1024
+N_MODES = 2000
+M_KLE = 20
+SEED = 20240
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(n, N, nnz, M):
+    """read X + write Y + K values + CSR pattern."""
+    return 8 * n * N + 8 * n * N + 8 * nnz * (M + 1) + 4 * nnz + 4 * (n + 1)
+
+
+def build_local_problem(A, rank, world):
+    """Returns (ctx, n_owned, n_local, send/recv row lists) for the strip owned by `rank`."""
+    ny_tot = NX * world
+    y_lo, y_hi = rank * NX, (rank + 1) * NX  # owned node rows [y_lo, y_hi)
+    ext_lo, ext_hi = max(y_lo - 1, 0), min(y_hi + 1, ny_tot)
+    h = 1.0 / (ny_tot - 1)
+    g = A.structured_unitsquare(NX, ext_hi - ext_lo, 0.0, 1.0, ext_lo * h, (ext_hi - 1) * h)
+    n_ext = g.nnodes
+    # renumber: owned rows first, then the lower halo row, then the upper halo row
+    rows = np.arange(ext_lo, ext_hi)
+    owned = (rows >= y_lo) & (rows < y_hi)
+    order = np.concatenate([np.where(owned)[0], np.where(rows < y_lo)[0], np.where(rows >= y_hi)[0]])
+    node_rows = np.arange(n_ext).reshape(len(rows), NX)
+    new_of_old = np.empty(n_ext, dtype=np.int64)
+    new_of_old[node_rows[order].reshape(-1)] = np.arange(n_ext)
+    coords = np.empty_like(g.coords)
+    coords[new_of_old] = g.coords
+    grid = A.Grid(coords, new_of_old[g.cellnodes], new_of_old[g.bfacenodes])
+    fes = A.FESpace(grid, 1)
+    n_owned = NX * NX
+    # physical Dirichlet boundary only (the cut lines of the strip are interior)
+    xb = grid.coords
+    on_bnd = (np.abs(xb[:, 0]) < 1e-14) | (np.abs(xb[:, 0] - 1) < 1e-14) | (np.abs(xb[:, 1]) < 1e-14) | \
+             (np.abs(xb[:, 1] - 1) < 1e-14)
+    bdofs = np.where(on_bnd)[0]
+    modes = A.graded_lex_multiindices(M_KLE, N_MODES)
+    ctx = A.Context(int(os.environ.get("LOCAL_RANK", 0)))
+    ctx.set_multiindices(A.LEGENDRE, np.array(modes, dtype=np.int64))
+    Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=M_KLE)
+    ctx.set_mesh(grid.coords, grid.cellnodes + 1)
+    ctx.set_space(1, fes.ndofs, fes.celldofs + 1)
+    ctx.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
+    xref, w = A.quadrature_rule(2)
+    ctx.assemble_stiffness(M_KLE, xref, w)
+    ctx.set_bdofs(bdofs + 1)
+    if world > 1:
+        ctx.set_owned_rows(n_owned)
+    halo = {}
+    if y_lo > 0:  # lower neighbour: send my first owned row, receive its last owned row into my lower halo
+        halo[rank - 1] = (np.arange(0, NX) + 1, n_owned + np.arange(0, NX) + 1)
+    if y_hi < ny_tot:
+        off = n_owned + (NX if y_lo > 0 else 0)
+        halo[rank + 1] = (np.arange(n_owned - NX, n_owned) + 1, off + np.arange(0, NX) + 1)
+    return ctx, fes, n_owned, halo
+
+
+def run_gpu(args):
+    import torch
+
+    import asgfem_b200 as A
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t_setup = time.time()
+    ctx, fes, n_owned, halo = build_local_problem(A, rank, world)
+    n_local = fes.ndofs
+    ctx.vec_alloc(2)
+    ctx.vec_fill_random(0, SEED + rank)
+    ctx.set_apply_variant(args.variant)
+    nnz = len(ctx.pattern_csc()[1])
+    t_setup = time.time() - t_setup
+
+    bufs = {}
+    if world > 1:
+        for nb in halo:
+            bufs[nb] = (torch.empty(NX * N_MODES, dtype=torch.float64, device="cuda"),
+                        torch.empty(NX * N_MODES, dtype=torch.float64, device="cuda"))
+
+    def exchange():
+        if world == 1:
+            return
+        ops = []
+        for nb, (send_rows, recv_rows) in halo.items():
+            sb, rb = bufs[nb]
+            ctx.pack_rows(0, send_rows, sb.data_ptr())
+            ops.append(dist.P2POp(dist.isend, sb, nb))
+            ops.append(dist.P2POp(dist.irecv, rb, nb))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        torch.cuda.synchronize()
+        for nb, (send_rows, recv_rows) in halo.items():
+            ctx.unpack_rows(0, recv_rows, bufs[nb][1].data_ptr())
+
+    def step():
+        exchange()
+        ctx.apply(0, 1)
+        return ctx.last_apply_ms()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    kernel_ms = []
+    for _ in range(args.steps):
+        kernel_ms.append(step())
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    # the library launches on its own stream and returns after draining it, so the wall clock between two device
+    # synchronisations bounds the device time; kernel_ms are CUDA-event times on the launching stream
+    step_ms = wall_ms / args.steps
+    if dist:
+        t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    dofmodes = n_owned * N_MODES * world
+    value = dofmodes / (step_ms * 1e-3) / 1e9
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kms = float(np.mean(kernel_ms))
+        bytes_alg = algorithmic_bytes(n_owned, N_MODES, nnz, M_KLE)
+        achieved = bytes_alg / (kms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "apply_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        out = {
+            "metric": "SGFE matvec GDoF/s (dofs x modes)", "value": round(value, 3), "unit": "GDoF/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[3]: synthetic 1024x1024 P1 mesh (1,048,576 dofs) x 2000 graded-lex "
+                                   "Legendre multi-indices, M=20 cosinus KLE, K_m assembled on device"
+                                   + (f"; weak scaling: one such strip per rank of a 1024x{1024 * world} mesh, "
+                                      "halo rows exchanged per step (NCCL send/recv)" if world > 1 else ""),
+                       "n_dofs_per_gpu": n_owned, "n_multiindices": N_MODES, "kle_terms": M_KLE, "nnz": nnz,
+                       "kernel_variant": args.variant or "auto",
+                       "l2_policy": "inputs (16.8 GB per vector) far larger than the 126 MB L2; no flush needed",
+                       "setup_s": round(t_setup, 2)},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": round(kms, 4), "algorithmic_bytes": bytes_alg,
+                         "flops": 2 * nnz * (N_MODES + 2 * 5266)},
+            "gpu_launches": args.steps * (1 + (2 * len(halo) if world > 1 else 0)),
+            "clocks": clocks,
+        }
+    # ---- end-to-end leg through the host-buffer seam (mul! on host vectors), N = 1 only ------------------
+    if rank == 0 and world == 1 and not args.no_e2e:
+        try:
+            nN = n_local * N_MODES
+            xh = torch.empty(nN, dtype=torch.float64).pin_memory()
+            yh = torch.empty(nN, dtype=torch.float64).pin_memory()
+            xh.uniform_(-1, 1)
+            ctx.apply_host_ptr(xh.data_ptr(), yh.data_ptr())  # warm-up (allocates staging)
+            ke = max(1, min(args.steps, 2))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                ctx.apply_host_ptr(xh.data_ptr(), yh.data_ptr())
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0) / ke
+            out["e2e"] = {"value": round(nN / te / 1e9, 3), "unit": "GDoF/s", "h2d_bytes_per_step": 8 * nN,
+                          "d2h_bytes_per_step": 8 * nN, "ms_per_step": round(te * 1e3, 2), "steps": ke,
+                          "path": "asgfem_apply_host (mul! seam) with pinned host vectors in the reference layout"}
+            del xh, yh
+        except Exception as e:  # pragma: no cover
+            out["e2e"] = {"value": None, "unit": "GDoF/s", "error": str(e)[:200]}
+    elif rank == 0:
+        out["e2e"] = {"value": None, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                      "note": "end-to-end leg is measured at N=1 only"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_reference(A, ctx, fes, budget_s=15.0)
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle/cpu_ref.c) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(A, ctx, fes, budget_s=15.0, steps=1, warmup=0):
+    """Times oracle/cpu_ref.c (C restatement of mul!, N + nnz(G) CSC sweeps) on a column sample of the workload.
+    K_m values come from the device assembly (or are assembled here by a throw-away context)."""
+    lib_path = os.path.join(ROOT, "oracle", "libcpu_ref.so")
+    lib = C.CDLL(lib_path)
+    nthreads = os.cpu_count() or 1
+    n = fes.ndofs
+    colptr, rowval = ctx.pattern_csc()
+    colptr = np.ascontiguousarray(colptr - 1, dtype=np.int64)
+    rowval = np.ascontiguousarray(rowval - 1, dtype=np.int32)
+    nnz = len(rowval)
+    vals = np.empty((M_KLE + 1, nnz))
+    for m in range(M_KLE + 1):
+        vals[m] = ctx.get_stiffness(m)
+    from oracle import multiindices as omi
+    from oracle import polynomials as opoly
+    full = omi.graded_lex_multiindices(M_KLE, N_MODES)
+    PLf, MNf = omi.get_neighbours(full)
+    sweeps_full = N_MODES + int((PLf > 0).sum() + (MNf > 0).sum())
+
+    def coupling(Ns):
+        modes = full[:Ns]
+        PL, MN = omi.get_neighbours(modes)
+        gp = [opoly.coupling_weights(opoly.LEGENDRE, k) for k in range(8)]
+        cptr, cm, cnu, cg = [0], [], [], []
+        for j in range(Ns):
+            ent = []
+            for m in range(M_KLE):
+                d = modes[j][m]
+                if PL[m, j] > 0:
+                    ent.append((PL[m, j] - 1, m + 1, gp[d][0]))
+                if MN[m, j] > 0:
+                    ent.append((MN[m, j] - 1, m + 1, gp[d][1]))
+            for nu, m, g in sorted(ent):
+                cnu.append(nu), cm.append(m), cg.append(g)
+            cptr.append(len(cm))
+        return (np.array(cptr, dtype=np.int32), np.array(cm, dtype=np.int32), np.array(cnu, dtype=np.int32),
+                np.array(cg, dtype=np.float64))
+
+    bd = np.ascontiguousarray(fes.bdofs, dtype=np.int64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def run(Ns):
+        cptr, cm, cnu, cg = coupling(Ns)
+        x = np.random.default_rng(0).uniform(-1, 1, n * Ns)
+        y = np.empty_like(x)
+        t0 = time.perf_counter()
+        lib.cpu_ref_mul(C.c_int64(n), C.c_int64(Ns), C.c_int64(nnz), p(colptr), p(rowval), p(vals), p(cptr), p(cm),
+                        p(cnu), p(cg), C.c_int64(len(bd)), p(bd), p(x), p(y), C.c_int(nthreads))
+        return time.perf_counter() - t0, Ns + len(cm)
+
+    t_probe, sw_probe = run(max(nthreads, 8))  # probe: a handful of modes
+    per_sweep = t_probe / sw_probe
+    target_sweeps = budget_s / per_sweep
+    Ns = int(np.clip(target_sweeps / 4.0, 32, 600))  # ~4 sweeps per mode in the sample region
+    ts = []
+    for k in range(warmup + steps):
+        t, sweeps = run(Ns)
+        if k >= warmup:
+            ts.append(t)
+    t = float(np.mean(ts))
+    # normalise to the sweeps-per-mode ratio of the full workload (cost is linear in the number of sweeps)
+    t_full_equiv = t / sweeps * sweeps_full
+    value = n * N_MODES / t_full_equiv / 1e9
+    return {"value": round(value, 4), "unit": "GDoF/s", "cores": nthreads, "kind": "port",
+            "sample": f"first {Ns} of the 2000 multi-indices on the full 1,048,576-dof mesh: {sweeps} CSC sweeps in "
+                      f"{t:.2f} s with {nthreads} OpenMP threads, scaled linearly to the {sweeps_full} sweeps of one "
+                      "full application (reference loop solvers_poisson_primal.jl:101-122; the reference itself is "
+                      "single-threaded Julia, not installed here)",
+            "seconds_per_full_apply_equiv": round(t_full_equiv, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import asgfem_b200 as A
+    try:
+        ctx, fes, n_owned, _ = build_local_problem(A, 0, 1)  # K_m values come from the device assembly
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"cannot assemble inputs: {str(e)[:150]}"}))
+        return
+    res = cpu_reference(A, ctx, fes, budget_s=12.0, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    ctx.close()
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    out = {"impl": "reference", "metric": "SGFE matvec GDoF/s (dofs x modes)", "value": res["value"], "unit": "GDoF/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(res["seconds_per_full_apply_equiv"] * 1e3, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "configs[3]: synthetic 1024x1024 P1 mesh x 2000 graded-lex Legendre multi-indices, "
+                                  "M=20 (CPU arm: bounded column sample, see cpu_baseline.sample)"},
+           "cpu_baseline": res,
+           "e2e": {"value": res["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--variant", type=int, default=0, help="operator kernel: 0 auto, 1 gather, 2 tiled")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
