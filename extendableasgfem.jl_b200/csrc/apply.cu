@@ -432,7 +432,9 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y) {
     const int64_t nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
     ApplyPlan* P = ctx->plan;
     int variant = ctx->apply_variant;
-    if (variant == 0) variant = (P && P->usable && ctx->n * ctx->N >= (1 << 16)) ? 2 : 1;
+    // automatic choice: the gather kernel is currently the faster one on B200 (profiles/r01_*): 129 ms vs 563 ms
+    // per application on the 1M-dof x 2000-mode problem
+    if (variant == 0) variant = 1;
     if (variant == 2 && !(P && P->usable))
         return fail(ctx, ASGFEM_ESTATE, "tiled operator plan not available for this pattern / multi-index set");
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "coeff.cuh"
 
 namespace asgfem {
 
@@ -18,25 +19,6 @@ namespace {
 constexpr int MAXQ = 64;
 __constant__ double c_xref[2 * MAXQ];
 __constant__ double c_w[MAXQ];
-
-__device__ __forceinline__ double eval_am(int m, double x, double y, double mean, const double* __restrict__ decay,
-                                          const int32_t* __restrict__ b1, const int32_t* __restrict__ b2) {
-    if (m == 0) return mean;
-    // decay_factors[m] * cos(pi * b1[m] * x[1]) * cos(pi * b2[m] * x[2]), evaluated left to right (cosinus.jl:62)
-    return decay[m - 1] * cos(3.141592653589793 * (double)b1[m - 1] * x) * cos(3.141592653589793 * (double)b2[m - 1] * y);
-}
-
-// d(phi_d)/d(lambda_l) of the P2 basis (l_i(2l_i-1), 4 l_i l_j on faces (1,2),(2,3),(3,1)) at barycentrics lam
-__device__ __forceinline__ void p2_dphi(const double* lam, int d, double* out3) {
-    out3[0] = out3[1] = out3[2] = 0.0;
-    if (d < 3) {
-        out3[d] = 4.0 * lam[d] - 1.0;
-    } else {
-        int i = d - 3, j = (d - 2) % 3;
-        out3[i] = 4.0 * lam[j];
-        out3[j] = 4.0 * lam[i];
-    }
-}
 
 template <int ORDER>
 __global__ void __launch_bounds__(256)

@@ -224,3 +224,36 @@ def test_reference_interface_solve_primal(c1):
     assert relerr(sol2.entries, ref) < TOL_SOLVE
     TB.ctx.close()
     sol2.TB.ctx.close()
+
+
+@pytest.mark.parametrize("order,domain", [(1, "square"), (2, "square"), (1, "lshape")])
+def test_estimator_matches_oracle(order, domain):
+    from oracle import estimate as oest
+    P = oproblem.poisson_simple(nrefs=3, order=order, domain=domain)
+    ref_sol = np.zeros(P.n * P.N)
+    osolver.solve_primal(ref_sol, P.A0, P.Am, P.b0, P.G, P.N, P.bdofs)
+    f = lambda x, y: 1.0 + x * y  # noqa: E731  non-constant rhs exercises f_at_qp
+    em, ec, ext = oest.estimate_poisson_primal(P.space, ref_sol, P.multi_indices, P.family, P.coeff, f=f,
+                                               bonus_quadorder=2, tail_extension=(10, 2))
+    g = A.uniform_refine(A.grid_unitsquare() if domain == "square" else A.grid_lshape(), 3)
+    fes = A.FESpace(g, order)
+    TB = A.TensorizedBasis(A.LegendrePolynomials, P.multi_indices)
+    sol = A.SGFEVector(fes, TB)
+    A.setup_device_problem(sol, A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0))
+    sol.entries[:] = ref_sol
+    gm, gc, gext = A.estimate(sol, None, rhs=f, bonus_quadorder=2, tail_extension=(10, 2))
+    assert gext == ext                                   # extended multi-index set bit-exact
+    assert gc.shape == ec.shape
+    assert np.abs(gm - em).max() <= TOL_SOLVE * em.max()
+    assert np.abs(gc - ec).max() <= TOL_SOLVE * ec.max()
+    # marked cells of the script's spatial refinement (poisson.jl:402): Doerfler marking on the active-mode sum
+    act = list(range(P.N))
+
+    def marked(ind, theta=0.5):
+        order_ = np.argsort(-ind, kind="stable")
+        csum = np.cumsum(ind[order_])
+        return set(order_[: int(np.searchsorted(csum, theta * csum[-1]) + 1)].tolist())
+
+    if domain == "lshape":  # non-degenerate indicators (no exact ties) -> the marked set must be identical
+        assert marked(gc[:, act].sum(axis=1)) == marked(ec[:, act].sum(axis=1))
+    TB.ctx.close()
