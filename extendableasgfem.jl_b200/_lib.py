@@ -50,6 +50,8 @@ PROTOTYPES = {
     "asgfem_vec_fill_random": (c_i32, [vp, c_i32, c_u64]),
     "asgfem_vec_dot": (c_i32, [vp, c_i32, c_i32, P(c_f64)]),
     "asgfem_vec_axpy": (c_i32, [vp, c_f64, c_i32, c_i32]),
+    "asgfem_vec_xpay": (c_i32, [vp, c_i32, c_f64, c_i32]),
+    "asgfem_vec_copy": (c_i32, [vp, c_i32, c_i32]),
     "asgfem_apply": (c_i32, [vp, c_i32, c_i32]),
     "asgfem_apply_host": (c_i32, [vp, vp, vp]),
     "asgfem_set_apply_variant": (c_i32, [vp, c_i32]),

@@ -167,6 +167,12 @@ class Context:
     def vec_axpy(self, alpha, x, y):
         self._ck(self.lib.asgfem_vec_axpy(self.h, alpha, x, y))
 
+    def vec_xpay(self, x, beta, y):
+        self._ck(self.lib.asgfem_vec_xpay(self.h, x, beta, y))
+
+    def vec_copy(self, src, dst):
+        self._ck(self.lib.asgfem_vec_copy(self.h, src, dst))
+
     # ---- operator / preconditioner / solver ----------------------------------------------------------
     def set_apply_variant(self, v):
         self._ck(self.lib.asgfem_set_apply_variant(self.h, v))

@@ -505,6 +505,27 @@ extern "C" int asgfem_vec_axpy(asgfem_ctx* ctx, double alpha, int32_t x, int32_t
     return 0;
 }
 
+extern "C" int asgfem_vec_xpay(asgfem_ctx* ctx, int32_t x, double beta, int32_t y) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, x) || check_slot(ctx, y)) return ASGFEM_EINVAL;
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    int rc = vec_xpay(ctx, ctx->slots[x], beta, ctx->slots[y]);
+    if (rc) return rc;
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int asgfem_vec_copy(asgfem_ctx* ctx, int32_t src, int32_t dst) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, src) || check_slot(ctx, dst)) return ASGFEM_EINVAL;
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    if (src != dst)
+        ASG_CUDA(ctx, cudaMemcpyAsync(ctx->slots[dst], ctx->slots[src], sizeof(double) * ctx->n * ctx->ld,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // ---- operator -----------------------------------------------------------------------------------
 static int ensure_ready_for_apply(asgfem_ctx* ctx) {
     ASG_CHECK(ctx, ctx->n > 0 && ctx->M >= 0, ASGFEM_ESTATE, "apply: stiffness matrices not set");

@@ -1,0 +1,206 @@
+"""Row-sharded multi-GPU operation: one process per GPU, `torch.distributed` for the plumbing.
+
+The operator shards by spatial dof rows: rank p owns the rows I_p of every K_m and of all vectors, for ALL
+modes, so the G-coupling is local.  One exchange per application (halo rows of X from the neighbouring ranks,
+`batch_isend_irecv` = grouped NCCL send/recv over NVLink), scalars of the Krylov loop by all-reduce.  The
+reference has no distributed path at all (dead `using Distributed`, src/ExtendableASGFEM.jl:3).
+
+Everything here is host-side bookkeeping (integer partitions, halo lists, the Krylov recurrence on scalars); all
+arithmetic on vectors happens in the per-rank `Context` (libasgfem_cuda.so).  The backend object is injectable so
+that the exchange/partition logic is tested with gloo on CPU (tests/test_distributed_cpu.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# ---- partitioning ----------------------------------------------------------------------------------
+def partition_rows(n, nparts, coords=None):
+    """owner[i] in [0, nparts): recursive coordinate bisection of the dof coordinates (METIS is not available);
+    contiguous index blocks if no coordinates are given."""
+    owner = np.zeros(n, dtype=np.int64)
+    if coords is None:
+        bounds = np.linspace(0, n, nparts + 1).astype(np.int64)
+        for p in range(nparts):
+            owner[bounds[p]:bounds[p + 1]] = p
+        return owner
+
+    def rcb(idx, p0, np_):
+        if np_ == 1:
+            owner[idx] = p0
+            return
+        c = coords[idx]
+        axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+        left = np_ // 2
+        order = np.argsort(c[:, axis], kind="stable")
+        cut = len(idx) * left // np_
+        rcb(idx[order[:cut]], p0, left)
+        rcb(idx[order[cut:]], p0 + left, np_ - left)
+
+    rcb(np.arange(n), 0, nparts)
+    return owner
+
+
+class LocalProblem:
+    """Local numbering of rank `rank`: owned dofs first (ascending global id), then halo dofs grouped by owner."""
+
+    def __init__(self, rank, owner, indptr, indices):
+        self.rank = rank
+        n = len(owner)
+        self.owned = np.where(owner == rank)[0]
+        self.n_owned = len(self.owned)
+        cols = np.unique(np.concatenate([indices[indptr[i]:indptr[i + 1]] for i in self.owned])
+                         if self.n_owned else np.zeros(0, dtype=np.int64))
+        halo = cols[owner[cols] != rank]
+        halo = halo[np.lexsort((halo, owner[halo]))]
+        self.halo = halo
+        self.local_to_global = np.concatenate([self.owned, halo])
+        self.n_local = len(self.local_to_global)
+        g2l = -np.ones(n, dtype=np.int64)
+        g2l[self.local_to_global] = np.arange(self.n_local)
+        self.global_to_local = g2l
+        # receive lists: local halo positions per neighbour rank
+        self.recv = {int(q): g2l[halo[owner[halo] == q]] for q in np.unique(owner[halo])}
+        # send lists: my owned dofs that rank q references (structurally symmetric pattern: the dofs of mine
+        # adjacent to q's rows are the ones whose rows reference q's dofs - computed from the rows of q's halo)
+        self.send = {}
+        for q in self.recv:
+            mine = set()
+            for j in halo[owner[halo] == q]:
+                for i in indices[indptr[j]:indptr[j + 1]]:
+                    if owner[i] == rank:
+                        mine.add(int(i))
+            self.send[q] = g2l[np.array(sorted(mine), dtype=np.int64)]
+        # local CSR: owned rows with local column ids, halo rows empty
+        lp = [0]
+        li = []
+        for i in self.owned:
+            c = g2l[indices[indptr[i]:indptr[i + 1]]]
+            li.append(np.sort(c))
+            lp.append(lp[-1] + len(c))
+        lp.extend([lp[-1]] * len(halo))
+        self.indptr = np.array(lp, dtype=np.int64)
+        self.indices = np.concatenate(li) if li else np.zeros(0, dtype=np.int64)
+
+    def local_values(self, indptr, indices, vals):
+        """Values of the owned rows in the order of the local CSR (columns re-sorted by local id)."""
+        out = []
+        for i in self.owned:
+            sl = slice(indptr[i], indptr[i + 1])
+            c = self.global_to_local[indices[sl]]
+            out.append(vals[sl][np.argsort(c, kind="stable")])
+        return np.concatenate(out) if out else np.zeros(0)
+
+
+# ---- halo exchange + Krylov loop ---------------------------------------------------------------------
+class HaloExchange:
+    """Grouped send/recv of halo rows.  `backend.pack_rows(slot, rows0)` returns a torch tensor (device of the
+    process group), `backend.unpack_rows(slot, rows0, tensor)` scatters it back."""
+
+    def __init__(self, local: LocalProblem, backend, dist):
+        self.local, self.backend, self.dist = local, backend, dist
+
+    def __call__(self, slot):
+        d = self.dist
+        if d is None or d.get_world_size() == 1:
+            return
+        ops, recv_bufs = [], {}
+        for q, rows in self.local.send.items():
+            ops.append(d.P2POp(d.isend, self.backend.pack_rows(slot, rows), q))
+        for q, rows in self.local.recv.items():
+            recv_bufs[q] = self.backend.empty_rows(len(rows))
+            ops.append(d.P2POp(d.irecv, recv_bufs[q], q))
+        for w in d.batch_isend_irecv(ops):
+            w.wait()
+        self.backend.sync()
+        for q, rows in self.local.recv.items():
+            self.backend.unpack_rows(slot, rows, recv_bufs[q])
+
+
+class DistributedOperator:
+    def __init__(self, local: LocalProblem, backend, dist):
+        self.local, self.backend, self.dist = local, backend, dist
+        self.exchange = HaloExchange(local, backend, dist)
+
+    def apply(self, sx, sy):
+        self.exchange(sx)
+        self.backend.apply(sx, sy)
+
+    def dot(self, a, b):
+        import torch
+        v = torch.tensor([self.backend.dot_owned(a, b)], dtype=torch.float64, device=self.backend.device)
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(v)
+        return float(v.item())
+
+
+def pcg(op: DistributedOperator, slots, atol=1e-14, rtol=1e-14, itmax=1000):
+    """Preconditioned CG with the rank-local mean preconditioner (block-Jacobi over the row partition: every rank
+    factorises its own block of K_0; same converged solution as the global mean preconditioner, more iterations -
+    SURVEY.md §7 'Multi-GPU preconditioner', option 2).  slots = dict(x, b, r, z, p, q) of vector slot ids;
+    x holds the warm start, b the right-hand side (boundary rows zeroed)."""
+    be = op.backend
+    x, b, r, z, p, q = (slots[k] for k in ("x", "b", "r", "z", "p", "q"))
+    op.apply(x, q)
+    be.copy(b, r)
+    be.axpy(-1.0, q, r)
+    be.precond_apply(r, z)
+    be.copy(z, p)
+    rz = op.dot(r, z)
+    rz0 = rz
+    eps = atol + rtol * np.sqrt(max(rz0, 0.0))
+    k = 0
+    hist = [np.sqrt(max(rz, 0.0))]
+    while k < itmax and np.sqrt(max(rz, 0.0)) > eps:
+        op.apply(p, q)
+        alpha = rz / op.dot(p, q)
+        be.axpy(alpha, p, x)
+        be.axpy(-alpha, q, r)
+        be.precond_apply(r, z)
+        rz_new = op.dot(r, z)
+        be.xpay(z, rz_new / rz, p)
+        rz = rz_new
+        k += 1
+        hist.append(np.sqrt(max(rz, 0.0)))
+    return dict(niter=k, solved=np.sqrt(max(rz, 0.0)) <= eps, residuals=hist)
+
+
+class ContextBackend:
+    """Backend on top of a libasgfem_cuda Context (one GPU)."""
+
+    def __init__(self, ctx, N):
+        import torch
+        self.ctx, self.N, self.torch = ctx, N, torch
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def empty_rows(self, nrows):
+        return self.torch.empty(nrows * self.N, dtype=self.torch.float64, device=self.device)
+
+    def pack_rows(self, slot, rows0):
+        buf = self.empty_rows(len(rows0))
+        self.ctx.pack_rows(slot, np.asarray(rows0) + 1, buf.data_ptr())
+        return buf
+
+    def unpack_rows(self, slot, rows0, buf):
+        self.ctx.unpack_rows(slot, np.asarray(rows0) + 1, buf.data_ptr())
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def apply(self, sx, sy):
+        self.ctx.apply(sx, sy)
+
+    def dot_owned(self, a, b):
+        return self.ctx.vec_dot_owned(a, b)
+
+    def axpy(self, alpha, x, y):
+        self.ctx.vec_axpy(alpha, x, y)
+
+    def xpay(self, x, beta, y):
+        self.ctx.vec_xpay(x, beta, y)
+
+    def copy(self, src, dst):
+        self.ctx.vec_copy(src, dst)
+
+    def precond_apply(self, r, z):
+        self.ctx.precond_apply(r, z)

@@ -112,6 +112,8 @@ int asgfem_vec_zero(asgfem_ctx* ctx, int32_t slot);
 int asgfem_vec_fill_random(asgfem_ctx* ctx, int32_t slot, uint64_t seed);
 int asgfem_vec_dot(asgfem_ctx* ctx, int32_t slot_a, int32_t slot_b, double* out);
 int asgfem_vec_axpy(asgfem_ctx* ctx, double alpha, int32_t slot_x, int32_t slot_y); /* y += alpha x */
+int asgfem_vec_xpay(asgfem_ctx* ctx, int32_t slot_x, double beta, int32_t slot_y); /* y = x + beta y */
+int asgfem_vec_copy(asgfem_ctx* ctx, int32_t slot_src, int32_t slot_dst);
 
 /* ---- (a7) operator ------------------------------------------------------------------------------
  * Y = sum_m (G_m (x) K_m) X with the rows of bdofs zeroed: LinearAlgebra.mul!(Ax, S::MySystemPrimal, x)
