@@ -351,6 +351,10 @@ extern "C" int asgfem_set_space(asgfem_ctx* ctx, int32_t order, int64_t ndofs, i
     }
     int rc = dev_upload(ctx, &ctx->d_celldofs, ctx->h_celldofs);
     if (rc) return rc;
+    if (ctx->h_rowptr.empty()) {  // no matrices yet: the space sizes the vectors (estimator-only use)
+        if (ctx->n != ndofs) free_vec_storage(ctx);
+        ctx->n = ndofs;
+    }
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -384,7 +388,7 @@ extern "C" int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq,
     ASG_CHECK(ctx, M >= 0 && M <= ctx->maxm, ASGFEM_EINVAL, "assemble_stiffness: M exceeds maxm of the coefficient");
     ASG_CHECK(ctx, nq >= 1 && nq <= 64 && xref && w, ASGFEM_EINVAL, "assemble_stiffness: bad quadrature rule");
     if (set_device(ctx)) return ASGFEM_ECUDA;
-    if (ctx->n == 0) {
+    if (ctx->h_rowptr.empty()) {
         // shared pattern from celldofs: all dof pairs sharing a cell (symmetric -> CSC == CSR)
         int64_t n = ctx->ndofs_space;
         int nd = ctx->ndofs4cell;
@@ -542,7 +546,7 @@ static int ensure_ready_for_apply(asgfem_ctx* ctx) {
 
 extern "C" int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant) {
     CTX_OR_FAIL(ctx);
-    ASG_CHECK(ctx, variant >= 0 && variant <= 2, ASGFEM_EINVAL, "apply variant must be 0, 1 or 2");
+    ASG_CHECK(ctx, variant >= 0 && variant <= 3, ASGFEM_EINVAL, "apply variant must be 0..3");
     ctx->apply_variant = variant;
     return 0;
 }

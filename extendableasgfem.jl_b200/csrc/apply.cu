@@ -156,6 +156,7 @@ void cluster_rows(int64_t nrows, const std::vector<int64_t>& rowptr, const std::
 }  // namespace
 
 void apply_free_plan(asgfem_ctx* ctx) {
+    apply_rows_free(ctx);
     if (!ctx->plan) return;
     free_plan_arrays(ctx->plan);
     delete ctx->plan;
@@ -173,6 +174,13 @@ int apply_build_plan(asgfem_ctx* ctx) {
     // ---- row blocks ---------------------------------------------------------------------------
     std::vector<int32_t> order;
     cluster_rows(nrows, ctx->h_rowptr, ctx->h_col, order);
+    // rows of a block sorted by global id: with mesh-ordered numberings lane r then reads column slot ~ r + const,
+    // which keeps the shared-memory gathers of X (nearly) bank-conflict free
+    for (size_t b0 = 0; b0 + TILED_ROWS <= order.size(); b0 += TILED_ROWS) {
+        auto first = order.begin() + (long)b0, last = first + TILED_ROWS;
+        auto mid = std::partition(first, last, [](int32_t v) { return v >= 0; });
+        std::sort(first, mid);
+    }
     P->nblocks = (int)(order.size() / TILED_ROWS);
     int KW = 0;
     for (int64_t i = 0; i < nrows; ++i) KW = std::max<int>(KW, (int)(ctx->h_rowptr[i + 1] - ctx->h_rowptr[i]));
@@ -338,15 +346,22 @@ struct TiledArgs {
     double* y;
 };
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 template <int KW>
 __global__ void __launch_bounds__(TILED_ROWS, 1) k_apply_tiled(TiledArgs a) {
     extern __shared__ __align__(16) double smem[];
-    double* Xs = smem;                                  // [Smax][Cpad]
-    double* Ys = smem + (size_t)a.Smax * a.Cpad;        // [Tmax][Rpad]
+    double* Xs = smem;                                  // [Smax][Cpad]  staged X, column (dof) index fastest
+    double* Ys = smem + (size_t)a.Smax * a.Cpad;        // [Tmax][Rpad]  partial sums, row (dof) index fastest
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int b = blockIdx.x; b < a.nblocks; b += gridDim.x) {
-        const int32_t row = a.blk_rows[(size_t)b * TILED_ROWS + tid];
         const int c0 = a.blk_colptr[b], C = a.blk_colptr[b + 1] - c0;
         int xoff[KW];
         int kpos[KW];
@@ -356,26 +371,37 @@ __global__ void __launch_bounds__(TILED_ROWS, 1) k_apply_tiled(TiledArgs a) {
             xoff[k] = a.ell_lcol[at];
             kpos[k] = a.ell_pos[at];
         }
-        const bool masked = row < 0 || a.bmask[row < 0 ? 0 : row];
 
         for (int tile = 0; tile < a.ntiles; ++tile) {
             const int s0 = a.tile_sptr[tile], S = a.tile_sptr[tile + 1] - s0;
             const int t0 = a.tile_t0[tile], T = a.tile_t[tile];
+            const int d0 = a.tile_dptr[tile], d1 = a.tile_dptr[tile + 1];
             __syncthreads();  // previous tile fully consumed
-            // stage X: warp per column, lanes over staged modes (own part is contiguous in global memory)
+            // stage X asynchronously (LDGSTS): warp per column, lanes over staged modes - the own modes of the tile
+            // are contiguous in global memory, the halo modes are gathered
             for (int c = warp; c < C; c += TILED_WARPS) {
                 const double* xr = a.x + (int64_t)a.blk_cols[c0 + c] * a.ld;
-                for (int s = lane; s < S; s += 32) Xs[s * a.Cpad + c] = __ldg(xr + a.tile_smodes[s0 + s]);
+                for (int s = lane; s < S; s += 32) cp_async8(Xs + s * a.Cpad + c, xr + a.tile_smodes[s0 + s]);
             }
             for (int k = tid; k < T * a.Rpad; k += TILED_ROWS) Ys[k] = 0.0;
+            // K_m row of the first direction travels while the copies land
+            double kr[KW], kn[KW];
+            {
+                const double* vm = a.vals + (int64_t)a.dir_m[d0] * a.nnz;
+#pragma unroll
+                for (int k = 0; k < KW; ++k) kn[k] = kpos[k] >= 0 ? __ldg(vm + kpos[k]) : 0.0;
+            }
+            cp_async_wait_all();
             __syncthreads();
 
-            const int d0 = a.tile_dptr[tile], d1 = a.tile_dptr[tile + 1];
             for (int d = d0; d < d1; ++d) {
-                const double* vm = a.vals + (int64_t)a.dir_m[d] * a.nnz;
-                double kr[KW];
 #pragma unroll
-                for (int k = 0; k < KW; ++k) kr[k] = kpos[k] >= 0 ? __ldg(vm + kpos[k]) : 0.0;
+                for (int k = 0; k < KW; ++k) kr[k] = kn[k];
+                if (d + 1 < d1) {  // prefetch the K_m row of the next direction
+                    const double* vm = a.vals + (int64_t)a.dir_m[d + 1] * a.nnz;
+#pragma unroll
+                    for (int k = 0; k < KW; ++k) kn[k] = kpos[k] >= 0 ? __ldg(vm + kpos[k]) : 0.0;
+                }
                 const int e0 = a.dir_eptr[d], e1 = a.dir_eptr[d + 1];
                 for (int e = e0; e < e1; e += EU) {  // EU independent dot-product chains for ILP
                     uint32_t ds[EU];
@@ -411,7 +437,6 @@ __global__ void __launch_bounds__(TILED_ROWS, 1) k_apply_tiled(TiledArgs a) {
                 for (int k = lane; k < T; k += 32) yr[k] = m ? 0.0 : Ys[k * a.Rpad + r];
             }
         }
-        (void)masked;
     }
 }
 
@@ -432,13 +457,16 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y) {
     const int64_t nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
     ApplyPlan* P = ctx->plan;
     int variant = ctx->apply_variant;
-    // automatic choice: the gather kernel is currently the faster one on B200 (profiles/r01_*): 129 ms vs 563 ms
-    // per application on the 1M-dof x 2000-mode problem
-    if (variant == 0) variant = 1;
+    // automatic choice (profiles/r01_*, 1M dofs x 2000 modes on B200): row-resident kernel 125 ms with DRAM traffic
+    // at the algorithmic minimum, gather kernel 129 ms with 2.6x the traffic, row-block tiled kernel 350 ms
+    if (variant == 0) variant = (ctx->n * ctx->N >= (1 << 16) && apply_rows_preferred(ctx)) ? 3 : 1;
     if (variant == 2 && !(P && P->usable))
         return fail(ctx, ASGFEM_ESTATE, "tiled operator plan not available for this pattern / multi-index set");
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (variant == 1) {
+    if (variant == 3) {
+        int rc = apply_rows_launch(ctx, x, y);
+        if (rc) return rc;
+    } else if (variant == 1) {
         int bx = (int)std::min<int64_t>(128, ((ctx->ld + 31) / 32) * 32);
         int by = 256 / bx;
         dim3 block(bx, by);

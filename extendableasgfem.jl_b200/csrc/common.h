@@ -118,6 +118,7 @@ struct asgfem_ctx {
     double last_apply_ms = 0;
     asgfem::ApplyPlan* plan = nullptr;
     asgfem::PrecondPlan* precond = nullptr;
+    void* rowplan = nullptr;  // asgfem::RowPlan (apply_rows.cu)
 };
 
 namespace asgfem {
@@ -157,6 +158,11 @@ int dev_upload(asgfem_ctx* ctx, T** dptr, const std::vector<T>& h) {
 int apply_build_plan(asgfem_ctx* ctx);
 void apply_free_plan(asgfem_ctx* ctx);
 int apply_launch(asgfem_ctx* ctx, const double* x, double* y);
+// apply_rows.cu
+int apply_rows_build(asgfem_ctx* ctx);
+void apply_rows_free(asgfem_ctx* ctx);
+int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y);
+bool apply_rows_preferred(asgfem_ctx* ctx);
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
 int vec_to_host_layout(asgfem_ctx* ctx, const double* dvec, double* host);
