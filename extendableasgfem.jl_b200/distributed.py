@@ -204,3 +204,29 @@ class ContextBackend:
 
     def precond_apply(self, r, z):
         self.ctx.precond_apply(r, z)
+
+
+def setup_context(ctx, local: LocalProblem, mats, bdofs0, family, multi_indices):
+    """Loads the rows owned by this rank (local numbering) into a Context.  mats = [K_0, K_1, ..., K_M] as global
+    scipy CSR matrices; bdofs0 = global Dirichlet dofs (0-based).  Halo rows are empty and flagged as excluded, so
+    the rank-local mean preconditioner factorises the owned interior block only (block-Jacobi)."""
+    import scipy.sparse as sp
+    n = local.n_local
+    ctx.set_multiindices(family, np.asarray(multi_indices, dtype=np.int64))
+    pat = sp.csr_matrix((np.ones(len(local.indices)), local.indices, local.indptr), shape=(n, n)).tocsc()
+    pat.sort_indices()
+    ctx.set_pattern_csc(n, pat.indptr.astype(np.int64) + 1, pat.indices.astype(np.int64) + 1)
+    ctx.set_num_stiffness(len(mats) - 1)
+    for m, K in enumerate(mats):
+        K = sp.csr_matrix(K)
+        vals = local.local_values(K.indptr, K.indices, K.data)
+        Kl = sp.csr_matrix((vals, local.indices, local.indptr), shape=(n, n)).tocsc()
+        Kl.sort_indices()
+        ctx.set_stiffness_csc(m, Kl.indptr.astype(np.int64) + 1, Kl.indices.astype(np.int64) + 1, Kl.data)
+    g2l = local.global_to_local
+    bl = g2l[np.asarray(bdofs0)]
+    bl = bl[bl >= 0]
+    excluded = np.unique(np.concatenate([bl, np.arange(local.n_owned, n)]))
+    ctx.set_bdofs(excluded + 1)
+    ctx.set_owned_rows(local.n_owned)
+    return ctx

@@ -1,0 +1,77 @@
+"""2-GPU parity of the row-sharded path (NCCL halo exchange + all-reduce) against the oracle.  Needs >= 2 CUDA
+devices: skipped on single-GPU boxes (the host logic is covered by tests/test_distributed_cpu.py with gloo)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    import asgfem_b200 as A
+    from asgfem_b200 import distributed as D
+    from oracle import problem as oproblem, solver as osolver
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        P = oproblem.poisson_simple(nrefs=3, order=2)
+        A0 = sp.csr_matrix(P.A0)
+        owner = D.partition_rows(P.n, world)  # index blocks (dof coordinates of P2 face dofs are not needed)
+        L = D.LocalProblem(rank, owner, A0.indptr, A0.indices)
+        ctx = A.Context(rank)
+        D.setup_context(ctx, L, [P.A0] + P.Am, P.bdofs, P.family, P.multi_indices)
+        ctx.vec_alloc(6)
+        be = D.ContextBackend(ctx, P.N)
+        op = D.DistributedOperator(L, be, dist)
+        xg = np.random.default_rng(0).standard_normal(P.n * P.N)
+        ref = osolver.SystemPrimal(P.A0, P.Am, P.G, P.bdofs, P.N).mul(xg).reshape(P.N, P.n)
+        xl = np.zeros((P.N, L.n_local))
+        xl[:, :L.n_owned] = xg.reshape(P.N, P.n)[:, L.owned]  # halo rows zero: the exchange must fill them
+        ctx.vec_upload(0, xl.reshape(-1))
+        op.apply(0, 1)
+        got = ctx.vec_download(1).reshape(P.N, L.n_local)[:, :L.n_owned]
+        err_apply = np.abs(got - ref[:, L.owned]).max() / np.abs(ref).max()
+        # distributed PCG (rank-local mean preconditioner) against the oracle's GMRES solution
+        refsol = np.zeros(P.n * P.N)
+        osolver.solve_primal(refsol, P.A0, P.Am, P.b0, P.G, P.N, P.bdofs)
+        refsol = refsol.reshape(P.N, P.n)
+        b = np.zeros((P.N, L.n_local))
+        b[0, :L.n_owned] = P.b0[L.owned]
+        g2l = L.global_to_local[P.bdofs]
+        b[:, g2l[g2l >= 0]] = 0
+        ctx.vec_zero(0)
+        ctx.vec_upload(1, b.reshape(-1))
+        st = D.pcg(op, dict(x=0, b=1, r=2, z=3, p=4, q=5), atol=1e-14, rtol=1e-13, itmax=500)
+        sol = ctx.vec_download(0).reshape(P.N, L.n_local)[:, :L.n_owned]
+        err_sol = np.abs(sol - refsol[:, L.owned]).max() / np.abs(refsol).max()
+        q.put((rank, err_apply, st["niter"], bool(st["solved"]), err_sol))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_operator_and_pcg():
+    world = 2
+    c = mp.get_context("spawn")
+    q = c.Queue()
+    procs = [c.Process(target=_worker, args=(r, world, 29650 + os.getpid() % 300, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err_apply, niter, solved, err_sol in res:
+        assert err_apply < 1e-12, (rank, err_apply)
+        assert solved and niter < 300
+        assert err_sol < 1e-10, (rank, err_sol)
