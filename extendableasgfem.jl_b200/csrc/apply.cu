@@ -157,6 +157,7 @@ void cluster_rows(int64_t nrows, const std::vector<int64_t>& rowptr, const std::
 
 void apply_free_plan(asgfem_ctx* ctx) {
     apply_rows_free(ctx);
+    apply_dir_free(ctx);
     if (!ctx->plan) return;
     free_plan_arrays(ctx->plan);
     delete ctx->plan;
@@ -463,7 +464,10 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y) {
     if (variant == 2 && !(P && P->usable))
         return fail(ctx, ASGFEM_ESTATE, "tiled operator plan not available for this pattern / multi-index set");
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (variant == 3) {
+    if (variant == 4 || variant == 5) {
+        int rc = apply_dir_launch(ctx, x, y, variant == 5);
+        if (rc) return rc;
+    } else if (variant == 3) {
         int rc = apply_rows_launch(ctx, x, y);
         if (rc) return rc;
     } else if (variant == 1) {

@@ -119,6 +119,7 @@ struct asgfem_ctx {
     asgfem::ApplyPlan* plan = nullptr;
     asgfem::PrecondPlan* precond = nullptr;
     void* rowplan = nullptr;  // asgfem::RowPlan (apply_rows.cu)
+    void* dirplan = nullptr;  // asgfem::DirPlan (apply_dir.cu)
 };
 
 namespace asgfem {
@@ -163,6 +164,11 @@ int apply_rows_build(asgfem_ctx* ctx);
 void apply_rows_free(asgfem_ctx* ctx);
 int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y);
 bool apply_rows_preferred(asgfem_ctx* ctx);
+// apply_dir.cu
+int apply_dir_build(asgfem_ctx* ctx, bool owned);
+void apply_dir_free(asgfem_ctx* ctx);
+int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned);
+bool apply_dir_preferred(asgfem_ctx* ctx);
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
 int vec_to_host_layout(asgfem_ctx* ctx, const double* dvec, double* host);

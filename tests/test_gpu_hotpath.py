@@ -87,7 +87,7 @@ def test_vector_layout_roundtrip_and_random_fill(c1):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_apply_matches_oracle(c1, mid, variant):
     for P in (c1, mid):
         ctx = make_ctx(P)
@@ -121,7 +121,7 @@ def test_apply_random_sets_lshape(family):
         S = osolver.SystemPrimal(P.A0, P.Am, P.G, P.bdofs, P.N)
         x = rng.standard_normal(P.n * P.N)
         ref = S.mul(x)
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 4, 5):
             ctx = make_ctx(P)
             ctx.set_apply_variant(variant)
             assert relerr(ctx.apply_host(x), ref) < TOL_APPLY
