@@ -55,7 +55,8 @@ int32_t bfs(const Graph& g, int32_t start, const std::vector<int32_t>& tag, int3
 }
 
 // nested dissection ordering; returns perm (elimination order -> node)
-void nested_dissection(const Graph& g, std::vector<int32_t>& perm) {
+void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double* xy, std::vector<int32_t>& cuts,
+                       int32_t max_block) {
     const int32_t n = g.n;
     const int32_t LEAF = 24;
     perm.assign((size_t)n, -1);
@@ -63,6 +64,14 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm) {
     struct Task {
         std::vector<int32_t> nodes;
         int32_t lo;  // this set occupies perm[lo, lo + nodes.size())
+    };
+    // block cuts for the blocked triangular solves: every subtree with <= max_block unknowns is one block, the
+    // separators above are cut into chunks of <= max_block rows
+    cuts.clear();
+    cuts.push_back(0);
+    auto cut_range = [&](int32_t lo, int32_t len) {  // a range that must not be merged with its neighbours
+        for (int32_t o = 0; o < len; o += max_block) cuts.push_back(lo + o);
+        cuts.push_back(lo + len);
     };
     std::vector<Task> stack;
     {
@@ -87,6 +96,64 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm) {
             tag[v] = id;
             dist[v] = -1;
         }
+        if (xy) {
+            // geometric separator: cut the bounding box at the median of its longer axis; the separator is the layer
+            // of nodes on the upper side that touch the lower side (straight lines on mesh-like point sets)
+            double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+            for (int32_t v : t.nodes)
+                for (int d = 0; d < 2; ++d) {
+                    lo[d] = std::min(lo[d], xy[2 * v + d]);
+                    hi[d] = std::max(hi[d], xy[2 * v + d]);
+                }
+            const int ax = (hi[0] - lo[0]) >= (hi[1] - lo[1]) ? 0 : 1;
+            if (hi[ax] > lo[ax]) {
+                tmp.assign(t.nodes.begin(), t.nodes.end());
+                auto midit = tmp.begin() + sz / 2;
+                std::nth_element(tmp.begin(), midit, tmp.end(), [&](int32_t a, int32_t b) {
+                    return xy[2 * a + ax] != xy[2 * b + ax] ? xy[2 * a + ax] < xy[2 * b + ax] : a < b;
+                });
+                const double cut = xy[2 * (*midit) + ax];
+                // dist doubles as side marker: 0 = lower side (coordinate < cut), 1 = upper side
+                int32_t nlow = 0;
+                for (int32_t v : t.nodes) {
+                    dist[v] = xy[2 * v + ax] < cut ? 0 : 1;
+                    nlow += dist[v] == 0;
+                }
+                if (nlow > 0 && nlow < sz) {
+                    Task a, b;
+                    std::vector<int32_t> sep;
+                    for (int32_t v : t.nodes) {
+                        if (dist[v] == 0) {
+                            a.nodes.push_back(v);
+                            continue;
+                        }
+                        bool touches = false;
+                        for (int64_t p = g.ptr[v]; p < g.ptr[v + 1] && !touches; ++p) {
+                            int32_t u = g.adj[p];
+                            touches = tag[u] == id && dist[u] == 0;
+                        }
+                        (touches ? sep : b.nodes).push_back(v);
+                    }
+                    if (!sep.empty() || a.nodes.empty() || b.nodes.empty()) {
+                        a.lo = t.lo;
+                        b.lo = t.lo + (int32_t)a.nodes.size();
+                        int32_t seplo = b.lo + (int32_t)b.nodes.size();
+                        for (size_t k = 0; k < sep.size(); ++k) perm[seplo + (int32_t)k] = sep[k];
+                        for (int32_t v : t.nodes) dist[v] = -1;
+                        if (sz > max_block) {
+                            cuts.push_back(a.lo);
+                            cuts.push_back(b.lo);
+                            cut_range(seplo, (int32_t)sep.size());
+                        }
+                        stack.push_back(std::move(a));
+                        stack.push_back(std::move(b));
+                        continue;
+                    }
+                    // the two sides are not connected: fall through to the component split below
+                }
+            }
+            for (int32_t v : t.nodes) dist[v] = -1;
+        }
         // connected component of the first node
         int32_t cnt = bfs(g, t.nodes[0], tag, id, dist, bfsout, lv);
         if (cnt < sz) {  // disconnected: split off the component, no separator needed
@@ -97,6 +164,10 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm) {
                 if (tag[v] == id) b.nodes.push_back(v);
             a.lo = t.lo;
             b.lo = t.lo + (int32_t)a.nodes.size();
+            if (sz > max_block) {
+                cuts.push_back(a.lo);
+                cuts.push_back(b.lo);
+            }
             stack.push_back(std::move(a));
             stack.push_back(std::move(b));
             continue;
@@ -110,6 +181,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm) {
         int32_t nlev = (int32_t)lv.size() - 1;
         if (nlev < 3) {  // (nearly) complete graph: no useful separator
             for (int32_t k = 0; k < sz; ++k) perm[t.lo + k] = t.nodes[k];
+            if (sz > max_block) cut_range(t.lo, sz);
             continue;
         }
         // separator = the level whose removal balances the two sides best
@@ -131,15 +203,30 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm) {
         b.lo = t.lo + (int32_t)a.nodes.size();
         int32_t seplo = b.lo + (int32_t)b.nodes.size();
         for (int32_t k = 0; k < nsep; ++k) perm[seplo + k] = bfsout[lv[best] + k];
+        if (sz > max_block) {
+            cuts.push_back(a.lo);
+            cuts.push_back(b.lo);
+            cut_range(seplo, nsep);
+        }
         stack.push_back(std::move(a));
         stack.push_back(std::move(b));
     }
+    cuts.push_back(n);
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    // safety: no block longer than max_block (e.g. leaves of an unsplittable set)
+    std::vector<int32_t> fixed;
+    for (size_t k = 0; k + 1 < cuts.size(); ++k)
+        for (int32_t o = cuts[k]; o < cuts[k + 1]; o += max_block) fixed.push_back(o);
+    fixed.push_back(n);
+    cuts.swap(fixed);
 }
 
 }  // namespace
 
 int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,
-                     const uint8_t* is_boundary, CholFactor& F, std::string& err) {
+                     const uint8_t* is_boundary, const double* coords_full, int32_t max_block, CholFactor& F,
+                     std::string& err) {
     // ---- reduced numbering -----------------------------------------------------------------------
     std::vector<int32_t> red((size_t)n_full, -1), full;
     for (int64_t i = 0; i < n_full; ++i)
@@ -173,7 +260,15 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
     }
 
     std::vector<int32_t> perm;
-    nested_dissection(g, perm);
+    std::vector<double> xy;
+    if (coords_full) {
+        xy.resize((size_t)2 * n);
+        for (int32_t r = 0; r < n; ++r) {
+            xy[2 * r] = coords_full[2 * (int64_t)full[r]];
+            xy[2 * r + 1] = coords_full[2 * (int64_t)full[r] + 1];
+        }
+    }
+    nested_dissection(g, perm, coords_full ? xy.data() : nullptr, F.block_start, max_block);
     std::vector<int32_t> iperm((size_t)n);
     for (int32_t k = 0; k < n; ++k) {
         if (perm[k] < 0) {

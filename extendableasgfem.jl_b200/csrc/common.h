@@ -43,10 +43,12 @@ struct CholFactor {
     std::vector<int32_t> Li;
     std::vector<double> Lx;
     std::vector<double> dinv;      // 1 / L_kk
+    std::vector<int32_t> block_start;  // cuts of the elimination order aligned with the dissection tree (last = n)
 };
 // A: full n_full x n_full CSR (rowptr int64, col int32), keep[i] != 0 for interior rows. Returns 0 or ASGFEM_E*.
 int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,
-                     const uint8_t* is_boundary, CholFactor& F, std::string& err);
+                     const uint8_t* is_boundary, const double* coords_full, int32_t max_block, CholFactor& F,
+                     std::string& err);
 
 // ---- device-side plans --------------------------------------------------------------------------
 struct ApplyPlan;    // apply.cu
