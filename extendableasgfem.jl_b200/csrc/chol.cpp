@@ -55,7 +55,7 @@ int32_t bfs(const Graph& g, int32_t start, const std::vector<int32_t>& tag, int3
 }
 
 // nested dissection ordering; returns perm (elimination order -> node)
-void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double* xy, std::vector<int32_t>& cuts,
+void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double* xy, std::vector<BlockRec>& blocks,
                        int32_t max_block) {
     const int32_t n = g.n;
     const int32_t LEAF = 24;
@@ -63,15 +63,17 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
     std::vector<int32_t> tag((size_t)n, 0), dist((size_t)n, -1), bfsout, lv, tmp;
     struct Task {
         std::vector<int32_t> nodes;
-        int32_t lo;  // this set occupies perm[lo, lo + nodes.size())
+        int32_t lo;     // this set occupies perm[lo, lo + nodes.size())
+        int32_t depth;  // depth in the dissection tree
     };
-    // block cuts for the blocked triangular solves: every subtree with <= max_block unknowns is one block, the
-    // separators above are cut into chunks of <= max_block rows
-    cuts.clear();
-    cuts.push_back(0);
-    auto cut_range = [&](int32_t lo, int32_t len) {  // a range that must not be merged with its neighbours
-        for (int32_t o = 0; o < len; o += max_block) cuts.push_back(lo + o);
-        cuts.push_back(lo + len);
+    // blocks for the tree-parallel triangular solves: every leaf and every separator of the dissection tree is a
+    // block (separators longer than max_block are cut into sequentially dependent chunks)
+    blocks.clear();
+    auto emit_range = [&](int32_t lo, int32_t len, int32_t depth) {
+        if (len <= 0) return;
+        int32_t nch = (len + max_block - 1) / max_block;
+        for (int32_t c = 0; c < nch; ++c)
+            blocks.push_back({lo + c * max_block, std::min(max_block, len - c * max_block), depth, c, nch});
     };
     std::vector<Task> stack;
     {
@@ -79,6 +81,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
         t.nodes.resize((size_t)n);
         std::iota(t.nodes.begin(), t.nodes.end(), 0);
         t.lo = 0;
+        t.depth = 0;
         stack.push_back(std::move(t));
     }
     int32_t next_id = 1;
@@ -89,6 +92,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
         if (sz == 0) continue;
         if (sz <= LEAF) {
             for (int32_t k = 0; k < sz; ++k) perm[t.lo + k] = t.nodes[k];
+            emit_range(t.lo, sz, t.depth);
             continue;
         }
         const int32_t id = next_id++;
@@ -140,11 +144,8 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
                         int32_t seplo = b.lo + (int32_t)b.nodes.size();
                         for (size_t k = 0; k < sep.size(); ++k) perm[seplo + (int32_t)k] = sep[k];
                         for (int32_t v : t.nodes) dist[v] = -1;
-                        if (sz > max_block) {
-                            cuts.push_back(a.lo);
-                            cuts.push_back(b.lo);
-                            cut_range(seplo, (int32_t)sep.size());
-                        }
+                        a.depth = b.depth = t.depth + 1;
+                        emit_range(seplo, (int32_t)sep.size(), t.depth);
                         stack.push_back(std::move(a));
                         stack.push_back(std::move(b));
                         continue;
@@ -164,10 +165,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
                 if (tag[v] == id) b.nodes.push_back(v);
             a.lo = t.lo;
             b.lo = t.lo + (int32_t)a.nodes.size();
-            if (sz > max_block) {
-                cuts.push_back(a.lo);
-                cuts.push_back(b.lo);
-            }
+            a.depth = b.depth = t.depth + 1;
             stack.push_back(std::move(a));
             stack.push_back(std::move(b));
             continue;
@@ -181,7 +179,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
         int32_t nlev = (int32_t)lv.size() - 1;
         if (nlev < 3) {  // (nearly) complete graph: no useful separator
             for (int32_t k = 0; k < sz; ++k) perm[t.lo + k] = t.nodes[k];
-            if (sz > max_block) cut_range(t.lo, sz);
+            emit_range(t.lo, sz, t.depth);
             continue;
         }
         // separator = the level whose removal balances the two sides best
@@ -203,23 +201,12 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
         b.lo = t.lo + (int32_t)a.nodes.size();
         int32_t seplo = b.lo + (int32_t)b.nodes.size();
         for (int32_t k = 0; k < nsep; ++k) perm[seplo + k] = bfsout[lv[best] + k];
-        if (sz > max_block) {
-            cuts.push_back(a.lo);
-            cuts.push_back(b.lo);
-            cut_range(seplo, nsep);
-        }
+        a.depth = b.depth = t.depth + 1;
+        emit_range(seplo, nsep, t.depth);
         stack.push_back(std::move(a));
         stack.push_back(std::move(b));
     }
-    cuts.push_back(n);
-    std::sort(cuts.begin(), cuts.end());
-    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
-    // safety: no block longer than max_block (e.g. leaves of an unsplittable set)
-    std::vector<int32_t> fixed;
-    for (size_t k = 0; k + 1 < cuts.size(); ++k)
-        for (int32_t o = cuts[k]; o < cuts[k + 1]; o += max_block) fixed.push_back(o);
-    fixed.push_back(n);
-    cuts.swap(fixed);
+    std::sort(blocks.begin(), blocks.end(), [](const BlockRec& x, const BlockRec& y) { return x.start < y.start; });
 }
 
 }  // namespace
@@ -268,7 +255,21 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
             xy[2 * r + 1] = coords_full[2 * (int64_t)full[r] + 1];
         }
     }
-    nested_dissection(g, perm, coords_full ? xy.data() : nullptr, F.block_start, max_block);
+    nested_dissection(g, perm, coords_full ? xy.data() : nullptr, F.blocks, max_block);
+    {
+        int32_t at = 0;
+        for (const BlockRec& b : F.blocks) {
+            if (b.start != at) {
+                err = "internal error: dissection blocks do not tile the elimination order";
+                return ASGFEM_ENUMERIC;
+            }
+            at += b.len;
+        }
+        if (at != n) {
+            err = "internal error: dissection blocks do not cover all unknowns";
+            return ASGFEM_ENUMERIC;
+        }
+    }
     std::vector<int32_t> iperm((size_t)n);
     for (int32_t k = 0; k < n; ++k) {
         if (perm[k] < 0) {

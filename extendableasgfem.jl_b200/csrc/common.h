@@ -36,6 +36,11 @@ struct Coupling {
 void build_coupling(const MultiIndexSet& S, int family, Coupling& C);
 
 // ---- sparse Cholesky of the Dirichlet-reduced K_0 (chol.cpp) -----------------------------------
+struct BlockRec {
+    int32_t start, len;     // rows [start, start+len) of the elimination order
+    int32_t depth;          // depth of the owning node in the dissection tree (same depth => independent)
+    int32_t chunk, nchunks;  // long separators are cut into sequentially dependent chunks
+};
 struct CholFactor {
     int64_t n = 0;                 // reduced dimension
     std::vector<int32_t> perm;     // perm[k] = original (full) row id of the k-th eliminated unknown
@@ -43,7 +48,7 @@ struct CholFactor {
     std::vector<int32_t> Li;
     std::vector<double> Lx;
     std::vector<double> dinv;      // 1 / L_kk
-    std::vector<int32_t> block_start;  // cuts of the elimination order aligned with the dissection tree (last = n)
+    std::vector<BlockRec> blocks;  // leaves and separators of the dissection tree, sorted by start
 };
 // A: full n_full x n_full CSR (rowptr int64, col int32), keep[i] != 0 for interior rows. Returns 0 or ASGFEM_E*.
 int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,

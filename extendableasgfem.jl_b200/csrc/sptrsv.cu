@@ -2,20 +2,21 @@
 // (LinearAlgebra.ldiv!(y, P::MyPreconditionerPrimal, b), src/modelproblems/solvers_poisson_primal.jl:46-78;
 //  the reference runs N sequential UMFPACK solves, one per mode block).
 //
-// Factor P K_0 P^T = L L^T from chol.cpp.  The N right-hand sides are independent, so the triangular solves need
-// no inter-CTA synchronisation at all: every CTA owns a tile of MT modes and performs the whole sweep by itself.
-//
-// Blocked right-looking sweep (k_trsv_blocked).  The unknowns are cut into column blocks of BW consecutive rows of
-// the elimination order (nested dissection keeps subtrees and separators contiguous).  For block J the CTA
-//   1. stages W[J, tile] in shared memory,
-//   2. solves the diagonal block L[J,J] there, level by level (rows of a level spread over the half-warps; the
-//      sequential rows of dense separator blocks are split over all half-warps and reduced),
-//   3. writes the finished rows back, and
-//   4. pushes W[r, tile] -= L[r, J] * Z_J to every later row r with entries in J: one half-warp per (row, block)
-//      segment of the CSR row, the sources Z_J come from shared memory (each is reused by all rows below), the
-//      target row is read and written once per segment instead of once per nonzero.
-// The backward sweep L^T z = y is the same algorithm on the reversed numbering k -> n-1-k (rows of L^T reversed).
-// Work vectors live in elimination order (W[k,:] <-> dof perm[k]).
+// Factor P K_0 P^T = L L^T from chol.cpp (nested dissection).  The N right-hand sides are independent, so the
+// triangular solves need no inter-CTA synchronisation: every CTA owns a tile of MT modes and performs the whole
+// sweep by itself.  Inside the CTA the sweep is TREE-PARALLEL and right-looking:
+//   * every leaf and every separator (chunk) of the dissection tree is a task; tasks of the same tree depth are
+//     independent, so one block barrier per tree depth replaces one barrier per row level;
+//   * small tasks (<= SMALL rows) are solved by single warps, 32 of them concurrently: rows and the task's diagonal
+//     block are staged in the warp's shared-memory slice, rows are eliminated in order (the two half-warps split a
+//     row's entries), then the task pushes  W[r] -= L[r, task] * Z_task  to the rows r above it - one (row, task)
+//     segment of the CSR row at a time, sources from shared memory, one fp64 RED per segment and mode (sibling
+//     tasks may hit the same ancestor row concurrently);
+//   * big tasks (separator chunks up to BW rows) are handled by the whole CTA: panels of PANEL rows, the part left
+//     of the panel for all panel rows in parallel (4 half-warps per row), the PANEL x PANEL triangle by one
+//     half-warp from shared memory, pushes by all 64 half-warps.
+// The backward sweep L^T z = y is the same algorithm on the reversed numbering k -> n-1-k with the tree walked from
+// the root down.  Work vectors live in elimination order (W[k,:] <-> dof perm[k]).
 #include <algorithm>
 
 #include "common.h"
@@ -23,29 +24,30 @@
 namespace asgfem {
 
 constexpr int MT = 16;                 // modes per CTA (half a warp wide)
-constexpr int RS = 64;                 // half-warps (row slots) per CTA
-constexpr int TRSV_THREADS = MT * RS;  // 1024
-constexpr int BW = 256;                // max rows per column block
-constexpr int DE_MAX = 6144;           // diagonal-block entries staged in shared memory (else streamed from L2)
-constexpr int PANEL = 16;              // rows per panel in dense (separator) blocks
+constexpr int NWARP = 32;
+constexpr int TRSV_THREADS = 32 * NWARP;  // 1024
+constexpr int RS = TRSV_THREADS / MT;  // half-warps per CTA
+constexpr int BW = 256;                // max rows of a big task
+constexpr int SMALL = 24;              // max rows of a warp task (= leaf size of the dissection)
+constexpr int SMALL_DE = SMALL * (SMALL - 1) / 2;  // max entries of its diagonal block
+constexpr int PANEL = 16;
+constexpr int PER = RS / PANEL;        // half-warps per panel row
 
 struct TriDev {  // one triangular system in its own (forward) numbering
-    // off-diagonal-block part: CSR of the strict lower triangle; only the entries outside a row's own block are used
-    int32_t* idx = nullptr;
+    int32_t* idx = nullptr;        // CSR of the strict lower triangle (only entries outside a row's own block are used)
     double* val = nullptr;
     int32_t* segptr = nullptr;     // per block: range of push segments
     int32_t* seg = nullptr;        // per segment: target row, first nonzero, length
-    // diagonal-block part, stored compactly block after block (block-local 16-bit column ids)
     double* dinv = nullptr;        // per row
-    int32_t* drow = nullptr;       // per row: offset of its diagonal-block entries (n+1 entries)
-    int32_t* dsplit = nullptr;     // per row: number of those entries left of the row's 16-row panel
-    uint16_t* didx = nullptr;
+    int32_t* drow = nullptr;       // per row: offset of its diagonal-block entries (n+1)
+    int32_t* dsplit = nullptr;     // per row: number of those entries left of the row's panel
+    uint16_t* didx = nullptr;      // diagonal-block entries, block-local column ids
     double* dval = nullptr;
-    int32_t* blk_start = nullptr;  // nblocks+1 block boundaries (aligned with the dissection tree)
-    int32_t* blk_info = nullptr;   // per block: offset into levptr, number of levels, dense flag, (pad)
-    int32_t* levptr = nullptr;     // per level: offset into levrows
-    uint16_t* levrows = nullptr;   // rows (block-local ids) sorted by level
-    int nblocks = 0;
+    int32_t* blk_start = nullptr;  // nblocks+1
+    int32_t* step_ptr = nullptr;   // nsteps+1 -> ranges of `tasks`
+    int32_t* step_nsmall = nullptr;  // per step: the first so many tasks are small
+    int32_t* tasks = nullptr;      // block ids
+    int nblocks = 0, nsteps = 0;
 };
 
 struct PrecondPlan {
@@ -57,7 +59,8 @@ struct PrecondPlan {
 };
 
 static void free_tri(TriDev& T) {
-    void* ptrs[] = {T.idx, T.val, T.segptr, T.seg, T.dinv, T.drow, T.dsplit, T.didx, T.dval, T.blk_start, T.blk_info, T.levptr, T.levrows};
+    void* ptrs[] = {T.idx, T.val, T.segptr, T.seg, T.dinv, T.drow, T.dsplit, T.didx, T.dval, T.blk_start, T.step_ptr,
+                    T.step_nsmall, T.tasks};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     T = TriDev();
@@ -109,138 +112,189 @@ __global__ void k_zero_masked_rows(double* __restrict__ z, const uint8_t* __rest
     }
 }
 
-// sum_e val[e] * Zs[idx[e]][lane] over e = e0, e0+step, ... < e1 with four independent accumulators (ILP)
-template <class VT, class IT>
-__device__ __forceinline__ double dot_rows(const VT* __restrict__ val, const IT* __restrict__ idx, int e0, int e1, int step,
-                                           const double (*Zs)[MT], int lane) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int e = e0;
-    for (; e + 3 * step < e1; e += 4 * step) {
-        const int i0 = idx[e], i1 = idx[e + step], i2 = idx[e + 2 * step], i3 = idx[e + 3 * step];
-        const double v0 = val[e], v1 = val[e + step], v2 = val[e + 2 * step], v3 = val[e + 3 * step];
-        a0 = fma(v0, Zs[i0][lane], a0);
-        a1 = fma(v1, Zs[i1][lane], a1);
-        a2 = fma(v2, Zs[i2][lane], a2);
-        a3 = fma(v3, Zs[i3][lane], a3);
+// shared-memory slice of one warp during the small-task phase
+struct WarpSlice {
+    double z[SMALL][MT];
+    double dval[SMALL_DE];
+    double dinv[SMALL];
+    int32_t drow[SMALL + 1];
+    uint16_t didx[SMALL_DE + 2];
+};
+// shared memory of the big-task phase (aliases the warp slices; the phases are separated by block barriers)
+struct BigSlice {
+    double z[BW][MT];
+    double red[RS][MT + 1];
+    double dinv[BW];
+    double pval[PANEL * PANEL];
+    int32_t drow[BW + 1];
+    int32_t dsplit[BW];
+    uint16_t pidx[PANEL * PANEL];
+};
+constexpr size_t TRSV_SMEM = sizeof(WarpSlice) * NWARP > sizeof(BigSlice) ? sizeof(WarpSlice) * NWARP : sizeof(BigSlice);
+
+// dot product of one push segment with the task rows in shared memory, by one half-warp: its 16 lanes fetch 16
+// entries at once (coalesced) and hand them round with shuffles, so that one L2 latency covers 16 entries
+__device__ __forceinline__ double segment_dot(const double* __restrict__ v, const int32_t* __restrict__ ix, int len, int j0,
+                                              const double (*Z)[MT], int m, unsigned hmask, int hbase) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int p = 0; p < len; p += MT) {
+        const int cnt = min(MT, len - p);
+        double myv = 0.0;
+        int myi = 0;
+        if (m < cnt) {
+            myv = __ldg(v + p + m);
+            myi = __ldg(ix + p + m) - j0;
+        }
+        for (int u = 0; u < cnt; u += 2) {  // an odd tail reads the zero-weight entry of the next lane
+            const double v0 = __shfl_sync(hmask, myv, hbase + u), v1 = __shfl_sync(hmask, myv, hbase + ((u + 1) & 15));
+            const int i0 = __shfl_sync(hmask, myi, hbase + u), i1 = __shfl_sync(hmask, myi, hbase + ((u + 1) & 15));
+            a0 = fma(v0, Z[i0][m], a0);
+            a1 = fma(u + 1 < cnt ? v1 : 0.0, Z[i1][m], a1);
+        }
     }
-    for (; e < e1; e += step) a0 = fma(val[e], Zs[idx[e]][lane], a0);
-    return (a0 + a1) + (a2 + a3);
+    return a0 + a1;
 }
 
-// Blocked right-looking sweep for the mode tile of this CTA; `rev` maps the system's numbering to memory rows.
 __global__ void __launch_bounds__(TRSV_THREADS, 1)
-k_trsv_blocked(double* __restrict__ w, int64_t ld, int64_t n, int rev, TriDev T) {
-    extern __shared__ __align__(16) double trsv_smem[];
-    double(*Zs)[MT] = reinterpret_cast<double(*)[MT]>(trsv_smem);                     // [BW][MT] rows of the block
-    double(*red)[MT + 1] = reinterpret_cast<double(*)[MT + 1]>(trsv_smem + BW * MT);  // [RS][MT+1] partial sums
-    double* s_dinv = trsv_smem + BW * MT + RS * (MT + 1);                             // [BW]
-    double* s_dval = s_dinv + BW;                                                     // [DE_MAX]
-    int32_t* s_drow = reinterpret_cast<int32_t*>(s_dval + DE_MAX);                    // [BW+1] block-relative offsets
-    int32_t* s_dsplit = s_drow + BW + 1;                                              // [BW]
-    int32_t* s_levptr = s_dsplit + BW;                                                // [BW+1]
-    uint16_t* s_levrows = reinterpret_cast<uint16_t*>(s_levptr + BW + 1);             // [BW]
-    uint16_t* s_didx = s_levrows + BW;                                                // [DE_MAX]
-    const int tid = threadIdx.x;
-    const int lane = tid % MT;  // mode within the tile
-    const int hw = tid / MT;    // half-warp = row slot
-    const int64_t mode = (int64_t)blockIdx.x * MT + lane;
+k_trsv_tree(double* __restrict__ w, int64_t ld, int64_t n, int rev, TriDev T) {
+    extern __shared__ __align__(16) unsigned char trsv_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = lane & (MT - 1), half = lane >> 4;  // mode within the tile, half-warp within the warp
+    const int hw = tid / MT;                          // half-warp within the CTA
+    const int64_t mode = (int64_t)blockIdx.x * MT + m;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+    const int hbase = half * MT;
     auto phys = [&](int64_t k) { return rev ? (n - 1 - k) : k; };
-    for (int b = 0; b < T.nblocks; ++b) {
-        const int64_t j0 = T.blk_start[b];
-        const int width = (int)(T.blk_start[b + 1] - j0);
-        const int lev0 = T.blk_info[4 * b], nlev = T.blk_info[4 * b + 1], dense = T.blk_info[4 * b + 2];
-        const int d0 = T.drow[j0];
-        const int nde = T.drow[j0 + width] - d0;
-        const bool staged = nde <= DE_MAX;
-        // ---- stage rows, per-row data and (if they fit) the diagonal-block entries -------------------------
-        for (int slot = hw; slot < width; slot += RS) Zs[slot][lane] = w[phys(j0 + slot) * ld + mode];
-        for (int k = tid; k < width; k += TRSV_THREADS) {
-            s_dinv[k] = T.dinv[j0 + k];
-            s_dsplit[k] = T.dsplit[j0 + k];
-            s_levrows[k] = T.levrows[j0 + k];
+
+    for (int st = 0; st < T.nsteps; ++st) {
+        const int t0 = T.step_ptr[st], t1 = T.step_ptr[st + 1], ns = T.step_nsmall[st];
+        // ================= small tasks: one warp each ======================================================
+        if (ns > 0) {
+            WarpSlice& S = reinterpret_cast<WarpSlice*>(trsv_raw)[warp];
+            for (int t = t0 + warp; t < t0 + ns; t += NWARP) {
+                const int b = T.tasks[t];
+                const int j0 = T.blk_start[b], len = T.blk_start[b + 1] - j0;
+                const int d0 = T.drow[j0], nde = T.drow[j0 + len] - d0;
+                for (int r = half; r < len; r += 2) S.z[r][m] = __ldcg(w + phys(j0 + r) * ld + mode);
+                if (lane <= len) S.drow[lane] = T.drow[j0 + lane] - d0;
+                if (lane < len) S.dinv[lane] = T.dinv[j0 + lane];
+                for (int e = lane; e < nde; e += 32) {
+                    S.dval[e] = T.dval[d0 + e];
+                    S.didx[e] = T.didx[d0 + e];
+                }
+                __syncwarp();
+                for (int r = 0; r < len; ++r) {
+                    const int e0 = S.drow[r], e1 = S.drow[r + 1];
+                    double dot = 0.0;
+                    for (int e = e0 + half; e < e1; e += 2) dot = fma(S.dval[e], S.z[S.didx[e]][m], dot);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+                    const double z = (S.z[r][m] - dot) * S.dinv[r];
+                    __syncwarp();
+                    if (half == 0) S.z[r][m] = z;
+                    __syncwarp();
+                }
+                for (int r = half; r < len; r += 2) w[phys(j0 + r) * ld + mode] = S.z[r][m];
+                const int s0 = T.segptr[b], s1 = T.segptr[b + 1];
+                for (int sg = s0 + half; sg < s1; sg += 2) {
+                    const int r = T.seg[3 * sg], p0 = T.seg[3 * sg + 1], sl = T.seg[3 * sg + 2];
+                    const double dot = segment_dot(T.val + p0, T.idx + p0, sl, j0, S.z, m, hmask, hbase);
+                    atomicAdd(w + phys(r) * ld + mode, -dot);
+                }
+                __syncwarp();
+            }
+            __threadfence();
+            __syncthreads();
         }
-        for (int k = tid; k <= width; k += TRSV_THREADS) s_drow[k] = T.drow[j0 + k] - d0;
-        for (int k = tid; k <= nlev; k += TRSV_THREADS) s_levptr[k] = T.levptr[lev0 + k];
-        if (staged)
-            for (int k = tid; k < nde; k += TRSV_THREADS) {
-                s_dval[k] = T.dval[d0 + k];
-                s_didx[k] = T.didx[d0 + k];
-            }
-        __syncthreads();
-        const double* gv = T.dval + d0;
-        const uint16_t* gi = T.didx + d0;
-        if (!dense) {
-            // ---- sparse diagonal block (subtree): level by level, one half-warp per row ---------------------
-            for (int l = 0; l < nlev; ++l) {
-                const int r0 = s_levptr[l], r1 = s_levptr[l + 1];
-                for (int q = r0 + hw; q < r1; q += RS) {
-                    const int rl = s_levrows[q];
-                    const int e0 = s_drow[rl], e1 = s_drow[rl + 1];
-                    const double dot = staged ? dot_rows(s_dval, s_didx, e0, e1, 1, Zs, lane) : dot_rows(gv, gi, e0, e1, 1, Zs, lane);
-                    Zs[rl][lane] = (Zs[rl][lane] - dot) * s_dinv[rl];
+        // ================= big tasks: whole CTA, one after the other =======================================
+        if (t1 > t0 + ns) {
+            BigSlice& B = *reinterpret_cast<BigSlice*>(trsv_raw);
+            for (int t = t0 + ns; t < t1; ++t) {
+                const int b = T.tasks[t];
+                const int j0 = T.blk_start[b], width = T.blk_start[b + 1] - j0;
+                const int d0 = T.drow[j0];
+                for (int slot = hw; slot < width; slot += RS) B.z[slot][m] = __ldcg(w + phys(j0 + slot) * ld + mode);
+                for (int k = tid; k < width; k += TRSV_THREADS) {
+                    B.dinv[k] = T.dinv[j0 + k];
+                    B.dsplit[k] = T.dsplit[j0 + k];
                 }
+                for (int k = tid; k <= width; k += TRSV_THREADS) B.drow[k] = T.drow[j0 + k] - d0;
                 __syncthreads();
-            }
-        } else {
-            // ---- dense diagonal block (separator chain): panels of PANEL rows --------------------------------
-            // (a) all half-warps: the part of every panel row that only needs rows left of the panel
-            // (b) half-warp 0: the PANEL x PANEL triangle, sequentially
-            constexpr int PER = RS / PANEL;  // half-warps per panel row
-            for (int p0 = 0; p0 < width; p0 += PANEL) {
-                const int rl = p0 + hw / PER, part = hw % PER;
-                double acc = 0.0;
-                if (rl < width) {
-                    const int e0 = s_drow[rl], e1 = e0 + s_dsplit[rl];
-                    acc = staged ? dot_rows(s_dval, s_didx, e0 + part, e1, PER, Zs, lane)
-                                 : dot_rows(gv, gi, e0 + part, e1, PER, Zs, lane);
-                }
-                red[hw][lane] = acc;
-                __syncthreads();
-                if (hw == 0) {
-                    const int pend = min(p0 + PANEL, width);
-                    for (int r = p0; r < pend; ++r) {
-                        double sum = Zs[r][lane];
+                const double* gv = T.dval + d0;
+                const uint16_t* gi = T.didx + d0;
+                for (int p0 = 0; p0 < width; p0 += PANEL) {
+                    // (a) part of every panel row left of the panel: PER half-warps per row, 16 entries per fetch
+                    const int rl = p0 + hw / PER, part = hw % PER;
+                    double acc = 0.0;
+                    if (rl < width) {
+                        const int e0 = B.drow[rl], nleft = B.dsplit[rl];
+                        // contiguous quarter of the row's left entries
+                        const int q0 = (int)(((int64_t)nleft * part) / PER), q1 = (int)(((int64_t)nleft * (part + 1)) / PER);
+                        double a0 = 0.0, a1 = 0.0;
+                        for (int p = q0; p < q1; p += MT) {
+                            const int cnt = min(MT, q1 - p);
+                            double myv = 0.0;
+                            int myi = 0;
+                            if (m < cnt) {
+                                myv = __ldg(gv + e0 + p + m);
+                                myi = __ldg(gi + e0 + p + m);
+                            }
 #pragma unroll
-                        for (int j = 0; j < PER; ++j) sum -= red[(r - p0) * PER + j][lane];
-                        const int e0 = s_drow[r] + s_dsplit[r], e1 = s_drow[r + 1];
-                        sum -= staged ? dot_rows(s_dval, s_didx, e0, e1, 1, Zs, lane) : dot_rows(gv, gi, e0, e1, 1, Zs, lane);
-                        Zs[r][lane] = sum * s_dinv[r];  // every lane only ever touches its own mode column
+                            for (int u = 0; u < MT; u += 2) {
+                                const double v0 = __shfl_sync(hmask, myv, hbase + u), v1 = __shfl_sync(hmask, myv, hbase + u + 1);
+                                const int i0 = __shfl_sync(hmask, myi, hbase + u), i1 = __shfl_sync(hmask, myi, hbase + u + 1);
+                                a0 = fma(v0, B.z[i0][m], a0);
+                                a1 = fma(v1, B.z[i1][m], a1);
+                            }
+                        }
+                        acc = a0 + a1;
                     }
+                    B.red[hw][m] = acc;
+                    // the panel triangle travels to shared memory meanwhile
+                    {
+                        const int r = p0 + tid / PANEL, c = tid % PANEL;  // threads 0..255
+                        if (tid < PANEL * PANEL && r < width) {
+                            const int e = B.drow[r] + B.dsplit[r] + c;
+                            const bool on = e < B.drow[r + 1];
+                            B.pval[tid] = on ? __ldg(gv + e) : 0.0;
+                            B.pidx[tid] = on ? __ldg(gi + e) : (uint16_t)r;  // zero weight: any valid row
+                        }
+                    }
+                    __syncthreads();
+                    // (b) the PANEL x PANEL triangle, rows in order, one half-warp (every lane owns one mode column)
+                    if (hw == 0) {
+                        const int pend = min(p0 + PANEL, width);
+                        for (int r = p0; r < pend; ++r) {
+                            double sum = B.z[r][m];
+#pragma unroll
+                            for (int j = 0; j < PER; ++j) sum -= B.red[(r - p0) * PER + j][m];
+                            const int ne = B.drow[r + 1] - B.drow[r] - B.dsplit[r];
+                            const double* pv = B.pval + (r - p0) * PANEL;
+                            const uint16_t* pi = B.pidx + (r - p0) * PANEL;
+                            double d0a = 0.0, d1a = 0.0;
+                            int c = 0;
+                            for (; c + 1 < ne; c += 2) {
+                                d0a = fma(pv[c], B.z[pi[c]][m], d0a);
+                                d1a = fma(pv[c + 1], B.z[pi[c + 1]][m], d1a);
+                            }
+                            if (c < ne) d0a = fma(pv[c], B.z[pi[c]][m], d0a);
+                            B.z[r][m] = (sum - (d0a + d1a)) * B.dinv[r];
+                        }
+                    }
+                    __syncthreads();
                 }
+                for (int slot = hw; slot < width; slot += RS) w[phys(j0 + slot) * ld + mode] = B.z[slot][m];
+                const int s0 = T.segptr[b], s1 = T.segptr[b + 1];
+                for (int sg = s0 + hw; sg < s1; sg += RS) {
+                    const int r = T.seg[3 * sg], p0 = T.seg[3 * sg + 1], sl = T.seg[3 * sg + 2];
+                    const double dot = segment_dot(T.val + p0, T.idx + p0, sl, j0, B.z, m, hmask, hbase);
+                    atomicAdd(w + phys(r) * ld + mode, -dot);
+                }
+                __threadfence();
                 __syncthreads();
             }
         }
-        // ---- finished rows back to memory, then push to all later rows --------------------------------------
-        for (int slot = hw; slot < width; slot += RS) w[phys(j0 + slot) * ld + mode] = Zs[slot][lane];
-        const int s0 = T.segptr[b], s1 = T.segptr[b + 1];
-        for (int sg = s0 + hw; sg < s1; sg += RS) {
-            const int r = T.seg[3 * sg], p0 = T.seg[3 * sg + 1], len = T.seg[3 * sg + 2];
-            const double* v = T.val + p0;
-            const int32_t* ix = T.idx + p0;
-            double* wr = w + phys(r) * ld + mode;
-            const double old = *wr;  // issued early: the latency hides behind the dot product
-            double a[4] = {0.0, 0.0, 0.0, 0.0};
-            int p = 0;
-            for (; p + 8 <= len; p += 8) {
-                double vv[8];
-                int ii[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    vv[u] = __ldg(v + p + u);
-                    ii[u] = __ldg(ix + p + u) - (int)j0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) a[u & 3] = fma(vv[u], Zs[ii[u]][lane], a[u & 3]);
-            }
-            for (; p < len; ++p) a[0] = fma(__ldg(v + p), Zs[__ldg(ix + p) - (int)j0][lane], a[0]);
-            *wr = old - ((a[0] + a[1]) + (a[2] + a[3]));
-        }
-        __syncthreads();
     }
 }
-
-constexpr size_t TRSV_SMEM = sizeof(double) * ((size_t)BW * MT + (size_t)RS * (MT + 1) + BW + DE_MAX) +
-                             sizeof(int32_t) * (3 * BW + 2) + sizeof(uint16_t) * (BW + DE_MAX) + 16;
 
 struct TriHost {
     std::vector<int64_t> ptr;
@@ -248,49 +302,41 @@ struct TriHost {
     std::vector<double> val, dinv;
 };
 
-int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, const std::vector<int32_t>& starts, TriDev& D) {
-    const int nblocks = (int)starts.size() - 1;
-    std::vector<int32_t> blk_of((size_t)n);
-    for (int b = 0; b < nblocks; ++b)
-        for (int32_t k = starts[b]; k < starts[b + 1]; ++k) blk_of[k] = b;
-    std::vector<int32_t> drow((size_t)n + 1, 0), dsplit((size_t)n, 0), blk_info((size_t)4 * nblocks, 0), levptr, segptr((size_t)nblocks + 1, 0), seg;
-    std::vector<uint16_t> didx, levrows((size_t)n);
+struct BlockDesc {
+    int32_t start, len;
+    int64_t step;  // tasks with equal step are independent; steps are processed in ascending order
+};
+
+int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDesc> blocks, TriDev& D) {
+    std::sort(blocks.begin(), blocks.end(), [](const BlockDesc& a, const BlockDesc& b) { return a.start < b.start; });
+    const int nblocks = (int)blocks.size();
+    std::vector<int32_t> starts((size_t)nblocks + 1), blk_of((size_t)n);
+    for (int b = 0; b < nblocks; ++b) {
+        starts[b] = blocks[b].start;
+        for (int32_t k = blocks[b].start; k < blocks[b].start + blocks[b].len; ++k) blk_of[k] = b;
+    }
+    starts[nblocks] = (int32_t)n;
+    std::vector<int32_t> drow((size_t)n + 1, 0), dsplit((size_t)n, 0), dcount((size_t)n, 0), segptr((size_t)nblocks + 1, 0), seg;
+    std::vector<uint16_t> didx;
     std::vector<double> dval;
-    std::vector<int32_t> lev((size_t)BW + 1), dcount((size_t)n, 0);
     for (int b = 0; b < nblocks; ++b) {
         const int64_t j0 = starts[b], j1 = starts[b + 1];
-        int nlev = 0;
         for (int64_t k = j0; k < j1; ++k) {
-            // diagonal-block part = trailing entries of the sorted row with column >= j0
             int64_t p = H.ptr[k + 1];
-            while (p > H.ptr[k] && H.idx[p - 1] >= j0) --p;
+            while (p > H.ptr[k] && H.idx[p - 1] >= j0) --p;  // trailing entries inside the own block
             dcount[k] = (int32_t)(H.ptr[k + 1] - p);
             const int64_t panel0 = j0 + ((k - j0) / PANEL) * PANEL;
-            int l = 0, split = 0;
+            int split = 0;
             for (int64_t q = p; q < H.ptr[k + 1]; ++q) {
                 didx.push_back((uint16_t)(H.idx[q] - j0));
                 dval.push_back(H.val[q]);
-                l = std::max(l, lev[H.idx[q] - j0] + 1);
                 if (H.idx[q] < panel0) ++split;
             }
             drow[k + 1] = (int32_t)didx.size();
             dsplit[k] = split;
-            lev[k - j0] = l;
-            nlev = std::max(nlev, l + 1);
         }
-        const int width = (int)(j1 - j0);
-        blk_info[4 * b] = (int32_t)levptr.size();
-        blk_info[4 * b + 1] = nlev;
-        blk_info[4 * b + 2] = (2 * nlev > width && width > PANEL) ? 1 : 0;  // chain-like block: panel algorithm
-        std::vector<int32_t> cnt((size_t)nlev + 1, 0);
-        for (int64_t k = j0; k < j1; ++k) cnt[lev[k - j0] + 1]++;
-        for (int l = 0; l < nlev; ++l) cnt[l + 1] += cnt[l];
-        for (int l = 0; l <= nlev; ++l) levptr.push_back(cnt[l]);
-        std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
-        for (int64_t k = j0; k < j1; ++k) levrows[j0 + fill[lev[k - j0]]++] = (uint16_t)(k - j0);
     }
-    // push segments: maximal runs of a row's entries inside one earlier block
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < 2; ++pass) {  // push segments: maximal runs of a row's entries inside one earlier block
         std::vector<int32_t> fill;
         if (pass == 1) {
             for (int b = 0; b < nblocks; ++b) segptr[b + 1] += segptr[b];
@@ -316,7 +362,28 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, const std::vector<i
             }
         }
     }
+    // schedule: steps in ascending order; inside a step the small tasks first
+    std::vector<int32_t> order((size_t)nblocks);
+    for (int b = 0; b < nblocks; ++b) order[b] = b;
+    auto small = [&](int b) { return blocks[b].len <= SMALL; };
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (blocks[a].step != blocks[b].step) return blocks[a].step < blocks[b].step;
+        if (small(a) != small(b)) return small(a);
+        return a < b;
+    });
+    std::vector<int32_t> step_ptr(1, 0), step_nsmall;
+    for (int k = 0; k < nblocks;) {
+        int k2 = k, nsm = 0;
+        while (k2 < nblocks && blocks[order[k2]].step == blocks[order[k]].step) {
+            nsm += small(order[k2]);
+            ++k2;
+        }
+        step_nsmall.push_back(nsm);
+        step_ptr.push_back(k2);
+        k = k2;
+    }
     D.nblocks = nblocks;
+    D.nsteps = (int)step_nsmall.size();
     int rc = 0;
     rc |= dev_upload(ctx, &D.idx, H.idx);
     rc |= dev_upload(ctx, &D.val, H.val);
@@ -328,9 +395,9 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, const std::vector<i
     rc |= dev_upload(ctx, &D.didx, didx);
     rc |= dev_upload(ctx, &D.dval, dval);
     rc |= dev_upload(ctx, &D.blk_start, starts);
-    rc |= dev_upload(ctx, &D.blk_info, blk_info);
-    rc |= dev_upload(ctx, &D.levptr, levptr);
-    rc |= dev_upload(ctx, &D.levrows, levrows);
+    rc |= dev_upload(ctx, &D.step_ptr, step_ptr);
+    rc |= dev_upload(ctx, &D.step_nsmall, step_nsmall);
+    rc |= dev_upload(ctx, &D.tasks, order);
     return rc;
 }
 
@@ -410,10 +477,14 @@ int precond_setup(asgfem_ctx* ctx) {
         }
     }
     rc = dev_upload(ctx, &P->d_perm, F.perm);
-    std::vector<int32_t> rstarts;
-    for (size_t k = F.block_start.size(); k-- > 0;) rstarts.push_back((int32_t)(n - F.block_start[k]));
-    rc |= upload_tri(ctx, fw, n, F.block_start, P->fwd);
-    rc |= upload_tri(ctx, bw, n, rstarts, P->bwd);
+    // forward: deepest tree level first, chunks of a separator in order; backward (reversed numbering): root first
+    std::vector<BlockDesc> fb, bb;
+    for (const BlockRec& b : F.blocks) {
+        fb.push_back({b.start, b.len, -(int64_t)b.depth * 4096 + b.chunk});
+        bb.push_back({(int32_t)(n - b.start - b.len), b.len, (int64_t)b.depth * 4096 + (b.nchunks - 1 - b.chunk)});
+    }
+    rc |= upload_tri(ctx, fw, n, fb, P->fwd);
+    rc |= upload_tri(ctx, bw, n, bb, P->bwd);
     if (rc) return rc;
     ASG_CUDA(ctx, cudaMalloc((void**)&P->d_work, sizeof(double) * (size_t)std::max<int64_t>(F.n, 1) * ctx->ld));
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -429,9 +500,9 @@ int precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
         k_gather_perm<<<blocks, 256, 0, ctx->stream>>>(r, P->d_work, P->d_perm, P->nred, ld);
         int tiles = (int)((ctx->N + MT - 1) / MT);
         const size_t smem = TRSV_SMEM;
-        ASG_CUDA(ctx, cudaFuncSetAttribute(k_trsv_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trsv_blocked<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 0, P->fwd);
-        k_trsv_blocked<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 1, P->bwd);
+        ASG_CUDA(ctx, cudaFuncSetAttribute(k_trsv_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_trsv_tree<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 0, P->fwd);
+        k_trsv_tree<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 1, P->bwd);
     }
     // z may alias r: boundary rows are zeroed first, interior rows are overwritten from the work vector
     k_zero_masked_rows<<<(unsigned)std::min<int64_t>(ctx->n, 148 * 8), 128, 0, ctx->stream>>>(z, ctx->d_bmask, ctx->n, ld);
