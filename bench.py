@@ -262,6 +262,26 @@ def run_gpu(args):
     elif rank == 0:
         out["e2e"] = {"value": None, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                       "note": "end-to-end leg is measured at N=1 only"}
+    # ---- PCG solve time (second half of the BASELINE metric): f = 1, zero start, atol = rtol = 1e-14 -------------
+    if rank == 0 and world == 1 and not args.no_pcg:
+        try:
+            t0 = time.perf_counter()
+            ctx.precond_setup()
+            t_fac = time.perf_counter() - t0
+            ctx.vec_zero(0)
+            b0 = fes.rhs()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st = ctx.pcg(b0, 0, 1e-14, 1e-14, 500)
+            torch.cuda.synchronize()
+            t_solve = time.perf_counter() - t0
+            out["pcg"] = {"solve_s": round(t_solve, 3), "iterations": int(st["niter"]), "solved": bool(st["solved"]),
+                          "factor_s_host": round(t_fac, 2), "ms_per_iteration": round(st["ms_iterations"] / max(st["niter"], 1), 2),
+                          "ms_operator_total": round(st["ms_apply"], 1), "ms_preconditioner_total": round(st["ms_precond"], 1),
+                          "residual": st["residual"],
+                          "note": "mean-preconditioned CG on the device (solve_primal! seam), K_0 factorised once on the host"}
+        except Exception as e:  # pragma: no cover
+            out["pcg"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_reference(A, ctx, fes, budget_s=15.0)
     if rank == 0:
@@ -325,10 +345,12 @@ def cpu_reference(A, ctx, fes, budget_s=15.0, steps=1, warmup=0):
                         p(cnu), p(cg), C.c_int64(len(bd)), p(bd), p(x), p(y), C.c_int(nthreads))
         return time.perf_counter() - t0, Ns + len(cm)
 
-    t_probe, sw_probe = run(max(nthreads, 8))  # probe: a handful of modes
-    per_sweep = t_probe / sw_probe
+    t_probe, sw_probe = run(max(2 * nthreads, 16))  # probe: a handful of modes
+    t_probe2, sw_probe2 = run(200)                  # second probe at a representative density of couplings
+    per_sweep = t_probe2 / sw_probe2
     target_sweeps = budget_s / per_sweep
-    Ns = int(np.clip(target_sweeps / 4.0, 32, 600))  # ~4 sweeps per mode in the sample region
+    full_sweeps_per_mode = sweeps_full / N_MODES
+    Ns = int(np.clip(target_sweeps / full_sweeps_per_mode, 64, N_MODES))
     ts = []
     for k in range(warmup + steps):
         t, sweeps = run(Ns)
@@ -379,6 +401,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="operator kernel: 0 auto, 1 gather, 2 tiled")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pcg", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":

@@ -458,9 +458,18 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y) {
     const int64_t nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
     ApplyPlan* P = ctx->plan;
     int variant = ctx->apply_variant;
-    // automatic choice (profiles/r01_*, 1M dofs x 2000 modes on B200): row-resident kernel 125 ms with DRAM traffic
-    // at the algorithmic minimum, gather kernel 129 ms with 2.6x the traffic, row-block tiled kernel 350 ms
-    if (variant == 0) variant = (ctx->n * ctx->N >= (1 << 16) && apply_rows_preferred(ctx)) ? 3 : 1;
+    // automatic choice (profiles/r01_*, 1M dofs x 2000 modes on B200): direction-major row-resident kernel 76 ms,
+    // dst-major row-resident kernel 125 ms (both with DRAM traffic at the algorithmic minimum), gather kernel 129 ms
+    // with 2.6x the traffic, row-block tiled kernel 350 ms
+    if (variant == 0) {
+        variant = 1;
+        if (ctx->n * ctx->N >= (1 << 16)) {
+            if (apply_dir_preferred(ctx))
+                variant = 4;
+            else if (apply_rows_preferred(ctx))
+                variant = 3;
+        }
+    }
     if (variant == 2 && !(P && P->usable))
         return fail(ctx, ASGFEM_ESTATE, "tiled operator plan not available for this pattern / multi-index set");
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));

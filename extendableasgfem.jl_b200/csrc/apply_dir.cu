@@ -172,7 +172,7 @@ int apply_dir_build(asgfem_ctx* ctx, bool owned) {
 }
 
 bool apply_dir_preferred(asgfem_ctx* ctx) {
-    if (!dp_of(ctx) && apply_dir_build(ctx, true)) return false;
+    if (!dp_of(ctx) && apply_dir_build(ctx, false)) return false;
     DirPlan* P = dp_of(ctx);
     return P && P->usable;
 }

@@ -122,7 +122,8 @@ int asgfem_vec_copy(asgfem_ctx* ctx, int32_t slot_src, int32_t slot_dst);
 int asgfem_apply(asgfem_ctx* ctx, int32_t slot_x, int32_t slot_y);
 int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax); /* host vectors, reference layout */
 /* selects the kernel: 0 = automatic, 1 = reference-order gather kernel, 2 = row-block tiled kernel,
- * 3 = row-resident kernel (all modes of the rows a dof touches staged in shared memory) */
+ * 3 = row-resident dst-major kernel, 4 = row-resident direction-major kernel (shared-memory atomics, run-to-run
+ * rounding-level differences), 5 = as 4 with warp-owned target ranges (deterministic) */
 int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant);
 /* duration of the last asgfem_apply kernel(s) in milliseconds, from CUDA events on the library's stream */
 int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms);
