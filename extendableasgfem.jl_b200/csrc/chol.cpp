@@ -371,6 +371,7 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
             else
                 x[Ci[p]] += Cx[p];
         }
+        const double d_orig = d;
         int64_t rp = F.Lp[k];
         for (int32_t q = top; q < n; ++q) {
             int32_t j = stack[q];
@@ -385,7 +386,8 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
             F.Lx[rp] = lkj;
             ++rp;
         }
-        if (!(d > 0.0) || !std::isfinite(d)) {
+        // a pivot that cancelled to rounding level means a (numerically) singular matrix, e.g. no Dirichlet dofs
+        if (!(d > 1.0e-12 * std::fabs(d_orig)) || !std::isfinite(d)) {
             err = "K_0 restricted to the interior dofs is not positive definite (pivot " + std::to_string(k) + ")";
             return ASGFEM_ENUMERIC;
         }

@@ -137,13 +137,22 @@ constexpr size_t TRSV_SMEM = sizeof(WarpSlice) * NWARP > sizeof(BigSlice) ? size
 __device__ __forceinline__ double segment_dot(const double* __restrict__ v, const int32_t* __restrict__ ix, int len, int j0,
                                               const double (*Z)[MT], int m, unsigned hmask, int hbase) {
     double a0 = 0.0, a1 = 0.0;
+    // software pipeline: the next 16 entries are in flight while the current 16 are consumed
+    double nv = 0.0;
+    int ni = 0;
+    if (m < len) {
+        nv = __ldg(v + m);
+        ni = __ldg(ix + m) - j0;
+    }
     for (int p = 0; p < len; p += MT) {
         const int cnt = min(MT, len - p);
-        double myv = 0.0;
-        int myi = 0;
-        if (m < cnt) {
-            myv = __ldg(v + p + m);
-            myi = __ldg(ix + p + m) - j0;
+        const double myv = nv;
+        const int myi = ni;
+        nv = 0.0;
+        ni = 0;
+        if (p + MT + m < len) {
+            nv = __ldg(v + p + MT + m);
+            ni = __ldg(ix + p + MT + m) - j0;
         }
         for (int u = 0; u < cnt; u += 2) {  // an odd tail reads the zero-weight entry of the next lane
             const double v0 = __shfl_sync(hmask, myv, hbase + u), v1 = __shfl_sync(hmask, myv, hbase + ((u + 1) & 15));

@@ -257,3 +257,115 @@ def test_estimator_matches_oracle(order, domain):
     if domain == "lshape":  # non-degenerate indicators (no exact ties) -> the marked set must be identical
         assert marked(gc[:, act].sum(axis=1)) == marked(ec[:, act].sum(axis=1))
     TB.ctx.close()
+
+
+def test_edge_cases_and_error_codes():
+    """Ragged / degenerate inputs and the error behaviour of the C ABI (negative codes + message, never a crash)."""
+    from asgfem_b200 import _lib
+    m = omesh.uniform_refine(omesh.grid_unitsquare(), 2)
+    C = ocoef.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=3)
+    # --- a single mode (no couplings at all): the operator is K_0, the solve is one Poisson problem ---------------
+    P1 = oproblem.build(m, 1, [[0]], opoly.LEGENDRE, C)
+    ctx = make_ctx(P1)
+    x = np.random.default_rng(0).standard_normal(P1.n)
+    S = osolver.SystemPrimal(P1.A0, P1.Am, P1.G, P1.bdofs, 1)
+    for variant in (1, 2, 3, 4, 5):
+        ctx.set_apply_variant(variant)
+        assert relerr(ctx.apply_host(x), S.mul(x)) < TOL_APPLY
+    sol = np.zeros(P1.n)
+    st = ctx.solve_primal_host(sol, P1.b0)
+    assert st["solved"] == 1 and st["niter"] <= 2  # the mean preconditioner is the exact inverse here
+    ref = np.zeros(P1.n)
+    osolver.solve_primal(ref, P1.A0, P1.Am, P1.b0, P1.G, 1, P1.bdofs)
+    assert relerr(sol, ref) < TOL_SOLVE
+    # --- non-zero incoming vector: the reference adds it to the right-hand side (b = deepcopy(sol); b[1] += b0,
+    #     solvers_poisson_primal.jl:149-150) and uses it as warm start; the oracle does the same ---------------------
+    warm = 0.1 * np.random.default_rng(1).standard_normal(P1.n)
+    warm[P1.bdofs] = 0
+    sol_w, ref_w = warm.copy(), warm.copy()
+    ctx.solve_primal_host(sol_w, P1.b0)
+    osolver.solve_primal(ref_w, P1.A0, P1.Am, P1.b0, P1.G, 1, P1.bdofs)
+    assert relerr(sol_w, ref_w) < TOL_SOLVE
+    # --- call-order and argument errors --------------------------------------------------------------------------
+    with pytest.raises(_lib.AsgfemError) as e:
+        ctx.apply(0, 0)
+    assert e.value.code == -1
+    with pytest.raises(_lib.AsgfemError) as e:
+        ctx.set_stiffness(9, np.zeros(3))
+    assert e.value.code == -1
+    with pytest.raises(_lib.AsgfemError) as e:
+        ctx.set_bdofs(np.array([0]))  # 0 is not a valid 1-based dof
+    assert e.value.code == -1
+    ctx.close()
+    fresh = A.Context()
+    with pytest.raises(_lib.AsgfemError) as e:
+        fresh.vec_alloc(1)
+    assert e.value.code == -2
+    fresh.set_multiindices(A.LEGENDRE, np.array([[0, 0], [1, 0], [0, 1]], dtype=np.int64))
+    with pytest.raises(_lib.AsgfemError) as e:
+        fresh.set_multiindices(A.LEGENDRE, np.array([[0, -1]], dtype=np.int64))
+    assert e.value.code == -1
+    fresh.close()
+    # --- multi-indices that couple in a direction without a stiffness matrix (maxlength > length(Am)) -----------------
+    P2 = oproblem.build(m, 1, [[0, 0], [1, 0], [0, 1]], opoly.LEGENDRE, C)
+    ctx = A.Context()
+    ctx.set_multiindices(P2.family, np.array(P2.multi_indices, dtype=np.int64))
+    A0 = sp.csc_matrix(P2.A0)
+    A0.sort_indices()
+    ctx.set_pattern_csc(P2.n, A0.indptr.astype(np.int64) + 1, A0.indices.astype(np.int64) + 1)
+    ctx.set_num_stiffness(1)  # only K_0, K_1 although direction 2 is coupled
+    ctx.set_stiffness(0, A0.data)
+    ctx.vec_alloc(2)
+    with pytest.raises(_lib.AsgfemError) as e:
+        ctx.apply(0, 1)
+    assert e.value.code == -1 and "direction" in str(e.value)
+    # --- no Dirichlet dofs: K_0 is singular -> the factorisation must report it, not crash ----------------------------
+    ctx.set_num_stiffness(2)
+    for mm, Am in enumerate([P2.A0] + P2.Am):
+        Am = sp.csc_matrix(Am)
+        Am.sort_indices()
+        ctx.set_stiffness(mm, Am.data)
+    ctx.set_bdofs(np.zeros(0, dtype=np.int64))
+    with pytest.raises(_lib.AsgfemError) as e:
+        ctx.precond_setup()
+    assert e.value.code == -5
+    ctx.close()
+
+
+def test_operator_properties_p2_hermite_at_scale():
+    """P2 space (rows up to 19+ entries), Hermite couplings, N > one shared-memory tile: symmetry <x, A y> = <A x, y>
+    of the Dirichlet-reduced operator and agreement of all kernels."""
+    g = A.uniform_refine(A.grid_lshape(), 5)
+    fes = A.FESpace(g, 2)
+    modes = A.graded_lex_multiindices(6, 400)
+    TB = A.TensorizedBasis(A.HermitePolynomials, modes)
+    sol = A.SGFEVector(fes, TB)
+    A.setup_device_problem(sol, A.StochasticCoefficientCosinus(tau=0.3, decay=2, mean=1, maxm=6))
+    ctx = TB.ctx
+    ctx.vec_alloc(5)
+    n, N = fes.ndofs, len(modes)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(n * N)
+    y = rng.standard_normal(n * N)
+    x.reshape(N, n)[:, fes.bdofs] = 0
+    y.reshape(N, n)[:, fes.bdofs] = 0
+    ctx.vec_upload(0, x)
+    ctx.vec_upload(1, y)
+    ref = None
+    for variant in (1, 2, 3, 4, 5):
+        ctx.set_apply_variant(variant)
+        try:
+            ctx.apply(0, 2)
+        except Exception as e:  # a kernel may decline a pattern it cannot hold; it must say so
+            assert "plan not available" in str(e)
+            continue
+        ctx.apply(1, 3)
+        xAy, yAx = ctx.vec_dot(0, 3), ctx.vec_dot(1, 2)
+        assert abs(xAy - yAx) <= 1e-12 * abs(xAy)
+        out = ctx.vec_download(2)
+        if ref is None:
+            ref = out
+        else:
+            assert relerr(out, ref) < TOL_APPLY
+    assert ref is not None
+    ctx.close()
