@@ -18,6 +18,7 @@
 // The backward sweep L^T z = y is the same algorithm on the reversed numbering k -> n-1-k with the tree walked from
 // the root down.  Work vectors live in elimination order (W[k,:] <-> dof perm[k]).
 #include <algorithm>
+#include <array>
 
 #include "common.h"
 
@@ -30,12 +31,13 @@ constexpr int RS = TRSV_THREADS / MT;  // half-warps per CTA
 constexpr int BW = 256;                // max rows of a big task
 constexpr int SMALL = 24;              // max rows of a warp task (= leaf size of the dissection)
 constexpr int SMALL_DE = SMALL * (SMALL - 1) / 2;  // max entries of its diagonal block
+constexpr int SMALL_SEG = 56;           // push segments of a warp task staged in shared memory (more are read from L2)
 constexpr int PANEL = 16;
 constexpr int PER = RS / PANEL;        // half-warps per panel row
 
 struct TriDev {  // one triangular system in its own (forward) numbering
-    int32_t* idx = nullptr;        // CSR of the strict lower triangle (only entries outside a row's own block are used)
-    double* val = nullptr;
+    uint16_t* idx = nullptr;       // push entries, stored source block after source block, segment after segment:
+    double* val = nullptr;         // block-local source row and value (a task streams one contiguous range)
     int32_t* segptr = nullptr;     // per block: range of push segments
     int32_t* seg = nullptr;        // per segment: target row, first nonzero, length
     double* dinv = nullptr;        // per row
@@ -118,6 +120,7 @@ struct WarpSlice {
     double dval[SMALL_DE];
     double dinv[SMALL];
     int32_t drow[SMALL + 1];
+    int32_t seg[3 * SMALL_SEG];
     uint16_t didx[SMALL_DE + 2];
 };
 // shared memory of the big-task phase (aliases the warp slices; the phases are separated by block barriers)
@@ -125,43 +128,68 @@ struct BigSlice {
     double z[BW][MT];
     double red[RS][MT + 1];
     double dinv[BW];
-    double pval[PANEL * PANEL];
+    double ptri[PANEL * PANEL];
     int32_t drow[BW + 1];
     int32_t dsplit[BW];
-    uint16_t pidx[PANEL * PANEL];
 };
 constexpr size_t TRSV_SMEM = sizeof(WarpSlice) * NWARP > sizeof(BigSlice) ? sizeof(WarpSlice) * NWARP : sizeof(BigSlice);
 
-// dot product of one push segment with the task rows in shared memory, by one half-warp: its 16 lanes fetch 16
-// entries at once (coalesced) and hand them round with shuffles, so that one L2 latency covers 16 entries
-__device__ __forceinline__ double segment_dot(const double* __restrict__ v, const int32_t* __restrict__ ix, int len, int j0,
+// Push segments of one half-warp.  The 16 lanes fetch 16 (value, source row) entries at once (coalesced, the entries of
+// a task are one contiguous stream) and hand them round with shuffles.  Software pipeline across chunks AND segments:
+// while one chunk is consumed the next one - of the same segment or the first of the half-warp's next segment - is in
+// flight, so the L2 latency is paid once per half-warp instead of once per segment.
+struct SegDesc {
+    int r, p0, len;
+};
+// Each half-warp walks its own segments; the first chunk of the next segment is prefetched during the last chunk of
+// the current one.  (Walking the two halves of a warp in lockstep to keep the warp converged was measured: no gain.)
+template <class GetDesc, class Emit>
+__device__ __forceinline__ void push_segments(int first, int end, int stride, GetDesc get_desc, Emit emit,
+                                              const double* __restrict__ val, const uint16_t* __restrict__ idx,
                                               const double (*Z)[MT], int m, unsigned hmask, int hbase) {
-    double a0 = 0.0, a1 = 0.0;
-    // software pipeline: the next 16 entries are in flight while the current 16 are consumed
+    int nmine = first < end ? (end - first + stride - 1) / stride : 0;
+    const int nit = nmine;
+    if (nit == 0) return;
+    SegDesc cur{0, 0, 0};
+    if (nmine > 0) cur = get_desc(first);
     double nv = 0.0;
     int ni = 0;
-    if (m < len) {
-        nv = __ldg(v + m);
-        ni = __ldg(ix + m) - j0;
+    if (m < cur.len) {
+        nv = __ldg(val + cur.p0 + m);
+        ni = __ldg(idx + cur.p0 + m);
     }
-    for (int p = 0; p < len; p += MT) {
-        const int cnt = min(MT, len - p);
-        const double myv = nv;
-        const int myi = ni;
-        nv = 0.0;
-        ni = 0;
-        if (p + MT + m < len) {
-            nv = __ldg(v + p + MT + m);
-            ni = __ldg(ix + p + MT + m) - j0;
+    for (int it = 0; it < nit; ++it) {
+        const int sgn = first + (it + 1) * stride;
+        const bool has_next = sgn < end;
+        SegDesc nxt{0, 0, 0};
+        if (has_next) nxt = get_desc(sgn);
+        const int lenmax = cur.len;
+        double a0 = 0.0, a1 = 0.0;
+        for (int p = 0; p < lenmax; p += MT) {
+            const double myv = nv;
+            const int myi = ni;
+            nv = 0.0;
+            ni = 0;
+            if (p + MT < cur.len) {
+                if (p + MT + m < cur.len) {
+                    nv = __ldg(val + cur.p0 + p + MT + m);
+                    ni = __ldg(idx + cur.p0 + p + MT + m);
+                }
+            } else if (p + MT >= lenmax && m < nxt.len) {  // last chunk of the pair: first chunk of the next segment
+                nv = __ldg(val + nxt.p0 + m);
+                ni = __ldg(idx + nxt.p0 + m);
+            }
+            const int cnt = min(MT, lenmax - p);
+            for (int u = 0; u < cnt; u += 2) {  // entries past the own length carry v = 0, i = 0
+                const double v0 = __shfl_sync(hmask, myv, hbase + u), v1 = __shfl_sync(hmask, myv, hbase + ((u + 1) & 15));
+                const int i0 = __shfl_sync(hmask, myi, hbase + u), i1 = __shfl_sync(hmask, myi, hbase + ((u + 1) & 15));
+                a0 = fma(v0, Z[i0][m], a0);
+                a1 = fma(v1, Z[i1][m], a1);
+            }
         }
-        for (int u = 0; u < cnt; u += 2) {  // an odd tail reads the zero-weight entry of the next lane
-            const double v0 = __shfl_sync(hmask, myv, hbase + u), v1 = __shfl_sync(hmask, myv, hbase + ((u + 1) & 15));
-            const int i0 = __shfl_sync(hmask, myi, hbase + u), i1 = __shfl_sync(hmask, myi, hbase + ((u + 1) & 15));
-            a0 = fma(v0, Z[i0][m], a0);
-            a1 = fma(u + 1 < cnt ? v1 : 0.0, Z[i1][m], a1);
-        }
+        if (it < nmine) emit(cur.r, a0 + a1);
+        cur = nxt;
     }
-    return a0 + a1;
 }
 
 __global__ void __launch_bounds__(TRSV_THREADS, 1)
@@ -191,11 +219,19 @@ k_trsv_tree(double* __restrict__ w, int64_t ld, int64_t n, int rev, TriDev T) {
                     S.dval[e] = T.dval[d0 + e];
                     S.didx[e] = T.didx[d0 + e];
                 }
+                const int s0 = T.segptr[b], s1 = T.segptr[b + 1];
+                for (int e = lane; e < 3 * min(s1 - s0, SMALL_SEG); e += 32) S.seg[e] = T.seg[3 * s0 + e];
                 __syncwarp();
                 for (int r = 0; r < len; ++r) {
                     const int e0 = S.drow[r], e1 = S.drow[r + 1];
-                    double dot = 0.0;
-                    for (int e = e0 + half; e < e1; e += 2) dot = fma(S.dval[e], S.z[S.didx[e]][m], dot);
+                    double dota = 0.0, dotb = 0.0;
+                    int e = e0 + half;
+                    for (; e + 2 < e1; e += 4) {
+                        dota = fma(S.dval[e], S.z[S.didx[e]][m], dota);
+                        dotb = fma(S.dval[e + 2], S.z[S.didx[e + 2]][m], dotb);
+                    }
+                    if (e < e1) dota = fma(S.dval[e], S.z[S.didx[e]][m], dota);
+                    double dot = dota + dotb;
                     dot += __shfl_xor_sync(0xffffffffu, dot, 16);
                     const double z = (S.z[r][m] - dot) * S.dinv[r];
                     __syncwarp();
@@ -203,12 +239,14 @@ k_trsv_tree(double* __restrict__ w, int64_t ld, int64_t n, int rev, TriDev T) {
                     __syncwarp();
                 }
                 for (int r = half; r < len; r += 2) w[phys(j0 + r) * ld + mode] = S.z[r][m];
-                const int s0 = T.segptr[b], s1 = T.segptr[b + 1];
-                for (int sg = s0 + half; sg < s1; sg += 2) {
-                    const int r = T.seg[3 * sg], p0 = T.seg[3 * sg + 1], sl = T.seg[3 * sg + 2];
-                    const double dot = segment_dot(T.val + p0, T.idx + p0, sl, j0, S.z, m, hmask, hbase);
-                    atomicAdd(w + phys(r) * ld + mode, -dot);
-                }
+                push_segments(
+                    s0 + half, s1, 2,
+                    [&](int sg) {
+                        const int q = sg - s0;
+                        return q < SMALL_SEG ? SegDesc{S.seg[3 * q], S.seg[3 * q + 1], S.seg[3 * q + 2]}
+                                             : SegDesc{T.seg[3 * sg], T.seg[3 * sg + 1], T.seg[3 * sg + 2]};
+                    },
+                    [&](int r, double dot) { atomicAdd(w + phys(r) * ld + mode, -dot); }, T.val, T.idx, S.z, m, hmask, hbase);
                 __syncwarp();
             }
             __threadfence();
@@ -260,44 +298,40 @@ k_trsv_tree(double* __restrict__ w, int64_t ld, int64_t n, int rev, TriDev T) {
                     B.red[hw][m] = acc;
                     // the panel triangle travels to shared memory meanwhile
                     {
-                        const int r = p0 + tid / PANEL, c = tid % PANEL;  // threads 0..255
+                        // dense PANEL x PANEL table ptri[row][col] = L[p0+row, p0+col] (zero where absent)
+                        if (tid < PANEL * PANEL) B.ptri[tid] = 0.0;
+                        __syncwarp();
+                        const int r = p0 + tid / PANEL, c = tid % PANEL;  // threads 0..255 = warps 0..7
                         if (tid < PANEL * PANEL && r < width) {
                             const int e = B.drow[r] + B.dsplit[r] + c;
-                            const bool on = e < B.drow[r + 1];
-                            B.pval[tid] = on ? __ldg(gv + e) : 0.0;
-                            B.pidx[tid] = on ? __ldg(gi + e) : (uint16_t)r;  // zero weight: any valid row
+                            if (e < B.drow[r + 1]) B.ptri[(tid / PANEL) * PANEL + (__ldg(gi + e) - p0)] = __ldg(gv + e);
                         }
                     }
                     __syncthreads();
-                    // (b) the PANEL x PANEL triangle, rows in order, one half-warp (every lane owns one mode column)
-                    if (hw == 0) {
+                    // (b) the PANEL x PANEL triangle, right-looking: half-warp h owns panel row p0+h and keeps its running
+                    //     sum in a register; row after row the owner finalises z_r, everybody below subtracts L[r',r] z_r
+                    {
                         const int pend = min(p0 + PANEL, width);
-                        for (int r = p0; r < pend; ++r) {
-                            double sum = B.z[r][m];
+                        const int myr = p0 + hw;  // only half-warps 0..PANEL-1 own a row
+                        double sum = 0.0;
+                        if (hw < PANEL && myr < pend) {
+                            sum = B.z[myr][m];
 #pragma unroll
-                            for (int j = 0; j < PER; ++j) sum -= B.red[(r - p0) * PER + j][m];
-                            const int ne = B.drow[r + 1] - B.drow[r] - B.dsplit[r];
-                            const double* pv = B.pval + (r - p0) * PANEL;
-                            const uint16_t* pi = B.pidx + (r - p0) * PANEL;
-                            double d0a = 0.0, d1a = 0.0;
-                            int c = 0;
-                            for (; c + 1 < ne; c += 2) {
-                                d0a = fma(pv[c], B.z[pi[c]][m], d0a);
-                                d1a = fma(pv[c + 1], B.z[pi[c + 1]][m], d1a);
-                            }
-                            if (c < ne) d0a = fma(pv[c], B.z[pi[c]][m], d0a);
-                            B.z[r][m] = (sum - (d0a + d1a)) * B.dinv[r];
+                            for (int j = 0; j < PER; ++j) sum -= B.red[hw * PER + j][m];
+                        }
+                        for (int r = p0; r < pend; ++r) {
+                            if (myr == r && hw < PANEL) B.z[r][m] = sum * B.dinv[r];
+                            __syncthreads();
+                            if (hw < PANEL && myr > r && myr < pend) sum = fma(-B.ptri[hw * PANEL + (r - p0)], B.z[r][m], sum);
                         }
                     }
                     __syncthreads();
                 }
                 for (int slot = hw; slot < width; slot += RS) w[phys(j0 + slot) * ld + mode] = B.z[slot][m];
                 const int s0 = T.segptr[b], s1 = T.segptr[b + 1];
-                for (int sg = s0 + hw; sg < s1; sg += RS) {
-                    const int r = T.seg[3 * sg], p0 = T.seg[3 * sg + 1], sl = T.seg[3 * sg + 2];
-                    const double dot = segment_dot(T.val + p0, T.idx + p0, sl, j0, B.z, m, hmask, hbase);
-                    atomicAdd(w + phys(r) * ld + mode, -dot);
-                }
+                push_segments(
+                    s0 + hw, s1, RS, [&](int sg) { return SegDesc{T.seg[3 * sg], T.seg[3 * sg + 1], T.seg[3 * sg + 2]}; },
+                    [&](int r, double dot) { atomicAdd(w + phys(r) * ld + mode, -dot); }, T.val, T.idx, B.z, m, hmask, hbase);
                 __threadfence();
                 __syncthreads();
             }
@@ -345,12 +379,21 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDe
             dsplit[k] = split;
         }
     }
+    std::vector<int32_t> segent((size_t)nblocks + 1, 0), entfill;
+    std::vector<uint16_t> pidx;
+    std::vector<double> pval;
     for (int pass = 0; pass < 2; ++pass) {  // push segments: maximal runs of a row's entries inside one earlier block
         std::vector<int32_t> fill;
         if (pass == 1) {
-            for (int b = 0; b < nblocks; ++b) segptr[b + 1] += segptr[b];
+            for (int b = 0; b < nblocks; ++b) {
+                segptr[b + 1] += segptr[b];
+                segent[b + 1] += segent[b];
+            }
             seg.resize((size_t)3 * segptr[nblocks]);
             fill.assign(segptr.begin(), segptr.end() - 1);
+            entfill.assign(segent.begin(), segent.end() - 1);
+            pidx.resize((size_t)segent[nblocks]);
+            pval.resize((size_t)segent[nblocks]);
         }
         for (int64_t k = 0; k < n; ++k) {
             const int64_t pend = H.ptr[k + 1] - dcount[k];
@@ -361,15 +404,29 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDe
                 while (q < pend && blk_of[H.idx[q]] == b) ++q;
                 if (pass == 0) {
                     segptr[b + 1]++;
+                    segent[b + 1] += (int32_t)(q - p);
                 } else {
                     int32_t at = fill[b]++;
+                    int32_t eo = entfill[b];
+                    entfill[b] += (int32_t)(q - p);
                     seg[3 * (size_t)at] = (int32_t)k;
-                    seg[3 * (size_t)at + 1] = (int32_t)p;
+                    seg[3 * (size_t)at + 1] = eo;  // offset into the block-major entry arrays
                     seg[3 * (size_t)at + 2] = (int32_t)(q - p);
+                    for (int64_t e = p; e < q; ++e) {
+                        pidx[(size_t)eo + (size_t)(e - p)] = (uint16_t)(H.idx[e] - starts[b]);
+                        pval[(size_t)eo + (size_t)(e - p)] = H.val[e];
+                    }
                 }
                 p = q;
             }
         }
+    }
+    for (int b = 0; b < nblocks; ++b) {  // partners in a warp get segments of similar length
+        std::vector<std::array<int32_t, 3>> tmp;
+        for (int32_t q = segptr[b]; q < segptr[b + 1]; ++q) tmp.push_back({seg[3 * (size_t)q], seg[3 * (size_t)q + 1], seg[3 * (size_t)q + 2]});
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::array<int32_t, 3>& x, const std::array<int32_t, 3>& y) { return x[2] > y[2]; });
+        for (size_t k = 0; k < tmp.size(); ++k)
+            for (int c = 0; c < 3; ++c) seg[3 * ((size_t)segptr[b] + k) + c] = tmp[k][c];
     }
     // schedule: steps in ascending order; inside a step the small tasks first
     std::vector<int32_t> order((size_t)nblocks);
@@ -394,8 +451,8 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDe
     D.nblocks = nblocks;
     D.nsteps = (int)step_nsmall.size();
     int rc = 0;
-    rc |= dev_upload(ctx, &D.idx, H.idx);
-    rc |= dev_upload(ctx, &D.val, H.val);
+    rc |= dev_upload(ctx, &D.idx, pidx);
+    rc |= dev_upload(ctx, &D.val, pval);
     rc |= dev_upload(ctx, &D.segptr, segptr);
     rc |= dev_upload(ctx, &D.seg, seg);
     rc |= dev_upload(ctx, &D.dinv, H.dinv);
