@@ -586,6 +586,9 @@ extern "C" int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax) {
     int rc = ensure_ready_for_apply(ctx);
     if (rc) return rc;
     if ((rc = ensure_work_slots(ctx, 2))) return rc;
+    // upload, operator and download overlap block by block unless the kernel cannot work on row ranges
+    if (ctx->apply_variant != 2 && ctx->n_owned < 0 && x != Ax)
+        return apply_host_pipelined(ctx, x, Ax, ctx->slots[0], ctx->slots[1]);
     if ((rc = vec_to_device_layout(ctx, x, ctx->slots[0]))) return rc;
     if ((rc = apply_launch(ctx, ctx->slots[0], ctx->slots[1]))) return rc;
     return vec_to_host_layout(ctx, ctx->slots[1], Ax);

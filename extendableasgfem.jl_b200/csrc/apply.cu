@@ -29,11 +29,11 @@ namespace asgfem {
 // variant 1: gather kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_apply_gather(int64_t nrows, int64_t N, int64_t ld, int64_t nnz, const int64_t* __restrict__ rowptr,
+k_apply_gather(int64_t row0, int64_t nrows, int64_t N, int64_t ld, int64_t nnz, const int64_t* __restrict__ rowptr,
                const int32_t* __restrict__ col, const double* __restrict__ vals, const int32_t* __restrict__ cptr,
                const int32_t* __restrict__ cm, const int32_t* __restrict__ cnu, const double* __restrict__ cg,
                const uint8_t* __restrict__ bmask, const double* __restrict__ x, double* __restrict__ y) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    int64_t i = row0 + (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
     int64_t mu = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (i >= nrows || mu >= ld) return;
     double acc = 0.0;
@@ -454,8 +454,15 @@ static int launch_tiled(asgfem_ctx* ctx, const TiledArgs& a, size_t smem) {
     return 0;
 }
 
-int apply_launch(asgfem_ctx* ctx, const double* x, double* y) {
-    const int64_t nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
+int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1) {
+    const int64_t nrows_all = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
+    const bool ranged = r1 >= 0;
+    if (!ranged) {
+        r0 = 0;
+        r1 = nrows_all;
+    }
+    r1 = std::min(r1, nrows_all);
+    const int64_t nrows = r1;
     ApplyPlan* P = ctx->plan;
     int variant = ctx->apply_variant;
     // automatic choice (profiles/r01_*, 1M dofs x 2000 modes on B200): direction-major row-resident kernel 76 ms,
@@ -472,19 +479,21 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y) {
     }
     if (variant == 2 && !(P && P->usable))
         return fail(ctx, ASGFEM_ESTATE, "tiled operator plan not available for this pattern / multi-index set");
+    if (variant == 2 && ranged) return fail(ctx, ASGFEM_ESTATE, "row ranges are not available for the tiled operator");
+    if (r1 <= r0) return 0;
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (variant == 4 || variant == 5) {
-        int rc = apply_dir_launch(ctx, x, y, variant == 5);
+        int rc = apply_dir_launch(ctx, x, y, variant == 5, r0, r1);
         if (rc) return rc;
     } else if (variant == 3) {
-        int rc = apply_rows_launch(ctx, x, y);
+        int rc = apply_rows_launch(ctx, x, y, r0, r1);
         if (rc) return rc;
     } else if (variant == 1) {
         int bx = (int)std::min<int64_t>(128, ((ctx->ld + 31) / 32) * 32);
         int by = 256 / bx;
         dim3 block(bx, by);
-        dim3 grid((unsigned)((nrows + by - 1) / by), (unsigned)((ctx->ld + bx - 1) / bx));
-        k_apply_gather<<<grid, block, 0, ctx->stream>>>(nrows, ctx->N, ctx->ld, ctx->nnz, ctx->d_rowptr, ctx->d_col,
+        dim3 grid((unsigned)((r1 - r0 + by - 1) / by), (unsigned)((ctx->ld + bx - 1) / bx));
+        k_apply_gather<<<grid, block, 0, ctx->stream>>>(r0, nrows, ctx->N, ctx->ld, ctx->nnz, ctx->d_rowptr, ctx->d_col,
                                                         ctx->d_vals, ctx->d_cptr, ctx->d_cm, ctx->d_cnu, ctx->d_cg,
                                                         ctx->d_bmask, x, y);
         ASG_CUDA(ctx, cudaGetLastError());

@@ -178,7 +178,7 @@ bool apply_dir_preferred(asgfem_ctx* ctx) {
 }
 
 struct DirArgs {
-    int64_t nrows, ld, nnz;
+    int64_t row0, nrows, ld, nnz;  // rows [row0, nrows)
     int N, Np, M, Mp, nslot, nunit_words;
     size_t nwords;
     const int64_t* rowptr;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(DIR_THREADS, 1) k_apply_dir(DirArgs a) {
     const unsigned gt_base = (unsigned)__cvta_generic_to_shared(gt);
     const unsigned xstride = (unsigned)a.Np * 8u;
 
-    for (int64_t row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+    for (int64_t row = a.row0 + blockIdx.x; row < a.nrows; row += gridDim.x) {
         const int64_t rp = a.rowptr[row];
         const int len = (int)(a.rowptr[row + 1] - rp);
         const bool masked = a.bmask[row] != 0;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(DIR_THREADS, 1) k_apply_dir(DirArgs a) {
     }
 }
 
-int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned) {
+int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned, int64_t r0, int64_t r1) {
     DirPlan* P = dp_of(ctx);
     if (!P || P->owned != owned) {
         int rc = apply_dir_build(ctx, owned);
@@ -312,7 +312,8 @@ int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned) {
     }
     if (!P->usable) return fail(ctx, ASGFEM_ESTATE, "direction-major operator plan not available (too many modes / row too long)");
     DirArgs a;
-    a.nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
+    a.row0 = r0;
+    a.nrows = r1;
     a.ld = ctx->ld;
     a.nnz = ctx->nnz;
     a.N = (int)ctx->N;
@@ -331,7 +332,8 @@ int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned) {
     a.gtab = P->d_gtab;
     a.x = x;
     a.y = y;
-    int grid = (int)std::min<int64_t>(a.nrows, 148);
+    if (r1 <= r0) return 0;
+    int grid = (int)std::min<int64_t>(r1 - r0, 148);
 #define LAUNCH_DIR(KWV)                                                                                              \
     do {                                                                                                             \
         if (owned) {                                                                                                 \

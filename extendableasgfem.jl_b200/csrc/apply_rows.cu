@@ -211,7 +211,7 @@ bool apply_rows_preferred(asgfem_ctx* ctx) {
 }
 
 struct RowArgs {
-    int64_t nrows, ld, nnz;
+    int64_t row0, nrows, ld, nnz;  // rows [row0, nrows)
     int M, Mp, Sp, KW, ntiles;
     const int64_t* rowptr;
     const int32_t* col;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_apply_rows(RowArgs a) {
     if (META_SMEM)
         for (size_t k = tid; k < a.meta_words; k += ROWS_THREADS) ms[k] = a.meta[k];
 
-    for (int64_t row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+    for (int64_t row = a.row0 + blockIdx.x; row < a.nrows; row += gridDim.x) {
         const int64_t rp = a.rowptr[row];
         const int len = (int)(a.rowptr[row + 1] - rp);
         const bool masked = a.bmask[row] != 0;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_apply_rows(RowArgs a) {
     }
 }
 
-int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y) {
+int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1) {
     RowPlan* P = rp_of(ctx);
     if (!P) {
         int rc = apply_rows_build(ctx);
@@ -336,7 +336,8 @@ int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y) {
     }
     if (!P->usable) return fail(ctx, ASGFEM_ESTATE, "row-resident operator plan not available (row too long or too many KLE terms)");
     RowArgs a;
-    a.nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
+    a.row0 = r0;
+    a.nrows = r1;
     a.ld = ctx->ld;
     a.nnz = ctx->nnz;
     a.M = ctx->M;
@@ -359,7 +360,8 @@ int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y) {
     a.gtab = P->d_gtab;
     a.x = x;
     a.y = y;
-    int grid = (int)std::min<int64_t>(a.nrows, 148);
+    if (r1 <= r0) return 0;
+    int grid = (int)std::min<int64_t>(r1 - r0, 148);
     if (P->meta_smem) {
         ASG_CUDA(ctx, cudaFuncSetAttribute(k_apply_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         k_apply_rows<true><<<grid, ROWS_THREADS, P->smem_bytes, ctx->stream>>>(a);

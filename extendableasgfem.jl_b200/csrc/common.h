@@ -165,19 +165,21 @@ int dev_upload(asgfem_ctx* ctx, T** dptr, const std::vector<T>& h) {
 // apply.cu
 int apply_build_plan(asgfem_ctx* ctx);
 void apply_free_plan(asgfem_ctx* ctx);
-int apply_launch(asgfem_ctx* ctx, const double* x, double* y);
+// rows [r0, r1) of Y (r1 < 0: all rows); row ranges are not available for the tiled variant 2
+int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0 = 0, int64_t r1 = -1);
 // apply_rows.cu
 int apply_rows_build(asgfem_ctx* ctx);
 void apply_rows_free(asgfem_ctx* ctx);
-int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y);
+int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
 bool apply_rows_preferred(asgfem_ctx* ctx);
 // apply_dir.cu
 int apply_dir_build(asgfem_ctx* ctx, bool owned);
 void apply_dir_free(asgfem_ctx* ctx);
-int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned);
+int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned, int64_t r0, int64_t r1);
 bool apply_dir_preferred(asgfem_ctx* ctx);
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
+int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* dX, double* dY);
 int vec_to_host_layout(asgfem_ctx* ctx, const double* dvec, double* host);
 int vec_dot(asgfem_ctx* ctx, const double* a, const double* b, int64_t nrows, double* out);
 int vec_fill_random(asgfem_ctx* ctx, double* d, uint64_t seed);

@@ -5,6 +5,7 @@
 // (src/sgfevector.jl:97-101: block mu contiguous = column-major n x N); conversion happens here, on the
 // device, chunk by chunk through a staging buffer.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -207,6 +208,89 @@ int vec_to_host_layout(asgfem_ctx* ctx, const double* dvec, double* host) {
     }
     ASG_CUDA(ctx, cudaGetLastError());
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Y = A X with X and Y on the host (the mul! seam): row blocks are pipelined over three streams so that the
+// upload of block b+1, the operator on block b and the download of block b-1 overlap (PCIe is full duplex).  A row
+// block may be applied as soon as every X row its columns reference has arrived, i.e. once the block holding its largest
+// column index is on the device (blocks are uploaded in ascending order).
+int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* dX, double* dY) {
+    const int64_t n = ctx->n, N = ctx->N, ld = ctx->ld;
+    int64_t RB = (256ll << 20) / (8 * std::max<int64_t>(N, 1));
+    RB = std::max<int64_t>(1024, RB / 1024 * 1024);
+    if (const char* e = std::getenv("ASGFEM_HOST_BLOCK_ROWS")) {  // test hook: force many small blocks
+        int64_t v = std::atoll(e);
+        if (v >= 32) RB = v / 32 * 32;
+    }
+    const int64_t nb = (n + RB - 1) / RB;
+    std::vector<int64_t> dep((size_t)nb, 0);
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t i0 = b * RB, i1 = std::min(n, i0 + RB);
+        int32_t maxc = (int32_t)i0;
+        for (int64_t p = ctx->h_rowptr[i0]; p < ctx->h_rowptr[i1]; ++p) maxc = std::max(maxc, ctx->h_col[p]);
+        dep[b] = maxc / RB;
+    }
+    struct Pipe {
+        cudaStream_t sH = nullptr, sD = nullptr;
+        cudaEvent_t copied[2] = {}, in_free[2] = {}, yready[2] = {}, out_free[2] = {};
+        double *in[2] = {}, *out[2] = {};
+        ~Pipe() {
+            for (int k = 0; k < 2; ++k) {
+                if (copied[k]) cudaEventDestroy(copied[k]);
+                if (in_free[k]) cudaEventDestroy(in_free[k]);
+                if (yready[k]) cudaEventDestroy(yready[k]);
+                if (out_free[k]) cudaEventDestroy(out_free[k]);
+                if (in[k]) cudaFree(in[k]);
+                if (out[k]) cudaFree(out[k]);
+            }
+            if (sH) cudaStreamDestroy(sH);
+            if (sD) cudaStreamDestroy(sD);
+        }
+    } P;
+    ASG_CUDA(ctx, cudaStreamCreateWithFlags(&P.sH, cudaStreamNonBlocking));
+    ASG_CUDA(ctx, cudaStreamCreateWithFlags(&P.sD, cudaStreamNonBlocking));
+    const size_t stage_bytes = sizeof(double) * (size_t)std::min(RB, n) * (size_t)N;
+    for (int k = 0; k < 2; ++k) {
+        ASG_CUDA(ctx, cudaEventCreateWithFlags(&P.copied[k], cudaEventDisableTiming));
+        ASG_CUDA(ctx, cudaEventCreateWithFlags(&P.in_free[k], cudaEventDisableTiming));
+        ASG_CUDA(ctx, cudaEventCreateWithFlags(&P.yready[k], cudaEventDisableTiming));
+        ASG_CUDA(ctx, cudaEventCreateWithFlags(&P.out_free[k], cudaEventDisableTiming));
+        ASG_CUDA(ctx, cudaMalloc((void**)&P.in[k], stage_bytes));
+        ASG_CUDA(ctx, cudaMalloc((void**)&P.out[k], stage_bytes));
+    }
+    if (ld != N) ASG_CUDA(ctx, cudaMemsetAsync(dX, 0, sizeof(double) * n * ld, ctx->stream));
+    auto block_grid = [&](int64_t rows) { return dim3((unsigned)((rows + TP - 1) / TP), (unsigned)((N + TP - 1) / TP)); };
+    int64_t next_apply = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int s = (int)(b & 1);
+        const int64_t i0 = b * RB, rows = std::min(n, i0 + RB) - i0;
+        if (b >= 2) ASG_CUDA(ctx, cudaStreamWaitEvent(P.sH, P.in_free[s], 0));
+        ASG_CUDA(ctx, cudaMemcpy2DAsync(P.in[s], sizeof(double) * rows, x + i0, sizeof(double) * n, sizeof(double) * rows,
+                                        (size_t)N, cudaMemcpyHostToDevice, P.sH));
+        ASG_CUDA(ctx, cudaEventRecord(P.copied[s], P.sH));
+        ASG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, P.copied[s], 0));
+        k_chunk_to_device<<<block_grid(rows), dim3(TP, 8), 0, ctx->stream>>>(P.in[s], dX + i0 * ld, rows, ld, 0, (int)N);
+        ASG_CUDA(ctx, cudaEventRecord(P.in_free[s], ctx->stream));
+        while (next_apply < nb && dep[next_apply] <= b) {
+            const int64_t a = next_apply++;
+            const int t = (int)(a & 1);
+            const int64_t a0 = a * RB, arows = std::min(n, a0 + RB) - a0;
+            int rc = apply_launch(ctx, dX, dY, a0, a0 + arows);
+            if (rc) return rc;
+            if (a >= 2) ASG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, P.out_free[t], 0));
+            k_chunk_to_host<<<block_grid(arows), dim3(TP, 8), 0, ctx->stream>>>(dY + a0 * ld, P.out[t], arows, ld, 0, (int)N);
+            ASG_CUDA(ctx, cudaEventRecord(P.yready[t], ctx->stream));
+            ASG_CUDA(ctx, cudaStreamWaitEvent(P.sD, P.yready[t], 0));
+            ASG_CUDA(ctx, cudaMemcpy2DAsync(Ax + a0, sizeof(double) * n, P.out[t], sizeof(double) * arows,
+                                            sizeof(double) * arows, (size_t)N, cudaMemcpyDeviceToHost, P.sD));
+            ASG_CUDA(ctx, cudaEventRecord(P.out_free[t], P.sD));
+        }
+    }
+    ASG_CUDA(ctx, cudaGetLastError());
+    ASG_CUDA(ctx, cudaStreamSynchronize(P.sH));
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ASG_CUDA(ctx, cudaStreamSynchronize(P.sD));
     return 0;
 }
 

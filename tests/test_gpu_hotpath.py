@@ -105,6 +105,24 @@ def test_apply_matches_oracle(c1, mid, variant):
         ctx.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
+def test_apply_host_pipelined_row_blocks(c1, mid, variant, monkeypatch):
+    """The mul! seam overlaps upload / operator / download block by block; small blocks force the multi-block
+    schedule, including rows whose columns live in much later blocks (P2 edge dofs of config 1)."""
+    for P, rb in ((c1, 64), (mid, 256), (mid, 96)):
+        monkeypatch.setenv("ASGFEM_HOST_BLOCK_ROWS", str(rb))
+        ctx = make_ctx(P)
+        ctx.set_apply_variant(variant)
+        S = osolver.SystemPrimal(P.A0, P.Am, P.G, P.bdofs, P.N)
+        x = np.random.default_rng(rb).standard_normal(P.n * P.N)
+        got = ctx.apply_host(x)
+        assert relerr(got, S.mul(x)) < TOL_APPLY
+        ctx.vec_upload(0, x)
+        ctx.apply(0, 1)
+        assert np.array_equal(got, ctx.vec_download(1)) or variant in (0, 4)  # atomics: order varies at rounding level
+        ctx.close()
+
+
 @pytest.mark.parametrize("family", [opoly.LEGENDRE, opoly.HERMITE])
 def test_apply_random_sets_lshape(family):
     m = omesh.uniform_refine(omesh.grid_lshape(), 3)
