@@ -123,7 +123,8 @@ int asgfem_apply(asgfem_ctx* ctx, int32_t slot_x, int32_t slot_y);
 int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax); /* host vectors, reference layout */
 /* selects the kernel: 0 = automatic, 1 = reference-order gather kernel, 2 = row-block tiled kernel,
  * 3 = row-resident dst-major kernel, 4 = row-resident direction-major kernel (shared-memory atomics, run-to-run
- * rounding-level differences), 5 = as 4 with warp-owned target ranges (deterministic) */
+ * rounding-level differences), 5 = as 4 with warp-owned target ranges (deterministic), 6 = mode-stationary kernel
+ * (operands in registers, partial products exchanged through shared memory; deterministic) */
 int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant);
 /* duration of the last asgfem_apply kernel(s) in milliseconds, from CUDA events on the library's stream */
 int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms);
