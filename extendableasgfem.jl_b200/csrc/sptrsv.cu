@@ -17,6 +17,16 @@
 //     half-warp from shared memory, pushes by all 64 half-warps.
 // The backward sweep L^T z = y is the same algorithm on the reversed numbering k -> n-1-k with the tree walked from
 // the root down.  Work vectors live in elimination order (W[k,:] <-> dof perm[k]).
+//
+// BOTTOM FOREST (k_small_sweep): the subtrees of the dissection tree that consist of blocks of <= 32 rows only
+// (leaves and the small separators right above them: 98 % of the blocks, a third of the flops) are handled by a
+// dense supernodal kernel instead.  The columns of one block share their row structure, so block T owns a DENSE panel
+// P = L[A(T), T] (A(T): the rows below the block that it touches) and the explicit inverse of its diagonal triangle:
+//   forward   z_T = inv(L_TT) w_T,  W[A(T)] -= P z_T      (one fp64 RED per target row and mode)
+//   backward  y_T = inv(L_TT)^T (z_T - P^T y_A(T))         (pull: no atomics)
+// A warp takes a block; its two half-warps hold the 16 modes of the tile, the block's <= 32 values per mode live in
+// registers, L is read with warp-uniform 16-byte loads (no column indices, no shuffles, no shared memory).  The
+// forest runs before (forward) / after (backward) the tree kernel above, which keeps the remaining top of the tree.
 #include <algorithm>
 #include <array>
 
@@ -52,10 +62,28 @@ struct TriDev {  // one triangular system in its own (forward) numbering
     int nblocks = 0, nsteps = 0;
 };
 
+// One block of the bottom forest (32 bytes, read with two uniform 16-byte loads).  Its factor data is ONE contiguous
+// record (16-byte aligned) so that a single bulk copy (TMA) moves a piece of it into shared memory:
+//   [ inverse diagonal triangle, rows packed in pairs of equal even length ]
+//   [ chunk 0 ][ chunk 1 ] ...     chunk = [ int32 target rows, padded to arB bytes ][ panel rows, even(w) doubles each ]
+// every chunk holds R = small_chunk_rows(w, buffer size) panel rows (the last one fewer).
+struct SmallBlk {
+    int32_t j0, w, nA, pad0;
+    int64_t rec_off, pad1;  // byte offset of the record
+};
+struct SmallDev {
+    SmallBlk* blk = nullptr;
+    int32_t* tasks = nullptr;     // block ids, launch after launch (forward order: deepest tree level first)
+    unsigned char* rec = nullptr;  // records
+    int nblocks = 0, nsteps = 0;
+};
+
 struct PrecondPlan {
     int64_t nred = 0;
     int32_t* d_perm = nullptr;
     TriDev fwd, bwd;
+    SmallDev small;
+    std::vector<std::array<int, 3>> small_launches;  // (t0, t1, width class), forward order
     double* d_work = nullptr;  // nred x ld
     int64_t lnz = 0;
 };
@@ -73,6 +101,12 @@ void precond_free(asgfem_ctx* ctx) {
     if (!P) return;
     free_tri(P->fwd);
     free_tri(P->bwd);
+    {
+        SmallDev& S = P->small;
+        void* ptrs[] = {S.blk, S.tasks, S.rec};
+        for (void* q : ptrs)
+            if (q) cudaFree(q);
+    }
     if (P->d_perm) cudaFree(P->d_perm);
     if (P->d_work) cudaFree(P->d_work);
     delete P;
@@ -339,6 +373,301 @@ k_trsv_tree(double* __restrict__ w, int64_t ld, int64_t n, int rev, TriDev T) {
     }
 }
 
+
+// =====================================================================================================================
+// bottom forest: dense supernodal warp tasks
+// =====================================================================================================================
+constexpr int SMALL_W = 32;        // widest block of the bottom forest
+constexpr int SWEEP_THREADS = 512;
+constexpr int SWEEP_SMEM = 224 * 1024;  // two staging buffers per warp
+
+// offset of row r in the pair-packed inverse triangle: rows 2i and 2i+1 both hold 2i+2 entries
+__host__ __device__ __forceinline__ int inv_row_off(int r) {
+    const int i = r >> 1;
+    return 2 * i * (i + 1) + (r & 1) * (2 * i + 2);
+}
+// record geometry for a block of width w staged through buffers of `buf` bytes
+struct SmallGeom {
+    int wp, invB, R, arB, chunkB;  // even(w), bytes of the inverse, rows per chunk, bytes of a chunk's row list, full chunk
+};
+__host__ __device__ __forceinline__ SmallGeom small_geom(int w, int buf) {
+    SmallGeom g;
+    g.wp = (w + 1) & ~1;
+    g.invB = inv_row_off(g.wp) * 8;
+    g.R = ((buf - 16) / (g.wp * 8 + 4)) & ~1;  // even, so that the pairing of rows over the half-warps stays aligned
+    g.arB = (4 * g.R + 15) & ~15;
+    g.chunkB = g.arB + g.R * g.wp * 8;
+    return g;
+}
+__host__ __device__ __forceinline__ int small_buf_bytes(int wclass) { return wclass <= 24 ? SWEEP_SMEM / (2 * 16) : SWEEP_SMEM / (2 * 8); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ SmallBlk load_blk(const SmallDev& S, int t) {
+    const int4* bp = reinterpret_cast<const int4*>(S.blk + S.tasks[t]);
+    const int4 q0 = __ldg(bp), q1 = __ldg(bp + 1);
+    SmallBlk b;
+    b.j0 = q0.x, b.w = q0.y, b.nA = q0.z, b.pad0 = 0;
+    b.rec_off = ((int64_t)(uint32_t)q1.y << 32) | (uint32_t)q1.x;
+    b.pad1 = 0;
+    return b;
+}
+
+// Per-warp two-stage pipeline of bulk copies (cp.async.bulk + mbarrier): while the warp works on one piece of a record,
+// the next piece - of the same task or of the warp's next task - is already on its way into the other buffer.  The factor
+// data is streamed from HBM exactly once per CTA with no reuse; without staging every warp-uniform load paid the full
+// memory latency in a dependent chain (profiles/r01_small_*).
+template <bool BWD>
+struct SmallPipe {
+    const SmallDev& S;
+    unsigned char* buf;   // this warp's two buffers
+    unsigned bar32;       // shared address of this warp's two mbarriers
+    int bufB, t1, stride, lane;
+    // producer position: piece `pc` of task `pt` (forward: -1 = inverse, then chunks 0..; backward: chunks, then -1)
+    int pt, pc, pnch;
+    SmallBlk pb;
+    SmallGeom pg;
+    unsigned k = 0, phase = 0;  // pieces acquired so far, parity bits of the two barriers
+
+    __device__ __forceinline__ void set_task(int t) {
+        pt = t;
+        if (t < t1) {
+            pb = load_blk(S, t);
+            pg = small_geom(pb.w, bufB);
+            pnch = (pb.nA + pg.R - 1) / pg.R;
+            pc = BWD ? (pnch > 0 ? 0 : -1) : -1;
+        }
+    }
+    __device__ __forceinline__ void advance() {
+        if (BWD) {
+            if (pc == -1)
+                set_task(pt + stride);
+            else
+                pc = pc + 1 < pnch ? pc + 1 : -1;
+        } else {
+            if (pc + 1 < pnch)
+                ++pc;
+            else
+                set_task(pt + stride);
+        }
+    }
+    __device__ __forceinline__ void issue(unsigned stage) {  // current producer piece -> buffer `stage`
+        if (pt >= t1) return;
+        const unsigned char* src = S.rec + pb.rec_off;
+        int bytes;
+        if (pc < 0) {
+            bytes = pg.invB;
+        } else {
+            src += pg.invB + (int64_t)pc * pg.chunkB;
+            const int r = min(pg.R, pb.nA - pc * pg.R);
+            bytes = pg.arB + r * pg.wp * 8;
+        }
+        if (lane == 0) {
+            const unsigned bar = bar32 + 8u * stage;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)stage * bufB);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src), "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+        advance();
+    }
+    __device__ __forceinline__ void start(int t0w) {
+        set_task(t0w);
+        issue(0);
+    }
+    // waits for the next piece in sequence and returns its buffer; the piece after it is put in flight first
+    __device__ __forceinline__ const unsigned char* acquire() {
+        const unsigned stage = k & 1u;
+        __syncwarp();  // every lane is done with the other buffer
+        issue(stage ^ 1u);
+        const unsigned bar = bar32 + 8u * stage, par = (phase >> stage) & 1u;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+            "r"(par)
+            : "memory");
+        phase ^= 1u << stage;
+        ++k;
+        return buf + (size_t)stage * bufB;
+    }
+};
+
+__device__ __forceinline__ double2 lds_d2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// forward task: z_T = inv(L_TT) w_T, then W[A(T)] -= P z_T
+template <int WMAX>
+__device__ __forceinline__ void small_fwd(const SmallBlk b, SmallPipe<false>& pipe, double* __restrict__ W, int64_t ld, int64_t mode,
+                                          int half) {
+    const int w = b.w;
+    double* wt = W + (int64_t)b.j0 * ld + mode;
+    double v[WMAX];
+#pragma unroll
+    for (int c = 0; c < WMAX; ++c) v[c] = c < w ? __ldcg(wt + (int64_t)c * ld) : 0.0;
+    const double* inv = reinterpret_cast<const double*>(pipe.acquire());
+    // rows from the bottom up: row r needs v[c <= r] only, so z overwrites v in place (one register array)
+#pragma unroll
+    for (int i = WMAX / 2 - 1; i >= 0; --i) {
+        if (2 * i < w) {  // warp-uniform
+            const double* row = inv + 2 * i * (i + 1) + half * (2 * i + 2);  // half h computes row 2i + h
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int q = 0; q <= i; ++q) {
+                const double2 l = lds_d2(row + 2 * q);
+                a0 = fma(l.x, v[2 * q], a0);
+                a1 = fma(l.y, v[2 * q + 1], a1);
+            }
+            const double mine = a0 + a1;
+            const double other = __shfl_xor_sync(0xffffffffu, mine, 16);
+            v[2 * i] = half ? other : mine;
+            v[2 * i + 1] = half ? mine : other;
+            if (2 * i + half < w) wt[(int64_t)(2 * i + half) * ld] = mine;
+        }
+    }
+    double(&z)[WMAX] = v;
+    const SmallGeom g = small_geom(w, pipe.bufB);
+    for (int a0r = 0; a0r < b.nA; a0r += g.R) {
+        const unsigned char* ch = pipe.acquire();
+        const int32_t* ar = reinterpret_cast<const int32_t*>(ch);
+        const double* P = reinterpret_cast<const double*>(ch + g.arB);
+        const int nr = min(g.R, b.nA - a0r);
+        for (int p = 0; p < nr; p += 2) {
+            const bool ok = p + half < nr;
+            const int a = ok ? p + half : nr - 1;
+            const int64_t r = ar[a];
+            const double* prow = P + a * g.wp;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int q = 0; q < WMAX / 2; q += 2) {
+                if (2 * q < w) {
+                    const double2 l = lds_d2(prow + 2 * q);
+                    s0 = fma(l.x, z[2 * q], s0);
+                    s1 = fma(l.y, z[2 * q + 1], s1);
+                }
+                if (2 * q + 2 < w) {
+                    const double2 l = lds_d2(prow + 2 * q + 2);
+                    s2 = fma(l.x, z[2 * q + 2], s2);
+                    s3 = fma(l.y, z[2 * q + 3], s3);
+                }
+            }
+            if (ok) atomicAdd(W + r * ld + mode, -((s0 + s1) + (s2 + s3)));  // sibling blocks share ancestor rows
+        }
+    }
+}
+
+// backward task: y_T = inv(L_TT)^T (z_T - P^T y_A(T))
+template <int WMAX>
+__device__ __forceinline__ void small_bwd(const SmallBlk b, SmallPipe<true>& pipe, double* __restrict__ W, int64_t ld, int64_t mode,
+                                          int half) {
+    const int w = b.w;
+    double* wt = W + (int64_t)b.j0 * ld + mode;
+    double acc[WMAX];
+#pragma unroll
+    for (int c = 0; c < WMAX; ++c) acc[c] = 0.0;
+    const SmallGeom g = small_geom(w, pipe.bufB);
+    for (int a0r = 0; a0r < b.nA; a0r += g.R) {
+        const unsigned char* ch = pipe.acquire();
+        const int32_t* ar = reinterpret_cast<const int32_t*>(ch);
+        const double* P = reinterpret_cast<const double*>(ch + g.arB);
+        const int nr = min(g.R, b.nA - a0r);
+        for (int a = pipe.lane; a < nr; a += 32) prefetch_l2(W + (int64_t)ar[a] * ld + (mode & ~(int64_t)(MT - 1)));
+        for (int p = 0; p < nr; p += 2) {
+            const bool ok = p + half < nr;
+            const int a = ok ? p + half : nr - 1;
+            const int64_t r = ar[a];
+            const double y = ok ? __ldcg(W + r * ld + mode) : 0.0;
+            const double* prow = P + a * g.wp;
+#pragma unroll
+            for (int q = 0; q < WMAX / 2; ++q) {
+                if (2 * q < w) {
+                    const double2 l = lds_d2(prow + 2 * q);
+                    acc[2 * q] = fma(l.x, y, acc[2 * q]);
+                    acc[2 * q + 1] = fma(l.y, y, acc[2 * q + 1]);
+                }
+            }
+        }
+    }
+    double(&t)[WMAX] = acc;  // t = z_T - P^T y_A, in place
+#pragma unroll
+    for (int c = 0; c < WMAX; ++c) {
+        const double own = c < w ? __ldcg(wt + (int64_t)c * ld) : 0.0;
+        t[c] = own - (acc[c] + __shfl_xor_sync(0xffffffffu, acc[c], 16));
+    }
+    const double* inv = reinterpret_cast<const double*>(pipe.acquire());
+#pragma unroll
+    for (int i = 0; i < WMAX / 2; ++i) {
+        if (2 * i < w) {
+            // y_r = sum_{c >= r} inv[c][r] t[c], r = 2i + half; inv[2i][2i+1] is a stored zero
+            const double* col = inv + 2 * i + half;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = i; j < WMAX / 2; ++j) {
+                if (2 * j < w) {
+                    a0 = fma(col[2 * j * (j + 1)], t[2 * j], a0);
+                    a1 = fma(col[2 * j * (j + 1) + 2 * j + 2], t[2 * j + 1], a1);
+                }
+            }
+            if (2 * i + half < w) wt[(int64_t)(2 * i + half) * ld] = a0 + a1;
+        }
+    }
+}
+
+// one launch per (tree level, width class): tasks [t0, t1) are independent; the launch boundary orders the levels
+template <int WMAX, bool BWD>
+__global__ void __launch_bounds__(WMAX <= 24 ? SWEEP_THREADS : SWEEP_THREADS / 2, 1)
+k_small_step(double* __restrict__ W, int64_t ld, SmallDev S, int t0, int t1) {
+    extern __shared__ __align__(128) unsigned char sweep_smem[];
+    __shared__ __align__(8) unsigned long long sweep_bars[2 * (SWEEP_THREADS / 32)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int half = lane >> 4;
+    const int64_t mode0 = (int64_t)blockIdx.x * MT, mode = mode0 + (lane & (MT - 1));
+    const int bufB = small_buf_bytes(WMAX);
+    if (lane == 0) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * warp);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    SmallPipe<BWD> pipe{S, sweep_smem + (size_t)warp * 2 * bufB, (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * warp),
+                        bufB,  t1, nwarps, lane};
+    pipe.start(t0 + warp);
+    for (int t = t0 + warp; t < t1; t += nwarps) {
+        const SmallBlk b = load_blk(S, t);
+        if (t + nwarps < t1) {  // rows of W of the warp's next task -> L2
+            const SmallBlk nb = load_blk(S, t + nwarps);
+            if (lane < nb.w) prefetch_l2(W + (int64_t)(nb.j0 + lane) * ld + mode0);
+        }
+        if constexpr (BWD)
+            small_bwd<WMAX>(b, pipe, W, ld, mode, half);
+        else
+            small_fwd<WMAX>(b, pipe, W, ld, mode, half);
+    }
+}
+
+struct SmallLaunch {
+    int t0, t1, wmax;
+};
+
+template <int WMAX, bool BWD>
+static void launch_small_k(const SmallLaunch& L, int tiles, cudaStream_t st, double* W, int64_t ld, const SmallDev& S) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_small_step<WMAX, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
+        configured = true;
+    }
+    k_small_step<WMAX, BWD><<<tiles, WMAX <= 24 ? SWEEP_THREADS : SWEEP_THREADS / 2, SWEEP_SMEM, st>>>(W, ld, S, L.t0, L.t1);
+}
+
+template <bool BWD>
+static void launch_small(const SmallLaunch& L, int tiles, cudaStream_t st, double* W, int64_t ld, const SmallDev& S) {
+    switch (L.wmax) {
+        case 8: launch_small_k<8, BWD>(L, tiles, st, W, ld, S); break;
+        case 16: launch_small_k<16, BWD>(L, tiles, st, W, ld, S); break;
+        case 24: launch_small_k<24, BWD>(L, tiles, st, W, ld, S); break;
+        default: launch_small_k<32, BWD>(L, tiles, st, W, ld, S); break;
+    }
+}
+
 struct TriHost {
     std::vector<int64_t> ptr;
     std::vector<int32_t> idx;
@@ -350,7 +679,10 @@ struct BlockDesc {
     int64_t step;  // tasks with equal step are independent; steps are processed in ascending order
 };
 
-int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDesc> blocks, TriDev& D) {
+// `top[k] != 0`: row k (numbering of this system) belongs to the part of the tree that this kernel handles; blocks and
+// push segments that involve other rows are left out (they belong to the bottom forest)
+int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDesc> blocks, const std::vector<uint8_t>& top,
+               TriDev& D) {
     std::sort(blocks.begin(), blocks.end(), [](const BlockDesc& a, const BlockDesc& b) { return a.start < b.start; });
     const int nblocks = (int)blocks.size();
     std::vector<int32_t> starts((size_t)nblocks + 1), blk_of((size_t)n);
@@ -402,6 +734,10 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDe
                 const int b = blk_of[H.idx[p]];
                 int64_t q = p + 1;
                 while (q < pend && blk_of[H.idx[q]] == b) ++q;
+                if (!top[(size_t)k] || !top[(size_t)starts[b]]) {
+                    p = q;
+                    continue;
+                }
                 if (pass == 0) {
                     segptr[b + 1]++;
                     segent[b + 1] += (int32_t)(q - p);
@@ -429,8 +765,10 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDe
             for (int c = 0; c < 3; ++c) seg[3 * ((size_t)segptr[b] + k) + c] = tmp[k][c];
     }
     // schedule: steps in ascending order; inside a step the small tasks first
-    std::vector<int32_t> order((size_t)nblocks);
-    for (int b = 0; b < nblocks; ++b) order[b] = b;
+    std::vector<int32_t> order;
+    for (int b = 0; b < nblocks; ++b)
+        if (top[(size_t)starts[b]]) order.push_back(b);
+    const int ntasks = (int)order.size();
     auto small = [&](int b) { return blocks[b].len <= SMALL; };
     std::sort(order.begin(), order.end(), [&](int a, int b) {
         if (blocks[a].step != blocks[b].step) return blocks[a].step < blocks[b].step;
@@ -438,9 +776,9 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDe
         return a < b;
     });
     std::vector<int32_t> step_ptr(1, 0), step_nsmall;
-    for (int k = 0; k < nblocks;) {
+    for (int k = 0; k < ntasks;) {
         int k2 = k, nsm = 0;
-        while (k2 < nblocks && blocks[order[k2]].step == blocks[order[k]].step) {
+        while (k2 < ntasks && blocks[order[k2]].step == blocks[order[k]].step) {
             nsm += small(order[k2]);
             ++k2;
         }
@@ -465,6 +803,126 @@ int upload_tri(asgfem_ctx* ctx, const TriHost& H, int64_t n, std::vector<BlockDe
     rc |= dev_upload(ctx, &D.step_nsmall, step_nsmall);
     rc |= dev_upload(ctx, &D.tasks, order);
     return rc;
+}
+
+
+// Splits the dissection tree into the bottom forest (subtrees made of blocks of <= SMALL_W rows) and the top part, and
+// builds the dense panels / inverse triangles of the forest.  Lp/Li/Lx: rows of L; cptr/cidx/cval: columns of L with
+// ascending rows.  top[k] = 1 for rows that stay with the tree kernel.
+int build_small(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx,
+                const std::vector<double>& cval, std::vector<uint8_t>& top, SmallDev& D,
+                std::vector<std::array<int, 3>>& launches) {
+    const int64_t n = F.n;
+    const int nb = (int)F.blocks.size();
+    std::vector<int32_t> blk_of((size_t)n);
+    for (int b = 0; b < nb; ++b)
+        for (int32_t k = 0; k < F.blocks[b].len; ++k) blk_of[(size_t)F.blocks[b].start + k] = b;
+    // a block stays on top if it is wide or if a top block pushes into it (its sources must be done before it)
+    std::vector<uint8_t> btop((size_t)nb, 0);
+    for (int b = 0; b < nb; ++b) {  // blocks are sorted by start; targets always come later
+        if (F.blocks[b].len > SMALL_W) btop[b] = 1;
+        if (!btop[b]) continue;
+        const int64_t j0 = F.blocks[b].start, j1 = j0 + F.blocks[b].len;
+        for (int64_t c = j0; c < j1; ++c)
+            for (int64_t p = cptr[c]; p < cptr[c + 1]; ++p)
+                if (cidx[p] >= j1) btop[blk_of[(size_t)cidx[p]]] = 1;
+    }
+    top.assign((size_t)n, 0);
+    for (int64_t k = 0; k < n; ++k) top[(size_t)k] = btop[blk_of[(size_t)k]];
+
+    std::vector<SmallBlk> blk;
+    std::vector<int32_t> depth_of;
+    std::vector<unsigned char> rec;
+    std::vector<int32_t> mark((size_t)n, -1), list;
+    std::vector<double> Ld, X;
+    for (int b = 0; b < nb; ++b) {
+        if (btop[b]) continue;
+        const int32_t j0 = F.blocks[b].start, w = F.blocks[b].len;
+        const int wcl = w <= 8 ? 8 : (w <= 16 ? 16 : (w <= 24 ? 24 : 32));
+        const SmallGeom g = small_geom(w, small_buf_bytes(wcl));
+        const int wp = g.wp;
+        SmallBlk sb;
+        sb.j0 = j0;
+        sb.w = w;
+        sb.pad0 = 0;
+        sb.pad1 = 0;
+        // target rows A(T)
+        list.clear();
+        for (int32_t c = j0; c < j0 + w; ++c)
+            for (int64_t p = cptr[c]; p < cptr[c + 1]; ++p) {
+                const int32_t i = cidx[p];
+                if (i >= j0 + w && mark[(size_t)i] != b) {
+                    mark[(size_t)i] = b;
+                    list.push_back(i);
+                }
+            }
+        std::sort(list.begin(), list.end());
+        const int nA = (int)list.size(), nch = (nA + g.R - 1) / g.R;
+        sb.nA = nA;
+        sb.rec_off = (int64_t)rec.size();
+        size_t bytes = (size_t)g.invB;
+        for (int c = 0; c < nch; ++c) bytes += (size_t)g.arB + (size_t)std::min(g.R, nA - c * g.R) * wp * 8;
+        // intermediate chunks are full, so chunk c starts at invB + c * chunkB
+        rec.resize(rec.size() + bytes, 0);
+        unsigned char* base = rec.data() + sb.rec_off;
+        double* inv = reinterpret_cast<double*>(base);
+        for (size_t a = 0; a < list.size(); ++a) mark[(size_t)list[a]] = (int32_t)a;  // position in the panel
+        for (int a = 0; a < nA; ++a) {
+            unsigned char* ch = base + g.invB + (size_t)(a / g.R) * g.chunkB;
+            reinterpret_cast<int32_t*>(ch)[a % g.R] = list[(size_t)a];
+        }
+        for (int32_t c = j0; c < j0 + w; ++c)
+            for (int64_t p = cptr[c]; p < cptr[c + 1]; ++p) {
+                const int32_t i = cidx[p];
+                if (i < j0 + w) continue;
+                const int a = mark[(size_t)i];
+                unsigned char* ch = base + g.invB + (size_t)(a / g.R) * g.chunkB;
+                reinterpret_cast<double*>(ch + g.arB)[(size_t)(a % g.R) * wp + (size_t)(c - j0)] = cval[p];
+            }
+        for (int32_t i : list) mark[(size_t)i] = -1;
+        // inverse of the diagonal triangle
+        Ld.assign((size_t)w * w, 0.0);
+        for (int32_t r = 0; r < w; ++r) {
+            Ld[(size_t)r * w + r] = 1.0 / F.dinv[(size_t)j0 + r];
+            for (int64_t p = F.Lp[(size_t)j0 + r]; p < F.Lp[(size_t)j0 + r + 1]; ++p)
+                if (F.Li[p] >= j0) Ld[(size_t)r * w + (F.Li[p] - j0)] = F.Lx[p];
+        }
+        X.assign((size_t)w * w, 0.0);
+        for (int32_t j = 0; j < w; ++j) {
+            X[(size_t)j * w + j] = 1.0 / Ld[(size_t)j * w + j];
+            for (int32_t r = j + 1; r < w; ++r) {
+                double sum = 0.0;
+                for (int32_t k = j; k < r; ++k) sum += Ld[(size_t)r * w + k] * X[(size_t)k * w + j];
+                X[(size_t)r * w + j] = -sum / Ld[(size_t)r * w + r];
+            }
+        }
+        for (int32_t r = 0; r < w; ++r)
+            for (int32_t c = 0; c <= r; ++c) inv[(size_t)inv_row_off(r) + c] = X[(size_t)r * w + c];
+        blk.push_back(sb);
+        depth_of.push_back(F.blocks[b].depth);
+    }
+    D.nblocks = (int)blk.size();
+    // launches: deepest level first, inside a level one launch per width class
+    auto wclass = [&](int k) { return blk[k].w <= 8 ? 8 : (blk[k].w <= 16 ? 16 : (blk[k].w <= 24 ? 24 : 32)); };
+    std::vector<int32_t> order((size_t)D.nblocks);
+    for (int k = 0; k < D.nblocks; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return depth_of[a] != depth_of[b] ? depth_of[a] > depth_of[b] : wclass(a) < wclass(b);
+    });
+    launches.clear();
+    for (int k = 0, k0 = 0; k < D.nblocks; ++k)
+        if (k + 1 == D.nblocks || depth_of[order[k + 1]] != depth_of[order[k]] || wclass(order[k + 1]) != wclass(order[k])) {
+            launches.push_back({k0, k + 1, wclass(order[k])});
+            k0 = k + 1;
+        }
+    D.nsteps = (int)launches.size();
+    int rc = 0;
+    rc |= dev_upload(ctx, &D.blk, blk);
+    rc |= dev_upload(ctx, &D.tasks, order);
+    rc |= dev_upload(ctx, &D.rec, rec);
+    if (rc) return rc;
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+    return 0;
 }
 
 }  // namespace
@@ -511,21 +969,29 @@ int precond_setup(asgfem_ctx* ctx) {
     fw.idx = F.Li;
     fw.val = F.Lx;
     fw.dinv = F.dinv;
-    // backward system L^T in the reversed numbering k' = n-1-k: row k' holds the column k of L, rows i > k mapped to
-    // i' = n-1-i < k' in ascending order
+    // columns of L (rows ascending inside every column)
+    std::vector<int64_t> cptr((size_t)n + 1, 0);
+    for (int32_t j : F.Li) cptr[j + 1]++;
+    for (int64_t k = 0; k < n; ++k) cptr[k + 1] += cptr[k];
+    std::vector<int32_t> cidx(F.Li.size());
+    std::vector<double> cval(F.Li.size());
     {
-        std::vector<int64_t> cptr((size_t)n + 1, 0);
-        for (int32_t j : F.Li) cptr[j + 1]++;
-        for (int64_t k = 0; k < n; ++k) cptr[k + 1] += cptr[k];
-        std::vector<int32_t> cidx(F.Li.size());
-        std::vector<double> cval(F.Li.size());
         std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
         for (int64_t k = 0; k < n; ++k)
             for (int64_t p = F.Lp[k]; p < F.Lp[k + 1]; ++p) {
                 int64_t at = fill[F.Li[p]]++;
-                cidx[at] = (int32_t)k;  // rows ascending inside every column
+                cidx[at] = (int32_t)k;
                 cval[at] = F.Lx[p];
             }
+    }
+    // bottom forest -> dense supernodal kernel; the rest of the tree -> tree kernel
+    std::vector<uint8_t> top_f, top_b;
+    rc = build_small(ctx, F, cptr, cidx, cval, top_f, P->small, P->small_launches);
+    if (rc) return rc;
+    top_b.assign(top_f.rbegin(), top_f.rend());
+    // backward system L^T in the reversed numbering k' = n-1-k: row k' holds the column k of L, rows i > k mapped to
+    // i' = n-1-i < k' in ascending order
+    {
         bw.ptr.assign((size_t)n + 1, 0);
         bw.idx.resize(F.Li.size());
         bw.val.resize(F.Li.size());
@@ -549,8 +1015,8 @@ int precond_setup(asgfem_ctx* ctx) {
         fb.push_back({b.start, b.len, -(int64_t)b.depth * 4096 + b.chunk});
         bb.push_back({(int32_t)(n - b.start - b.len), b.len, (int64_t)b.depth * 4096 + (b.nchunks - 1 - b.chunk)});
     }
-    rc |= upload_tri(ctx, fw, n, fb, P->fwd);
-    rc |= upload_tri(ctx, bw, n, bb, P->bwd);
+    rc |= upload_tri(ctx, fw, n, fb, top_f, P->fwd);
+    rc |= upload_tri(ctx, bw, n, bb, top_b, P->bwd);
     if (rc) return rc;
     ASG_CUDA(ctx, cudaMalloc((void**)&P->d_work, sizeof(double) * (size_t)std::max<int64_t>(F.n, 1) * ctx->ld));
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -567,8 +1033,21 @@ int precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
         int tiles = (int)((ctx->N + MT - 1) / MT);
         const size_t smem = TRSV_SMEM;
         ASG_CUDA(ctx, cudaFuncSetAttribute(k_trsv_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trsv_tree<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 0, P->fwd);
-        k_trsv_tree<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 1, P->bwd);
+        const bool has_small = P->small.nblocks > 0, has_top = P->fwd.nsteps > 0;
+        if (has_small)
+            for (size_t k = 0; k < P->small_launches.size(); ++k) {
+                const auto& L = P->small_launches[k];
+                launch_small<false>({L[0], L[1], L[2]}, tiles, ctx->stream, P->d_work, ld, P->small);
+            }
+        if (has_top) {
+            k_trsv_tree<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 0, P->fwd);
+            k_trsv_tree<<<tiles, TRSV_THREADS, smem, ctx->stream>>>(P->d_work, ld, P->nred, 1, P->bwd);
+        }
+        if (has_small)
+            for (size_t k = P->small_launches.size(); k-- > 0;) {
+                const auto& L = P->small_launches[k];
+                launch_small<true>({L[0], L[1], L[2]}, tiles, ctx->stream, P->d_work, ld, P->small);
+            }
     }
     // z may alias r: boundary rows are zeroed first, interior rows are overwritten from the work vector
     k_zero_masked_rows<<<(unsigned)std::min<int64_t>(ctx->n, 148 * 8), 128, 0, ctx->stream>>>(z, ctx->d_bmask, ctx->n, ld);
