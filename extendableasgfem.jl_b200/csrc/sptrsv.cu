@@ -303,12 +303,17 @@ __device__ __forceinline__ void small_bwd(const SmallBlk b, SmallPipe<true>& pip
         const int32_t* ar = reinterpret_cast<const int32_t*>(ch);
         const double* P = reinterpret_cast<const double*>(ch + g.arB);
         const int nr = min(g.R, b.nA - a0r);
-        for (int a = pipe.lane; a < nr; a += 32) prefetch_l2(W + (int64_t)ar[a] * ld + (mode & ~(int64_t)(MT - 1)));
+        // y values two pairs ahead of their use: the gathers from W are the only global loads of this loop
+        auto load_y = [&](int p) {
+            const int a = p + half;
+            return a < nr ? __ldcg(W + (int64_t)ar[a] * ld + mode) : 0.0;
+        };
+        double y0 = load_y(0), y1 = load_y(2);
         for (int p = 0; p < nr; p += 2) {
-            const bool ok = p + half < nr;
-            const int a = ok ? p + half : nr - 1;
-            const int64_t r = ar[a];
-            const double y = ok ? __ldcg(W + r * ld + mode) : 0.0;
+            const double y = y0;
+            y0 = y1;
+            y1 = load_y(p + 4);
+            const int a = min(p + half, nr - 1);
             const double* prow = P + a * g.wp;
 #pragma unroll
             for (int q = 0; q < WMAX / 2; ++q) {
