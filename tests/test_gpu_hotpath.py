@@ -237,6 +237,35 @@ def test_preconditioner_matches_oracle(c1, mid):
         ctx.close()
 
 
+@pytest.mark.parametrize("nx,order,N", [(257, 1, 40), (129, 2, 24), (513, 1, 17)])
+def test_preconditioner_direct_solve_at_scale(nx, order, N):
+    """Meshes whose dissection tree has long separators (sub-blocks split into solve-only and push-only tasks, chunked
+    separators at 513^2): every mode block of ldiv! must equal the sparse direct solve with K_0 restricted to the
+    interior dofs (the oracle's LU of the penalised matrix is the same thing up to 1e-60)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    g = A.structured_unitsquare(nx)
+    fes = A.FESpace(g, order)
+    modes = A.graded_lex_multiindices(3, N)
+    TB = A.TensorizedBasis(A.LegendrePolynomials, modes)
+    sol = A.SGFEVector(fes, TB)
+    A.setup_device_problem(sol, A.StochasticCoefficientCosinus(tau=0.9, decay=2, mean=1, maxm=3))
+    ctx = TB.ctx
+    n = fes.ndofs
+    colptr, rowval = ctx.pattern_csc()
+    K0 = sp.csc_matrix((ctx.get_stiffness(0), rowval - 1, colptr - 1), shape=(n, n))
+    interior = np.setdiff1d(np.arange(n), fes.bdofs)
+    lu = spla.splu(sp.csc_matrix(K0[interior][:, interior]))
+    b = np.random.default_rng(nx).standard_normal(n * N)
+    b.reshape(N, n)[:, fes.bdofs] = 0
+    ref = np.zeros((N, n))
+    ref[:, interior] = lu.solve(b.reshape(N, n)[:, interior].T).T
+    got = ctx.precond_apply_host(b).reshape(N, n)
+    assert np.all(got[:, fes.bdofs] == 0)
+    assert relerr(got.ravel(), ref.ravel()) < 1e-10
+    ctx.close()
+
+
 def test_pcg_matches_reference_gmres_solution(c1, mid):
     for P in (c1, mid):
         ref = np.zeros(P.n * P.N)
