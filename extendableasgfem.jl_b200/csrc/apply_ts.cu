@@ -286,12 +286,21 @@ __device__ __forceinline__ unsigned ts_lds_u32(unsigned addr) {
 __device__ __forceinline__ void ts_sts_f64_if(unsigned addr, double v, unsigned on) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr), "d"(v), "r"(on));
 }
+// store if (bits & mask) != 0: the test is one LOP3 with predicate output
+__device__ __forceinline__ void ts_sts_f64_ifbit(unsigned addr, double v, unsigned bits, unsigned mask) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr),
+                 "d"(v), "r"(bits), "r"(mask));
+}
+__device__ __forceinline__ void ts_sts_f64_ifbit(unsigned addr, double v, unsigned long long bits, unsigned long long mask) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 t;\n\tand.b64 t, %2, %3;\n\tsetp.ne.u64 p, t, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr),
+                 "d"(v), "l"(bits), "l"(mask));
+}
 
 // T_m for the slots BASE + {bits of MK}: independent FMA chains, then the stores of the active lanes
 template <int NS, int SLOTS, int BASE, unsigned MK, bool FIRST, typename ACT>
 __device__ __forceinline__ void ts_dir_block(const double (&kr)[NS + (NS & 1)], const double (&x)[SLOTS][NS],
                                              const ACT (&act)[SLOTS], const unsigned* d, int m, unsigned Tl32) {
-    constexpr int NB = SLOTS - BASE < 4 ? SLOTS - BASE : 4;
+    constexpr int NB = SLOTS - BASE;  // all slots of the warp: NB independent FMA chains
     double t[NB];
 #pragma unroll
     for (int q = 0; q < NB; ++q)
@@ -305,11 +314,11 @@ __device__ __forceinline__ void ts_dir_block(const double (&kr)[NS + (NS & 1)], 
 #pragma unroll
     for (int q = 0; q < NB; ++q)
         if (MK >> q & 1u) {
-            const unsigned on = (unsigned)((act[BASE + q] >> m) & (ACT)1);
+            const ACT mbit = (ACT)1 << m;
             const unsigned addr = Tl32 + d[q];
             if (FIRST) {
-                ts_sts_f64_if(addr, t[q], on);
-            } else if (on) {
+                ts_sts_f64_ifbit(addr, t[q], act[BASE + q], mbit);
+            } else if (act[BASE + q] & mbit) {
                 ts_sts_f64_if(addr, ts_lds_f64(addr) + t[q], 1u);
             }
         }
@@ -322,11 +331,7 @@ __device__ __forceinline__ void ts_dir_switch(unsigned mk, const double (&kr)[NS
     case V: ts_dir_block<NS, SLOTS, BASE, V, FIRST, ACT>(kr, x, act, d, m, Tl32); break;
     // all slots of the block at once: the FMA chains of unused slots are wasted, but 4 independent chains per warp keep
     // the fp64 pipe busy (a per-mask switch with only the needed chains was measured 15 % slower: latency-bound)
-    if constexpr (SLOTS - BASE >= 4) {
-        if (mk & 15u) ts_dir_block<NS, SLOTS, BASE, 15u, FIRST, ACT>(kr, x, act, d, m, Tl32);
-    } else {
-        if (mk & 3u) ts_dir_block<NS, SLOTS, BASE, 3u, FIRST, ACT>(kr, x, act, d, m, Tl32);
-    }
+    if (mk) ts_dir_block<NS, SLOTS, BASE, (1u << (SLOTS - BASE)) - 1u, FIRST, ACT>(kr, x, act, d, m, Tl32);
 #undef TS_CASE
 }
 
@@ -334,6 +339,11 @@ template <int NS, int SLOTS, typename ACT>
 __global__ void __launch_bounds__(SLOTS == 8 ? 256 : 512, 1) k_apply_ts(TsArgs a) {
     extern __shared__ __align__(16) unsigned char ts_raw[];
     __shared__ __align__(512) double gt[64];
+    // CSR metadata of the CTA's upcoming rows, fetched with cp.async two / three rows ahead so that the address chain
+    // rowptr -> col -> X is off the critical path when the X loads of the next row are issued
+    __shared__ __align__(16) long long info_rp[4][2];  // [row j % 4]: rowptr[row], rowptr[row + 1]
+    __shared__ int info_msk[4];                         // Dirichlet flag (1 also for rows past the end)
+    __shared__ int cols_ring[2][NS];                    // [row j % 2]: first NS column indices
     const unsigned raw32 = (unsigned)__cvta_generic_to_shared(ts_raw);
     const TsLayout L = ts_layout(a.D, a.nbuf, a.Mp, a.kstr, a.nwords, a.warps, SLOTS);
     const int Dpad = (a.D + 2) / 2 * 2;
@@ -375,11 +385,12 @@ __global__ void __launch_bounds__(SLOTS == 8 ? 256 : 512, 1) k_apply_ts(TsArgs a
         }
     };
     const unsigned long long xbase = (unsigned long long)a.x, ldb = (unsigned long long)a.ld * 8ull;
-    auto load_x = [&](int64_t rp, int len, int c0) {
+    auto load_x = [&](int64_t rp, int len, int c0, const int* cols_s) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             if (c0 + k < len) {  // block-uniform
-                const unsigned long long rowp = xbase + (unsigned long long)(unsigned)__ldg(a.col + rp + c0 + k) * ldb;
+                const unsigned cj = cols_s ? (unsigned)cols_s[k] : (unsigned)__ldg(a.col + rp + c0 + k);
+                const unsigned long long rowp = xbase + (unsigned long long)cj * ldb;
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s)
                     x[s][k] = ldg_f64_volatile(reinterpret_cast<const double*>(rowp + (unsigned)(8 * moff[s])));
@@ -394,18 +405,78 @@ __global__ void __launch_bounds__(SLOTS == 8 ? 256 : 512, 1) k_apply_ts(TsArgs a
     int64_t rp = 0;
     int len = 0;
     bool masked = true;
+    const int64_t G = gridDim.x;
+    // metadata loader: threads 0..NS-1 fetch column ids, thread NS the row pointers, thread NS+1 the Dirichlet flags
+    auto fetch_info = [&](int64_t j) {  // row j of this CTA -> info ring (cp.async, completes at the next wait)
+        const int64_t r = a.row0 + blockIdx.x + j * G;
+        if (tid == NS) {
+            if (r < a.nrows) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&info_rp[j & 3][0]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(a.rowptr + r));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u), "l"(a.rowptr + r + 1));
+            } else {
+                info_rp[j & 3][0] = 0;
+                info_rp[j & 3][1] = 0;
+            }
+        }
+    };
+    auto fetch_cols = [&](int64_t j) {  // needs info of row j complete
+        if (tid < NS) {
+            const long long p0 = info_rp[j & 3][0], p1 = info_rp[j & 3][1];
+            if (tid < (int)(p1 - p0)) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&cols_ring[j & 1][tid]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(a.col + p0 + tid));
+            }
+        }
+    };
+    auto fetch_msk = [&](int64_t j) -> int {
+        const int64_t r = a.row0 + blockIdx.x + j * G;
+        return r < a.nrows ? (int)a.bmask[r] : 1;
+    };
+    auto cp_wait_all = [&]() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); };
     if (row < a.nrows) {
         rp = a.rowptr[row];
         len = (int)(a.rowptr[row + 1] - rp);
         masked = a.bmask[row] != 0 || len == 0;
         if (!masked) {
             stage_k(rp, len, 0);
-            load_x(rp, len, 0);
+            load_x(rp, len, 0, nullptr);
         }
     }
+    fetch_info(1);
+    fetch_info(2);
+    if (tid == NS + 1) {
+        info_msk[1] = fetch_msk(1);
+        info_msk[2] = fetch_msk(2);
+    }
+    cp_wait_all();
+    __syncthreads();
+    fetch_cols(1);
+    cp_wait_all();
     __syncthreads();
     int buf = 0;
-    for (; row < a.nrows; row += gridDim.x, buf ^= 1) {
+    for (int64_t it = 0; row < a.nrows; row += gridDim.x, buf ^= 1, ++it) {
+        // loader: column ids of row it+2 (its row pointers arrived one iteration ago), row pointers of row it+3
+        fetch_cols(it + 2);
+        fetch_info(it + 3);
+        const int msk3 = tid == NS + 1 ? fetch_msk(it + 3) : 0;
+        // K values of the next row: loaded now (HBM latency hidden behind phase 1), stored to shared memory after it
+        const int64_t nrow = row + gridDim.x;
+        int64_t nrp = 0;
+        int nlen = 0;
+        bool nmasked = true;
+        if (nrow < a.nrows) {
+            const int js = (int)((it + 1) & 3);
+            nrp = info_rp[js][0];
+            nlen = (int)(info_rp[js][1] - nrp);
+            nmasked = info_msk[js] != 0 || nlen == 0;
+        }
+        const int kper = (a.Mp * a.kstr + nthr - 1) / nthr;  // K values per thread (1 for P1: 168 values, 512 threads)
+        double kval0 = 0.0;
+        if (!nmasked && kper == 1 && tid < a.Mp * a.kstr) {
+            const int m = tid / a.kstr, k = tid - m * a.kstr;
+            if (k < nlen) kval0 = __ldg(a.vals + (int64_t)m * a.nnz + nrp + k);
+        }
         const int tb = a.nbuf == 2 ? buf : 0;
         const unsigned T32 = ts32 + (unsigned)tb * (unsigned)Dpad * 8u;
         unsigned Tl32 = T32 + 8u * (unsigned)lane;
@@ -417,7 +488,7 @@ __global__ void __launch_bounds__(SLOTS == 8 ? 256 : 512, 1) k_apply_ts(TsArgs a
         // ---------------- phase 1: T_m[nu] for the own modes, all operands in registers ---------------------
         if (!masked) {
             for (int c0 = 0; c0 < len; c0 += NS) {
-                if (c0 > 0) load_x(rp, len, c0);
+                if (c0 > 0) load_x(rp, len, c0, nullptr);
                 constexpr int NK = NS + (NS & 1);  // K rows are read as 16-byte pairs (the pad entry is zero)
                 double kr[NK];
                 {
@@ -450,12 +521,13 @@ __global__ void __launch_bounds__(SLOTS == 8 ? 256 : 512, 1) k_apply_ts(TsArgs a
                             ts_dir_switch<NS, SLOTS, 0, FIRST, ACT>(r0.x, kr, x, act, d, m, Tl32);
                         } else {
                             const uint4 r1 = r[1];
-                            const unsigned d[4] = {r1.x, r1.y, r1.z, r1.w};
-                            ts_dir_switch<NS, SLOTS, 0, FIRST, ACT>(r0.x, kr, x, act, d, m, Tl32);
                             if constexpr (SLOTS == 8) {
                                 const uint4 r2 = r[2];
-                                const unsigned e[4] = {r2.x, r2.y, r2.z, r2.w};
-                                ts_dir_switch<NS, SLOTS, 4, FIRST, ACT>(r0.x >> 4, kr, x, act, e, m, Tl32);
+                                const unsigned d[8] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                                ts_dir_switch<NS, SLOTS, 0, FIRST, ACT>(r0.x, kr, x, act, d, m, Tl32);
+                            } else {
+                                const unsigned d[4] = {r1.x, r1.y, r1.z, r1.w};
+                                ts_dir_switch<NS, SLOTS, 0, FIRST, ACT>(r0.x, kr, x, act, d, m, Tl32);
                             }
                         }
                     };
@@ -467,19 +539,16 @@ __global__ void __launch_bounds__(SLOTS == 8 ? 256 : 512, 1) k_apply_ts(TsArgs a
             }
         }
         // ---------------- next row: K values into the other buffer, X loads in flight during phase 2 --------
-        const int64_t nrow = row + gridDim.x;
-        int64_t nrp = 0;
-        int nlen = 0;
-        bool nmasked = true;
-        if (nrow < a.nrows) {
-            nrp = a.rowptr[nrow];
-            nlen = (int)(a.rowptr[nrow + 1] - nrp);
-            nmasked = a.bmask[nrow] != 0 || nlen == 0;
-            if (!nmasked) {
+        if (!nmasked) {
+            if (kper == 1) {
+                if (tid < a.Mp * a.kstr) (Ks + (size_t)(buf ^ 1) * a.Mp * a.kstr)[tid] = kval0;
+            } else {
                 stage_k(nrp, nlen, buf ^ 1);
-                load_x(nrp, nlen, 0);
             }
+            load_x(nrp, nlen, 0, cols_ring[(it + 1) & 1]);
         }
+        if (tid == NS + 1) info_msk[(it + 3) & 3] = msk3;
+        cp_wait_all();
         __syncthreads();
         // ---------------- phase 2: gather the couplings that end in the own modes ---------------------------
         double* yr = a.y + row * a.ld;
