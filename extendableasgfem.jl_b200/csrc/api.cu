@@ -546,7 +546,7 @@ static int ensure_ready_for_apply(asgfem_ctx* ctx) {
 
 extern "C" int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant) {
     CTX_OR_FAIL(ctx);
-    ASG_CHECK(ctx, variant >= 0 && variant <= 6, ASGFEM_EINVAL, "apply variant must be 0..6");
+    ASG_CHECK(ctx, variant >= 0 && variant <= 7, ASGFEM_EINVAL, "apply variant must be 0..7");
     ctx->apply_variant = variant;
     return 0;
 }

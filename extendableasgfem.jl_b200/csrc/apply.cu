@@ -159,6 +159,7 @@ void apply_free_plan(asgfem_ctx* ctx) {
     apply_rows_free(ctx);
     apply_dir_free(ctx);
     apply_ts_free(ctx);
+    apply_ts2_free(ctx);
     if (!ctx->plan) return;
     free_plan_arrays(ctx->plan);
     delete ctx->plan;
@@ -472,7 +473,9 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_
     if (variant == 0) {
         variant = 1;
         if (ctx->n * ctx->N >= (1 << 16)) {
-            if (apply_ts_preferred(ctx))
+            if (apply_ts2_preferred(ctx))
+                variant = 7;
+            else if (apply_ts_preferred(ctx))
                 variant = 6;
             else if (apply_dir_preferred(ctx))
                 variant = 4;
@@ -485,7 +488,10 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_
     if (variant == 2 && ranged) return fail(ctx, ASGFEM_ESTATE, "row ranges are not available for the tiled operator");
     if (r1 <= r0) return 0;
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (variant == 6) {
+    if (variant == 7) {
+        int rc = apply_ts2_launch(ctx, x, y, r0, r1);
+        if (rc) return rc;
+    } else if (variant == 6) {
         int rc = apply_ts_launch(ctx, x, y, r0, r1);
         if (rc) return rc;
     } else if (variant == 4 || variant == 5) {

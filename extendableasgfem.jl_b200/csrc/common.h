@@ -128,6 +128,7 @@ struct asgfem_ctx {
     void* rowplan = nullptr;  // asgfem::RowPlan (apply_rows.cu)
     void* dirplan = nullptr;  // asgfem::DirPlan (apply_dir.cu)
     void* tsplan = nullptr;   // asgfem::TsPlan (apply_ts.cu)
+    void* ts2plan = nullptr;  // asgfem::Ts2Plan (apply_ts2.cu)
 };
 
 namespace asgfem {
@@ -183,6 +184,11 @@ int apply_ts_build(asgfem_ctx* ctx);
 void apply_ts_free(asgfem_ctx* ctx);
 int apply_ts_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
 bool apply_ts_preferred(asgfem_ctx* ctx);
+// apply_ts2.cu
+int apply_ts2_build(asgfem_ctx* ctx);
+void apply_ts2_free(asgfem_ctx* ctx);
+int apply_ts2_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
+bool apply_ts2_preferred(asgfem_ctx* ctx);
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
 int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* dX, double* dY);
