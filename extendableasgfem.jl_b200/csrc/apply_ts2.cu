@@ -102,8 +102,9 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     if (P->kstr > 66 || Mp * P->kstr * 8 > 32768 || Mp * P->kstr2 * 8 > 32768) return 0;
     const int G = (int)((N + 31) / 32);
     if (G > 64) return 0;
-    // 8 warps x 8 slots (255 registers per thread: room for independent FMA chains) or 16 warps x 4 slots
-    P->slots = G > 32 ? 8 : 4;
+    // 16 warps x 4 slots; 8 warps x 8 slots (255 registers per thread, more independent FMA chains per warp) and
+    // 32 warps x 2 slots (64 registers, spills) were measured slower at N = 2000: 67 / 72 ms against 55.6 ms
+    P->slots = 4;
     if (const char* e = getenv("ASGFEM_TS2_SLOTS")) {
         int v = atoi(e);
         if (v == 2 || v == 4 || v == 8) P->slots = v;
