@@ -38,7 +38,8 @@ struct Ts2Plan {
     int nwords = 0, ndl = 0;
     int units = 0;  // evaluated units per row (statistics)
     size_t smem_bytes = 0;
-    int32_t* d_slotinfo = nullptr;  // [warps*4*8] group (-1 unused), kind (1 dense, 2 sparse), #dense units, list base, words base, jmax
+    int32_t* d_slotinfo = nullptr;  // [warps*(slots+1)*8] group (-1 unused), kind (1 dense, 2 sparse, 3 dense with exported
+                                    // phase 2), #dense units, list base, words base, jmax, byte offset of the mean-term block
     uint32_t* d_lane = nullptr;     // [warps*4*4*32] sparse lanes: K row byte offset | T index << 15 per unit
     uint32_t* d_dl = nullptr;       // dense unit lists (same packing, T index of the block start)
     uint32_t* d_words = nullptr;    // phase-2 words: T index << 12 | weight index << 3
@@ -78,7 +79,7 @@ static __host__ __device__ inline Ts2Layout ts2_layout(int D, int nbuf, int Mp, 
     at += (uint32_t)ndl * 4u;
     at = (at + 15u) & ~15u;
     L.sinfo = at;
-    at += (uint32_t)warps * (uint32_t)slots * 32u;
+    at += (uint32_t)warps * (uint32_t)(slots + 1) * 32u;  // + the gather-only slot of every warp
     L.total = at + 16u;
     return L;
 }
@@ -222,38 +223,121 @@ int apply_ts2_build(asgfem_ctx* ctx) {
         return ng++;
     };
 
+    // ---- groups -> (warp, slot): longest processing time first, then warps dealt to the four schedulers ---------
+    // Phase 2 of a listed group (a long gather list) does not need the X registers of the group: it may run in another
+    // warp.  The owner then exports the mean term through the exchange buffer (one more entry of the gather list with
+    // weight 1) and a warp with little phase-1 work takes the list as its extra, gather-only slot.
+    std::vector<int> jlen((size_t)G, 0);
+    for (int g = 0; g < G; ++g)
+        for (int l = 0; l < 32; ++l) {
+            int64_t mu = 32ll * g + l;
+            if (mu < N) jlen[(size_t)g] = std::max(jlen[(size_t)g], (int)(C.ptr[mu + 1] - C.ptr[mu]));
+        }
+    auto even = [](int v) { return (v + 1) / 2 * 2; };
+    auto cost1 = [&](int g) -> int64_t {  // phase 1 (+ phase 2 for sparse groups, which stay with their owner)
+        return sparse[(size_t)g] ? 16ll * Q + 9ll * even(jlen[(size_t)g]) + 20 : 16ll * nd4(g) + 20;
+    };
+    auto cost2 = [&](int g) -> int64_t { return 9ll * even(jlen[(size_t)g] + 1) + 10; };
+    std::vector<int> order((size_t)G);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost1(a) > cost1(b); });
+    std::vector<int64_t> load((size_t)W, 0);
+    std::vector<std::vector<int>> wg((size_t)W);
+    std::vector<int> owner((size_t)G, 0);
+    for (int g : order) {
+        int best = -1;
+        for (int w = 0; w < W; ++w)
+            if ((int)wg[(size_t)w].size() < S_used && (best < 0 || load[(size_t)w] < load[(size_t)best])) best = w;
+        wg[(size_t)best].push_back(g);
+        owner[(size_t)g] = best;
+        load[(size_t)best] += cost1(g);
+    }
+    std::vector<int> extra((size_t)W, -1);     // logical warp -> listed group whose phase 2 it runs
+    std::vector<int> exported((size_t)G, -1);  // listed group -> index of its mean-term block, -1: phase 2 stays with the owner
+    int nexp = 0;
+    {
+        std::vector<int> lst;
+        for (int g = 0; g < G; ++g)
+            if (!sparse[(size_t)g]) lst.push_back(g);
+        std::stable_sort(lst.begin(), lst.end(), [&](int a, int b) { return cost2(a) > cost2(b); });
+        const bool allow = getenv("ASGFEM_TS2_NOEXPORT") == nullptr;
+        for (int g : lst) {
+            int best = -1;
+            for (int w = 0; w < W; ++w)
+                if (extra[(size_t)w] < 0 && (best < 0 || load[(size_t)w] < load[(size_t)best])) best = w;
+            if (!allow || best < 0 || best == owner[(size_t)g] ||
+                load[(size_t)best] + cost2(g) >= load[(size_t)owner[(size_t)g]] + cost2(g) - 16) {
+                load[(size_t)owner[(size_t)g]] += cost2(g) - 9;  // no export: the list is one entry shorter
+                continue;
+            }
+            extra[(size_t)best] = g;
+            exported[(size_t)g] = nexp++;
+            load[(size_t)best] += cost2(g);
+            load[(size_t)owner[(size_t)g]] += 2;
+        }
+    }
+    const int D0 = D;  // mean-term blocks of the exported groups behind the unit blocks
+    D = D0 + 32 * nexp;
+    if (D + TS2_DUMMY >= (1 << 17)) return 0;
+    P->D = D;
+    std::vector<int> wrank((size_t)W);
+    std::iota(wrank.begin(), wrank.end(), 0);
+    std::stable_sort(wrank.begin(), wrank.end(), [&](int a, int b) { return load[(size_t)a] > load[(size_t)b]; });
+    std::vector<int> phys((size_t)W, -1);  // logical warp (by rank) -> physical warp id: snake over warp_id % 4
+    {
+        std::vector<int> freeids;
+        for (int r = 0; r < W; ++r) {
+            const int j = r / 4, c = r % 4;
+            const int smsp = (j & 1) ? 3 - c : c;
+            int id = 4 * j + smsp;
+            if (id >= W) id = -1;
+            phys[(size_t)r] = id;
+        }
+        std::vector<uint8_t> taken((size_t)W, 0);
+        for (int r = 0; r < W; ++r)
+            if (phys[(size_t)r] >= 0) taken[(size_t)phys[(size_t)r]] = 1;
+        for (int id = 0; id < W; ++id)
+            if (!taken[(size_t)id]) freeids.push_back(id);
+        for (int r = 0; r < W; ++r)
+            if (phys[(size_t)r] < 0) {
+                phys[(size_t)r] = freeids.back();
+                freeids.pop_back();
+            }
+    }
+
     // ---- phase-2 lists per group: words[wbase + 32*j + lane] ------------------------------------------
     std::vector<int32_t> jmax((size_t)G, 0), wbase((size_t)G, 0);
     std::vector<uint32_t> words;
     int64_t confl_before = 0, confl_after = 0;
     for (int g = 0; g < G; ++g) {
-        int jm = 0;
-        for (int l = 0; l < 32; ++l) {
-            int64_t mu = 32ll * g + l;
-            if (mu < N) jm = std::max(jm, (int)(C.ptr[mu + 1] - C.ptr[mu]));
-        }
-        jm = (jm + 1) / 2 * 2;  // the gather loop is unrolled by 4 with a tail of 2
+        const bool exp = exported[(size_t)g] >= 0;
+        const int jm = even(jlen[(size_t)g] + (exp ? 1 : 0));  // the gather loop is unrolled by 4 with a tail of 2
         jmax[(size_t)g] = jm;
         wbase[(size_t)g] = (int32_t)words.size();
         words.resize(words.size() + (size_t)jm * 32, 0u);
-        uint32_t* wg = words.data() + wbase[(size_t)g];
+        uint32_t* wl = words.data() + wbase[(size_t)g];
         for (int l = 0; l < 32; ++l) {
             // padding: weight index 0 -> 0.0 and a zero entry of the exchange buffer in the lane's own bank
-            for (int j = 0; j < jm; ++j) wg[(size_t)j * 32 + l] = (uint32_t)(D + (l & 15)) << 12;
+            for (int j = 0; j < jm; ++j) wl[(size_t)j * 32 + l] = (uint32_t)(D + (l & 15)) << 12;
             int64_t mu = 32ll * g + l;
             if (mu >= N) continue;
             int j = 0;
             for (int32_t e = C.ptr[mu]; e < C.ptr[mu + 1]; ++e, ++j) {
                 int gi = gindex(C.g[e]);
                 if (gi < 0) return 0;
-                wg[(size_t)j * 32 + l] = ((uint32_t)pairidx(C.nu[e], C.m[e]) << 12) | ((uint32_t)gi << 3);
+                wl[(size_t)j * 32 + l] = ((uint32_t)pairidx(C.nu[e], C.m[e]) << 12) | ((uint32_t)gi << 3);
+            }
+            if (exp) {  // mean term of the mode, written by the owner of the group
+                int gi = gindex(1.0);
+                if (gi < 0) return 0;
+                wl[(size_t)j * 32 + l] = ((uint32_t)(D0 + 32 * exported[(size_t)g] + l) << 12) | ((uint32_t)gi << 3);
             }
         }
         // The order of a lane's couplings is free: permute every lane's list so that the 16 lanes of a half-warp read
         // 16 different banks (8-byte granules mod 16) in as many slots as possible (local search on pairwise swaps).
         for (int h = 0; h < 2; ++h) {
             std::vector<int> cnt((size_t)jm * 16, 0);
-            auto bank = [&](int l, int j) { return (int)((wg[(size_t)j * 32 + l] >> 12) & 15u); };
+            auto bank = [&](int l, int j) { return (int)((wl[(size_t)j * 32 + l] >> 12) & 15u); };
             for (int j = 0; j < jm; ++j)
                 for (int l = 16 * h; l < 16 * h + 16; ++l) ++cnt[(size_t)j * 16 + bank(l, j)];
             auto excess = [&]() {
@@ -285,7 +369,7 @@ int apply_ts2_build(asgfem_ctx* ctx) {
                             const int b2 = bank(l, best);
                             --cnt[(size_t)j1 * 16 + b1], ++cnt[(size_t)j1 * 16 + b2];
                             --cnt[(size_t)best * 16 + b2], ++cnt[(size_t)best * 16 + b1];
-                            std::swap(wg[(size_t)j1 * 32 + l], wg[(size_t)best * 32 + l]);
+                            std::swap(wl[(size_t)j1 * 32 + l], wl[(size_t)best * 32 + l]);
                             improved = true;
                         }
                     }
@@ -296,48 +380,8 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     }
     P->nwords = (int)words.size();
 
-    // ---- groups -> (warp, slot): longest processing time first, then warps dealt to the four schedulers ---------
-    auto cost = [&](int g) -> int64_t {
-        return 16ll * (sparse[(size_t)g] ? Q : nd4(g)) + 9ll * jmax[(size_t)g] + 20;
-    };
-    std::vector<int> order((size_t)G);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
-    std::vector<int64_t> load((size_t)W, 0);
-    std::vector<std::vector<int>> wg((size_t)W);
-    for (int g : order) {
-        int best = -1;
-        for (int w = 0; w < W; ++w)
-            if ((int)wg[(size_t)w].size() < S_used && (best < 0 || load[(size_t)w] < load[(size_t)best])) best = w;
-        wg[(size_t)best].push_back(g);
-        load[(size_t)best] += cost(g);
-    }
-    std::vector<int> wrank((size_t)W);
-    std::iota(wrank.begin(), wrank.end(), 0);
-    std::stable_sort(wrank.begin(), wrank.end(), [&](int a, int b) { return load[(size_t)a] > load[(size_t)b]; });
-    std::vector<int> phys((size_t)W, -1);  // logical warp (by rank) -> physical warp id: snake over warp_id % 4
-    {
-        std::vector<int> freeids;
-        for (int r = 0; r < W; ++r) {
-            const int j = r / 4, c = r % 4;
-            const int smsp = (j & 1) ? 3 - c : c;
-            int id = 4 * j + smsp;
-            if (id >= W) id = -1;
-            phys[(size_t)r] = id;
-        }
-        std::vector<uint8_t> taken((size_t)W, 0);
-        for (int r = 0; r < W; ++r)
-            if (phys[(size_t)r] >= 0) taken[(size_t)phys[(size_t)r]] = 1;
-        for (int id = 0; id < W; ++id)
-            if (!taken[(size_t)id]) freeids.push_back(id);
-        for (int r = 0; r < W; ++r)
-            if (phys[(size_t)r] < 0) {
-                phys[(size_t)r] = freeids.back();
-                freeids.pop_back();
-            }
-    }
-
-    std::vector<int32_t> slotinfo((size_t)W * TS2_SLOTS * 8, 0);
+    const int SI = TS2_SLOTS + 1;  // slot records per warp: the X slots + one gather-only slot
+    std::vector<int32_t> slotinfo((size_t)W * SI * 8, 0);
     for (size_t k = 0; k < slotinfo.size(); k += 8) slotinfo[k] = -1;
     std::vector<uint32_t> lane((size_t)W * TS2_SLOTS * 4 * 32, 0u);
     std::vector<uint32_t> dl;
@@ -347,12 +391,13 @@ int apply_ts2_build(asgfem_ctx* ctx) {
         const int lw = wrank[(size_t)r], w = phys[(size_t)r];
         for (int s = 0; s < (int)wg[(size_t)lw].size(); ++s) {
             const int g = wg[(size_t)lw][(size_t)s];
-            int32_t* si = &slotinfo[((size_t)w * TS2_SLOTS + s) * 8];
+            int32_t* si = &slotinfo[((size_t)w * SI + s) * 8];
             si[0] = g;
             si[4] = wbase[(size_t)g];
             si[5] = jmax[(size_t)g];
             if (!sparse[(size_t)g]) {
-                si[1] = 1;
+                si[1] = exported[(size_t)g] >= 0 ? 3 : 1;  // 3: phase 2 runs elsewhere, the mean term is exported
+                si[6] = exported[(size_t)g] >= 0 ? 8 * (D0 + 32 * exported[(size_t)g]) : 0;
                 si[3] = (int32_t)dl.size();
                 int cnt = 0;
                 for (int m = 1; m <= M; ++m) {
@@ -381,6 +426,13 @@ int apply_ts2_build(asgfem_ctx* ctx) {
             }
         }
     }
+    for (int r = 0; r < W; ++r) {  // gather-only slots
+        const int lw = wrank[(size_t)r], w = phys[(size_t)r];
+        int32_t* si = &slotinfo[((size_t)w * SI + TS2_SLOTS) * 8];
+        const int g = extra[(size_t)lw];
+        si[0] = g;
+        if (g >= 0) si[4] = wbase[(size_t)g], si[5] = jmax[(size_t)g];
+    }
     P->ndl = (int)dl.size();
 
     const size_t limit = 226 * 1024;  // 512 bytes of static shared memory (weight table) + the metadata rings come on top
@@ -400,10 +452,15 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     if (rc) return rc;
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     P->usable = true;
-    if (getenv("ASGFEM_TS2_VERBOSE"))
-        fprintf(stderr, "[ts2] N=%lld G=%d warps=%d slots=%d Q=%d units/row=%d D=%d words=%d smem=%zu nbuf=%d NS=%d chunks=%d gather bank excess %lld -> %lld\n",
-                (long long)N, G, W, TS2_SLOTS, Q, P->units, P->D, P->nwords, P->smem_bytes, P->nbuf, P->NS, P->nchunk_max, (long long)confl_before,
-                (long long)confl_after);
+    if (getenv("ASGFEM_TS2_VERBOSE")) {
+        int64_t lmin = 1 << 30, lmax = 0;
+        for (int64_t v : load) lmin = std::min(lmin, v), lmax = std::max(lmax, v);
+        fprintf(stderr,
+                "[ts2] N=%lld G=%d warps=%d slots=%d Q=%d units/row=%d D=%d words=%d smem=%zu nbuf=%d NS=%d chunks=%d "
+                "gather bank excess %lld -> %lld, exported phase-2 lists %d, warp cost %lld..%lld\n",
+                (long long)N, G, W, TS2_SLOTS, Q, P->units, P->D, P->nwords, P->smem_bytes, P->nbuf, P->NS, P->nchunk_max,
+                (long long)confl_before, (long long)confl_after, nexp, (long long)lmin, (long long)lmax);
+    }
     return 0;
 }
 
@@ -432,6 +489,7 @@ struct Ts2Args {
 namespace {
 __device__ __forceinline__ double t2_ldg_f64(const double* p) {
     double v;
+    // (L1::no_allocate was measured slower: 57.9 ms against 55.0 ms)
     asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
@@ -524,7 +582,7 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
     double* Ks2 = reinterpret_cast<double*>(ts2_raw + L.ks2);          // [2][Mp][kstr2]
     uint32_t* words = reinterpret_cast<uint32_t*>(ts2_raw + L.words);  // [nwords]
     uint32_t* dls = reinterpret_cast<uint32_t*>(ts2_raw + L.dl);       // [ndl]
-    int32_t* sinfo = reinterpret_cast<int32_t*>(ts2_raw + L.sinfo);    // [warps][SLOTS][8]
+    int32_t* sinfo = reinterpret_cast<int32_t*>(ts2_raw + L.sinfo);    // [warps][SLOTS + 1][8]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
     const unsigned gt32 = (unsigned)__cvta_generic_to_shared(gt), ts32 = raw32 + L.ts, words32 = raw32 + L.words,
                    ks32 = raw32 + L.ks, ks2_32 = raw32 + L.ks2, dl32 = raw32 + L.dl;
@@ -532,15 +590,15 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
     for (int k = tid; k < 64; k += nthr) gt[k] = a.gtab[k];
     for (int k = tid; k < a.nwords; k += nthr) words[k] = a.words[k];
     for (int k = tid; k < a.ndl; k += nthr) dls[k] = a.dl[k];
-    for (int k = tid; k < a.warps * SLOTS * 8; k += nthr) sinfo[k] = a.slotinfo[k];
+    for (int k = tid; k < a.warps * (SLOTS + 1) * 8; k += nthr) sinfo[k] = a.slotinfo[k];
     for (int k = tid; k < a.nbuf * Dpad; k += nthr) Ts[k] = 0.0;  // includes the zero entry D of the padded gather lists
     unsigned li[SLOTS][Q];   // sparse slots: per-lane unit constants
     int moff[SLOTS];         // own mode of the slot (clamped to a valid mode for idle lanes / unused slots: loads stay in
     unsigned validmask = 0;  // bounds and unpredicated, nothing is stored for them)
-    unsigned kindmask = 0;   // 2 bits per slot: 0 unused, 1 dense, 2 sparse
+    unsigned kindmask = 0;   // 2 bits per slot: 0 unused, 1 dense, 2 sparse, 3 dense with exported phase 2
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-        const int32_t* si = a.slotinfo + ((size_t)warp * SLOTS + s) * 8;
+        const int32_t* si = a.slotinfo + ((size_t)warp * (SLOTS + 1) + s) * 8;
         const int g = si[0];
         const bool valid = g >= 0 && 32 * g + lane < a.N;
         moff[s] = valid ? 32 * g + lane : (g >= 0 ? a.N - 1 : 0);
@@ -549,7 +607,8 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
 #pragma unroll
         for (int q = 0; q < Q; ++q) li[s][q] = a.lane[(((size_t)warp * SLOTS + s) * 4 + q) * 32 + lane];
     }
-    const int32_t* myinfo = sinfo + warp * SLOTS * 8;
+    const int32_t* myinfo = sinfo + warp * (SLOTS + 1) * 8;
+    const int xgroup = a.slotinfo[((size_t)warp * (SLOTS + 1) + SLOTS) * 8];  // gather-only slot: group or -1
 
     double x[SLOTS][NS];
     auto stage_k = [&](int64_t rp, int len, int buf) {
@@ -683,7 +742,7 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
                     const unsigned kind = (kindmask >> (2 * s)) & 3u;
-                    if (kind == 1u) {  // dense: unit list in shared memory, four units per step
+                    if (kind & 1u) {  // dense: unit list in shared memory, four units per step
                         const int nd = myinfo[8 * s + 2];
                         unsigned p = dl32 + 4u * (unsigned)myinfo[8 * s + 3];
                         for (int u = 0; u < nd; u += 4, p += 16u) {
@@ -705,6 +764,9 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
                     }
                 }
             }
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)  // mean term of the groups whose phase 2 runs in another warp
+                if (((kindmask >> (2 * s)) & 3u) == 3u) t2_sts_f64(Tl32 + (unsigned)myinfo[8 * s + 6], acc[s]);
         }
         // ---------------- next row: K values into the other buffer, X loads in flight during phase 2 --------
         if (!nmasked) {
@@ -728,34 +790,42 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
         __syncthreads();
         // ---------------- phase 2: gather the couplings that end in the own modes ---------------------------
         double* yr = a.y + row * a.ld;
+        auto gather = [&](int jm, unsigned wp, double r0) -> double {
+            double r1 = 0.0;
+            for (int j = 0; j + 4 <= jm; j += 4, wp += 512u) {
+                const unsigned w0 = t2_lds_u32(wp), w1 = t2_lds_u32(wp + 128u), w2 = t2_lds_u32(wp + 256u),
+                               w3 = t2_lds_u32(wp + 384u);
+                const double g0 = t2_lds_f64(gt32 + (w0 & 0x1f8u)), t0 = t2_lds_f64(T32 + (w0 >> 9));
+                const double g1 = t2_lds_f64(gt32 + (w1 & 0x1f8u)), t1 = t2_lds_f64(T32 + (w1 >> 9));
+                const double g2 = t2_lds_f64(gt32 + (w2 & 0x1f8u)), t2 = t2_lds_f64(T32 + (w2 >> 9));
+                const double g3 = t2_lds_f64(gt32 + (w3 & 0x1f8u)), t3 = t2_lds_f64(T32 + (w3 >> 9));
+                r0 = fma(g0, t0, r0);
+                r1 = fma(g1, t1, r1);
+                r0 = fma(g2, t2, r0);
+                r1 = fma(g3, t3, r1);
+            }
+            if (jm & 2) {
+                const unsigned w0 = t2_lds_u32(wp), w1 = t2_lds_u32(wp + 128u);
+                const double g0 = t2_lds_f64(gt32 + (w0 & 0x1f8u)), t0 = t2_lds_f64(T32 + (w0 >> 9));
+                const double g1 = t2_lds_f64(gt32 + (w1 & 0x1f8u)), t1 = t2_lds_f64(T32 + (w1 >> 9));
+                r0 = fma(g0, t0, r0);
+                r1 = fma(g1, t1, r1);
+            }
+            return r0 + r1;
+        };
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
+            if (((kindmask >> (2 * s)) & 3u) == 3u) continue;  // phase 2 of this group runs in another warp
             if (!(validmask >> s & 1u)) continue;
-            double r0 = acc[s], r1 = 0.0;
-            if (!masked) {
-                const int jm = myinfo[8 * s + 5];
-                unsigned wp = words32 + 4u * (unsigned)(myinfo[8 * s + 4] + lane);
-                for (int j = 0; j + 4 <= jm; j += 4, wp += 512u) {
-                    const unsigned w0 = t2_lds_u32(wp), w1 = t2_lds_u32(wp + 128u), w2 = t2_lds_u32(wp + 256u),
-                                   w3 = t2_lds_u32(wp + 384u);
-                    const double g0 = t2_lds_f64(gt32 + (w0 & 0x1f8u)), t0 = t2_lds_f64(T32 + (w0 >> 9));
-                    const double g1 = t2_lds_f64(gt32 + (w1 & 0x1f8u)), t1 = t2_lds_f64(T32 + (w1 >> 9));
-                    const double g2 = t2_lds_f64(gt32 + (w2 & 0x1f8u)), t2 = t2_lds_f64(T32 + (w2 >> 9));
-                    const double g3 = t2_lds_f64(gt32 + (w3 & 0x1f8u)), t3 = t2_lds_f64(T32 + (w3 >> 9));
-                    r0 = fma(g0, t0, r0);
-                    r1 = fma(g1, t1, r1);
-                    r0 = fma(g2, t2, r0);
-                    r1 = fma(g3, t3, r1);
-                }
-                if (jm & 2) {
-                    const unsigned w0 = t2_lds_u32(wp), w1 = t2_lds_u32(wp + 128u);
-                    const double g0 = t2_lds_f64(gt32 + (w0 & 0x1f8u)), t0 = t2_lds_f64(T32 + (w0 >> 9));
-                    const double g1 = t2_lds_f64(gt32 + (w1 & 0x1f8u)), t1 = t2_lds_f64(T32 + (w1 >> 9));
-                    r0 = fma(g0, t0, r0);
-                    r1 = fma(g1, t1, r1);
-                }
-            }
-            yr[moff[s]] = masked ? 0.0 : r0 + r1;
+            double v = 0.0;
+            if (!masked) v = gather(myinfo[8 * s + 5], words32 + 4u * (unsigned)(myinfo[8 * s + 4] + lane), acc[s]);
+            yr[moff[s]] = v;
+        }
+        if (xgroup >= 0) {  // gather-only slot: a listed group owned by another warp (its mean term is in the list)
+            double v = 0.0;
+            if (!masked)
+                v = gather(myinfo[8 * SLOTS + 5], words32 + 4u * (unsigned)(myinfo[8 * SLOTS + 4] + lane), 0.0);
+            if (32 * xgroup + lane < a.N) yr[32 * xgroup + lane] = v;
         }
         if (a.nbuf == 1) __syncthreads();  // single exchange buffer: phase 1 of the next row overwrites it
         rp = nrp;
