@@ -209,7 +209,11 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     auto pairidx = [&](int64_t nu, int m) -> int32_t {
         const int g = (int)(nu / 32);
         const int32_t u = uidx[(size_t)g * 64 + (sparse[(size_t)g] ? rank_of(nu, m) : m)];
-        return units[(size_t)u].disp + (int32_t)(nu % 32);
+        if (sparse[(size_t)g]) return units[(size_t)u].disp + (int32_t)(nu % 32);
+        // dense blocks are rotated by the position of the unit in the list of the group: the entries of one mode for
+        // consecutive directions (gathered by consecutive lanes of a sparse group) then lie in different banks
+        const int k = __builtin_popcountll(gunion[(size_t)g] & ((1ull << m) - 1ull));
+        return units[(size_t)u].disp + (int32_t)((nu % 32 + k) & 31);
     };
 
     // ---- weight table: distinct coupling coefficients -------------------------------------------------
@@ -555,7 +559,10 @@ __device__ __forceinline__ void t2_units(const unsigned* wa, const double (&xa)[
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-        const unsigned addr = (u < NA ? tba : tbb) + ((w[u] >> 12) & 0xfffffff8u);
+        // dense units (WIDE): tba = start of the exchange buffer, tbb = lane + position of the first unit in the list of
+        // the group; the 32-entry block of unit u is rotated by its position
+        const unsigned addr = WIDE ? tba + 8u * ((tbb + (unsigned)u) & 31u) + ((w[u] >> 12) & 0xfffffff8u)
+                                   : (u < NA ? tba : tbb) + ((w[u] >> 12) & 0xfffffff8u);
         if (!MULTI || first)
             t2_sts_f64(addr, t[u]);
         else
@@ -621,7 +628,8 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
             if (k < a.kstr2) dst2[m * a.kstr2 + k] = v;
         }
     };
-    const unsigned long long xbase = (unsigned long long)a.x, ldb = (unsigned long long)a.ld * 8ull;
+    const unsigned long long xbase = (unsigned long long)a.x;
+    const unsigned ldb = (unsigned)a.ld * 8u;  // row pitch in bytes (< 4 GB)
     auto load_x = [&](int64_t rp, int len, int c0, const int* cols_s) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -695,7 +703,14 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
     __syncthreads();
     int buf = 0;
     for (int64_t it = 0; row < a.nrows; row += gridDim.x, buf ^= 1, ++it) {
-        const unsigned msk3 = warp == 0 ? load_msk(it + 3) : 0u;
+        // loader (warp 0): column ids of row it+2 (its row pointers arrived one iteration ago), metadata of row it+3;
+        // issued first, so that the copies complete behind phase 1
+        unsigned msk3 = 0u;
+        if (warp == 0) {
+            fetch_cols(it + 2);
+            fetch_info(it + 3);
+            msk3 = load_msk(it + 3);
+        }
         // K values of the next row: loaded now (HBM latency hidden behind phase 1), stored to shared memory after it
         const int64_t nrow = row + gridDim.x;
         int64_t nrp = 0;
@@ -707,11 +722,19 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
             nlen = (int)(info_rp[js][1] - nrp);
             nmasked = info_msk[js] != 0 || nlen == 0;
         }
+        // K values of the next row: asynchronous copies into the other buffer (both layouts) while phase 1 runs on this
+        // one; columns past the end of the row are zero-filled (source size 0)
         const int kper = (a.Mp * a.kstr + nthr - 1) / nthr;  // K values per thread (1 for P1: 210 values)
-        double kval0 = 0.0;
         if (!nmasked && kper == 1 && tid < a.Mp * a.kstr) {
             const int m = tid / a.kstr, k = tid - m * a.kstr;
-            if (k < nlen) kval0 = __ldg(a.vals + (int64_t)m * a.nnz + nrp + k);
+            const double* src = a.vals + (int64_t)m * a.nnz + nrp + (k < nlen ? k : 0);
+            const unsigned sz = k < nlen ? 8u : 0u;
+            const unsigned d1 = ks32 + (unsigned)((buf ^ 1) * a.Mp * a.kstr + tid) * 8u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d1), "l"(src), "r"(sz));
+            if (k < a.kstr2) {
+                const unsigned d2 = ks2_32 + (unsigned)((buf ^ 1) * a.Mp * a.kstr2 + m * a.kstr2 + k) * 8u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d2), "l"(src), "r"(sz));
+            }
         }
         const int tb = a.nbuf == 2 ? buf : 0;
         const unsigned T32 = ts32 + (unsigned)tb * (unsigned)Dpad * 8u;
@@ -748,7 +771,7 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
                         for (int u = 0; u < nd; u += 4, p += 16u) {
                             const uint4 ww = t2_lds_u32x4(p);
                             const unsigned w4[4] = {ww.x, ww.y, ww.z, ww.w};
-                            t2_units<NS, 4, 0, MULTI, true>(w4, x[s], Tl32, w4, x[s], Tl32, Kc, first);
+                            t2_units<NS, 4, 0, MULTI, true>(w4, x[s], T32, w4, x[s], (unsigned)(lane + u), Kc, first);
                         }
                     }
                 }
@@ -770,22 +793,10 @@ __global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_app
         }
         // ---------------- next row: K values into the other buffer, X loads in flight during phase 2 --------
         if (!nmasked) {
-            if (kper == 1) {
-                if (tid < a.Mp * a.kstr) {
-                    (Ks + (size_t)(buf ^ 1) * a.Mp * a.kstr)[tid] = kval0;
-                    const int m = tid / a.kstr, k = tid - m * a.kstr;
-                    if (k < a.kstr2) (Ks2 + (size_t)(buf ^ 1) * a.Mp * a.kstr2)[m * a.kstr2 + k] = kval0;
-                }
-            } else {
-                stage_k(nrp, nlen, buf ^ 1);
-            }
+            if (kper != 1) stage_k(nrp, nlen, buf ^ 1);
             load_x(nrp, nlen, 0, cols_ring[(it + 1) & 1]);
         }
-        if (warp == 0) {  // loader: column ids of row it+2 (its row pointers arrived one iteration ago), metadata of row it+3
-            fetch_cols(it + 2);
-            fetch_info(it + 3);
-            if (tid == NS + 1) info_msk[(it + 3) & 3] = (int)msk3;
-        }
+        if (tid == NS + 1) info_msk[(it + 3) & 3] = (int)msk3;
         cp_wait_all();
         __syncthreads();
         // ---------------- phase 2: gather the couplings that end in the own modes ---------------------------
