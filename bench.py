@@ -282,6 +282,39 @@ def run_gpu(args):
                           "note": "mean-preconditioned CG on the device (solve_primal! seam), K_0 factorised once on the host"}
         except Exception as e:  # pragma: no cover
             out["pcg"] = {"error": str(e)[:200]}
+    # ---- residual estimator (second half of the hot path, src/estimate.jl:260-418) on a configs[1]-like level -------
+    # eta4cell is an ncells x N_ext matrix in the reference interface, so the estimator is timed on a mesh whose output
+    # fits the host (257 x 257 P1 mesh, 300 multi-indices), not on the 1M-dof operator workload.
+    if rank == 0 and world == 1 and not args.no_est:
+        try:
+            g2 = A.structured_unitsquare(257)
+            fes2 = A.FESpace(g2, 1)
+            TB2 = A.TensorizedBasis(A.LegendrePolynomials, A.graded_lex_multiindices(M_KLE, 300))
+            sol2 = A.SGFEVector(fes2, TB2)
+            A.setup_device_problem(sol2, A.StochasticCoefficientCosinus(tau=0.9, decay=2, mean=1, maxm=M_KLE + 16))
+            sol2.entries[:] = np.random.default_rng(SEED).standard_normal(sol2.entries.shape)
+            frhs = lambda x, y: 1.0 + 0.0 * x  # noqa: E731
+            A.estimate(sol2, None, rhs=frhs, bonus_quadorder=1, tail_extension=(10, 2))  # warm-up
+            t0 = time.perf_counter()
+            em, ec, ext = A.estimate(sol2, None, rhs=frhs, bonus_quadorder=1, tail_extension=(10, 2))
+            t_all = time.perf_counter() - t0
+            kms = TB2.ctx.last_estimate_ms()
+            pairs = ec.shape[0] * ec.shape[1]
+            # algorithmic bytes of the kernels: u read once per cell (3 dofs x N), eta4cell + face jumps written and
+            # re-read by the column sums and the jump scatter (3 passes over ncells x N_ext, 2 over nfaces x N_ext)
+            nfaces = (3 * g2.ncells + 4 * 256) // 2
+            bytes_est = 8 * (3 * g2.ncells * 300 + 3 * pairs + 3 * nfaces * ec.shape[1])
+            out["estimator"] = {"workload": "257x257 P1 mesh (131072 cells) x 300 multi-indices, M=20, tail_extension=(10,2)",
+                                "n_cells": int(ec.shape[0]), "n_multiindices_extended": int(ec.shape[1]),
+                                "kernel_ms": round(kms, 3), "call_ms": round(t_all * 1e3, 1),
+                                "gpairs_per_s_kernels": round(pairs / (kms * 1e-3) / 1e9, 3),
+                                "hbm_gbs_kernels": round(bytes_est / (kms * 1e-3) / 1e9, 1),
+                                "note": "kernel_ms = CUDA events around k_est_volume, k_est_jumps, column sums and the jump "
+                                        "scatter; call_ms adds table upload, the D2H of eta4cell (ncells x N_ext doubles) "
+                                        "and the host-side multi-index extension"}
+            TB2.ctx.close()
+        except Exception as e:  # pragma: no cover
+            out["estimator"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_reference(A, ctx, fes, budget_s=15.0)
     if rank == 0:
@@ -402,6 +435,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcg", action="store_true")
+    ap.add_argument("--no-est", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":

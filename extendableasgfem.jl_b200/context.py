@@ -185,6 +185,11 @@ class Context:
         self._ck(self.lib.asgfem_last_apply_ms(self.h, C.byref(out)))
         return out.value
 
+    def last_estimate_ms(self):
+        out = C.c_double()
+        self._ck(self.lib.asgfem_last_estimate_ms(self.h, C.byref(out)))
+        return out.value
+
     def apply_host(self, x, out=None):
         x = _f64(x)
         out = np.empty_like(x) if out is None else out

@@ -574,6 +574,13 @@ extern "C" int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms) {
     return 0;
 }
 
+extern "C" int asgfem_last_estimate_ms(asgfem_ctx* ctx, double* ms) {
+    CTX_OR_FAIL(ctx);
+    ASG_CHECK(ctx, ms, ASGFEM_EINVAL, "null output");
+    *ms = ctx->last_estimate_ms;
+    return 0;
+}
+
 static int ensure_work_slots(asgfem_ctx* ctx, int need) {
     if ((int)ctx->slots.size() >= need) return 0;
     return asgfem_vec_alloc(ctx, need);

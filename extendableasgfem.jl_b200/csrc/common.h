@@ -123,6 +123,7 @@ struct asgfem_ctx {
     // kernels
     int apply_variant = 0;
     double last_apply_ms = 0;
+    double last_estimate_ms = 0;
     asgfem::ApplyPlan* plan = nullptr;
     asgfem::PrecondPlan* precond = nullptr;
     void* rowplan = nullptr;  // asgfem::RowPlan (apply_rows.cu)

@@ -410,6 +410,7 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
     ASG_CUDA(ctx, cudaFuncSetAttribute(k_est_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ASG_CUDA(ctx, cudaFuncSetAttribute(k_est_jumps, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int gridc = (int)std::min<int64_t>(ncells, 148 * 8), gridf = (int)std::min<int64_t>(nfaces, 148 * 8);
+    ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     k_est_volume<<<gridc, 256, smem_vol, ctx->stream>>>(a);
     k_est_jumps<<<gridf, 256, smem_jmp, ctx->stream>>>(a);
     ASG_CUDA(ctx, cudaGetLastError());
@@ -428,6 +429,7 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
                                                                             (double*)d_sums.p + N_ext);
     k_add_face_jumps<<<gridc, 256, 0, ctx->stream>>>(a.E, a.JF, a.cell_faces, ncells, ldE, (int)N_ext);
     ASG_CUDA(ctx, cudaGetLastError());
+    ASG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     std::vector<double> sums((size_t)(2 * N_ext));
     ASG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums.p, sizeof(double) * 2 * N_ext, cudaMemcpyDeviceToHost, ctx->stream));
 
@@ -443,6 +445,11 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
     }
     ASG_CUDA(ctx, cudaGetLastError());
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        float ms = 0;
+        ASG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_estimate_ms = ms;
+    }
     for (int64_t j = 0; j < N_ext; ++j) {
         double vol = std::sqrt(sums[j]);                       // eta4modes[j] = sqrt(sum(eta4cell[:,j]))  (:362-364)
         eta4modes[j] = std::sqrt(vol * vol + sums[N_ext + j]);  // sqrt(eta4modes[j]^2 + sum(jumps4face))   (:414)

@@ -128,6 +128,9 @@ int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax); /* host vec
 int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant);
 /* duration of the last asgfem_apply kernel(s) in milliseconds, from CUDA events on the library's stream */
 int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms);
+/* Device time (CUDA events) of the kernels of the last asgfem_estimate_poisson_primal call: cell residuals, face jumps,
+ * column sums; excludes the upload of the tables and the download of eta4cell.  Measurement hook, no reference seam. */
+int asgfem_last_estimate_ms(asgfem_ctx* ctx, double* ms);
 
 /* ---- (a8) mean-based preconditioner -------------------------------------------------------------
  * setup: MyPreconditionerPrimal (solvers_poisson_primal.jl:30-44): K_0 with the boundary dofs pinned,
