@@ -55,6 +55,7 @@ PROTOTYPES = {
     "asgfem_apply": (c_i32, [vp, c_i32, c_i32]),
     "asgfem_apply_host": (c_i32, [vp, vp, vp]),
     "asgfem_set_apply_variant": (c_i32, [vp, c_i32]),
+    "asgfem_apply_rows": (c_i32, [vp, c_i32, c_i32, c_i64, c_i64]),
     "asgfem_last_apply_ms": (c_i32, [vp, P(c_f64)]),
     "asgfem_last_estimate_ms": (c_i32, [vp, P(c_f64)]),
     "asgfem_precond_setup": (c_i32, [vp]),

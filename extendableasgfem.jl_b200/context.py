@@ -180,6 +180,10 @@ class Context:
     def apply(self, sx, sy):
         self._ck(self.lib.asgfem_apply(self.h, sx, sy))
 
+    def apply_rows(self, sx, sy, row0, row1):
+        """Operator on the local rows [row0, row1) (0-based); see asgfem_apply_rows."""
+        self._ck(self.lib.asgfem_apply_rows(self.h, sx, sy, row0, row1))
+
     def last_apply_ms(self):
         out = C.c_double()
         self._ck(self.lib.asgfem_last_apply_ms(self.h, C.byref(out)))

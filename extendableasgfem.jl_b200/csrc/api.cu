@@ -567,6 +567,26 @@ extern "C" int asgfem_apply(asgfem_ctx* ctx, int32_t sx, int32_t sy) {
     return 0;
 }
 
+extern "C" int asgfem_apply_rows(asgfem_ctx* ctx, int32_t sx, int32_t sy, int64_t row0, int64_t row1) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, sx) || check_slot(ctx, sy)) return ASGFEM_EINVAL;
+    ASG_CHECK(ctx, sx != sy, ASGFEM_EINVAL, "apply_rows: x and y must be different slots");
+    ASG_CHECK(ctx, row0 >= 0 && row1 >= row0, ASGFEM_EINVAL, "apply_rows: bad row range");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    int rc = ensure_ready_for_apply(ctx);
+    if (rc) return rc;
+    ctx->last_apply_ms = 0;
+    const int64_t nrows_all = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
+    if (row0 >= std::min(row1, nrows_all)) return 0;
+    rc = apply_launch(ctx, ctx->slots[sx], ctx->slots[sy], row0, row1);
+    if (rc) return rc;
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    ASG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_apply_ms = ms;
+    return 0;
+}
+
 extern "C" int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms) {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ms, ASGFEM_EINVAL, "null output");

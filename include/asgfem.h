@@ -182,6 +182,10 @@ int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ex
  * Vectors have n_local rows; only owned rows are written by apply.  The host layer (torch.distributed /
  * NCCL) exchanges halo rows between the pack/unpack calls and all-reduces the partial dots. */
 int asgfem_set_owned_rows(asgfem_ctx* ctx, int64_t n_owned);
+/* Operator on the local rows [row0, row1) only (0-based, half open, clipped to the owned rows); the other rows of slot sy
+ * are left untouched.  Lets the host layer apply the rows that reference no halo column while the halo exchange is in
+ * flight, and the rows along the partition boundary afterwards.  asgfem_last_apply_ms reports this launch. */
+int asgfem_apply_rows(asgfem_ctx* ctx, int32_t sx, int32_t sy, int64_t row0, int64_t row1);
 /* device pointer to the private (row-major n_local x ldN) storage of a slot, and its leading dimension */
 int asgfem_vec_device_ptr(asgfem_ctx* ctx, int32_t slot, void** dptr, int64_t* ld);
 /* gather rows[0..nrows) (1-based local ids) of a slot into a dense device buffer (nrows x N) / scatter back */

@@ -444,3 +444,26 @@ def test_operator_properties_p2_hermite_at_scale():
             assert relerr(out, ref) < TOL_APPLY
     assert ref is not None
     ctx.close()
+
+
+def test_apply_rows_ranges_compose(c1):
+    """asgfem_apply_rows on a partition of the rows reproduces asgfem_apply bit for bit and leaves the other rows alone."""
+    ctx = make_ctx(c1)
+    ctx.vec_alloc(3)
+    ctx.vec_fill_random(0, 11)
+    ctx.apply(0, 1)
+    full = ctx.vec_download(1)
+    ctx.vec_fill_random(2, 5)
+    before = ctx.vec_download(2).copy()
+    n = c1.n
+    ctx.apply_rows(0, 2, n // 3, 2 * n // 3)
+    part = ctx.vec_download(2).reshape(c1.N, n)  # reference layout: mode blocks of n dofs
+    assert np.array_equal(part[:, n // 3:2 * n // 3], full.reshape(c1.N, n)[:, n // 3:2 * n // 3])
+    assert np.array_equal(part[:, :n // 3], before.reshape(c1.N, n)[:, :n // 3])
+    ctx.apply_rows(0, 2, 0, n // 3)
+    ctx.apply_rows(0, 2, 2 * n // 3, n + 100)  # clipped to the owned rows
+    assert np.array_equal(ctx.vec_download(2), full)
+    from asgfem_b200 import _lib
+    with pytest.raises(_lib.AsgfemError):
+        ctx.apply_rows(0, 2, 5, 3)
+    ctx.close()
