@@ -63,6 +63,9 @@ PROTOTYPES = {
     "asgfem_precond_apply_host": (c_i32, [vp, vp, vp]),
     "asgfem_pcg": (c_i32, [vp, vp, c_i32, c_f64, c_f64, c_i64, P(Stats)]),
     "asgfem_solve_primal_host": (c_i32, [vp, vp, vp, c_f64, c_f64, c_i64, P(Stats)]),
+    "asgfem_set_precond_matrix_csc": (c_i32, [vp, vp, vp, vp]),
+    "asgfem_bicgstab": (c_i32, [vp, c_i32, c_i32, c_f64, c_f64, c_i64, P(Stats)]),
+    "asgfem_solve_logprimal_host": (c_i32, [vp, vp, vp, c_f64, c_f64, c_i64, P(Stats)]),
     "asgfem_estimate_poisson_primal": (c_i32, [vp, c_i32, c_i64, c_i64, vp, c_i32, vp, vp, vp, c_i32, vp, vp, vp, vp]),
     "asgfem_set_owned_rows": (c_i32, [vp, c_i64]),
     "asgfem_vec_device_ptr": (c_i32, [vp, c_i32, P(vp), P(c_i64)]),

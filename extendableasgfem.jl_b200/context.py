@@ -229,6 +229,28 @@ class Context:
         self._ck(self.lib.asgfem_solve_primal_host(self.h, _ptr(sol), _ptr(b0), atol, rtol, itmax, C.byref(st)))
         return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
 
+    # ---- log-transformed primal problem ------------------------------------------------------------
+    def set_precond_matrix_csc(self, colptr=None, rowval=None, nzval=None):
+        """SPD matrix for the mean preconditioner (default: matrix 0); None returns to the default."""
+        if colptr is None:
+            self._ck(self.lib.asgfem_set_precond_matrix_csc(self.h, None, None, None))
+            return
+        colptr, rowval, nzval = _i64(colptr), _i64(rowval), _f64(nzval)
+        self._ck(self.lib.asgfem_set_precond_matrix_csc(self.h, _ptr(colptr), _ptr(rowval), _ptr(nzval)))
+
+    def bicgstab(self, slot_b, slot_x, atol=1e-14, rtol=1e-14, itmax=0):
+        st = _lib.Stats()
+        self._ck(self.lib.asgfem_bicgstab(self.h, slot_b, slot_x, atol, rtol, itmax, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
+
+    def solve_logprimal_host(self, sol, b, atol=1e-14, rtol=1e-14, itmax=0):
+        assert sol.dtype == np.float64 and sol.flags.c_contiguous
+        b = _f64(b)
+        assert b.size == sol.size
+        st = _lib.Stats()
+        self._ck(self.lib.asgfem_solve_logprimal_host(self.h, _ptr(sol), _ptr(b), atol, rtol, itmax, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
+
     # ---- estimator -------------------------------------------------------------------------------
     def estimate_poisson_primal(self, slot_u, mi_ext, xref, w, sf, wf, ncells, f_at_qp=None):
         mi = _i64(np.asarray(mi_ext))

@@ -683,6 +683,59 @@ extern "C" int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const doub
     return vec_to_host_layout(ctx, ctx->slots[0], sol);
 }
 
+// ---- log-transformed primal problem ----------------------------------------------------------------
+extern "C" int asgfem_set_precond_matrix_csc(asgfem_ctx* ctx, const int64_t* colptr, const int64_t* rowval,
+                                             const double* nzval) {
+    CTX_OR_FAIL(ctx);
+    ASG_CHECK(ctx, ctx->n > 0 && ctx->nnz > 0, ASGFEM_ESTATE, "set_precond_matrix_csc: set_pattern_csc first");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    precond_free(ctx);
+    ctx->h_precond_vals.clear();
+    if (!colptr) return 0;
+    ASG_CHECK(ctx, rowval && nzval, ASGFEM_EINVAL, "set_precond_matrix_csc: bad arguments");
+    std::vector<double> csr((size_t)ctx->nnz, 0.0);
+    for (int64_t c = 0; c < ctx->n; ++c) {
+        int64_t q = ctx->h_csc_colptr[c], q1 = ctx->h_csc_colptr[c + 1];
+        for (int64_t p = colptr[c] - 1; p < colptr[c + 1] - 1; ++p) {
+            int64_t r = rowval[p] - 1;
+            while (q < q1 && ctx->h_csc_row[q] < r) ++q;
+            ASG_CHECK(ctx, q < q1 && ctx->h_csc_row[q] == r, ASGFEM_EINVAL,
+                      "set_precond_matrix_csc: entry outside the shared pattern");
+            csr[ctx->h_csc2csr[q]] = nzval[p];
+        }
+    }
+    ctx->h_precond_vals.swap(csr);
+    return 0;
+}
+
+extern "C" int asgfem_bicgstab(asgfem_ctx* ctx, int32_t slot_b, int32_t slot_x, double atol, double rtol, int64_t itmax,
+                               asgfem_stats* stats) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, slot_b) || check_slot(ctx, slot_x)) return ASGFEM_EINVAL;
+    ASG_CHECK(ctx, slot_b != slot_x, ASGFEM_EINVAL, "bicgstab: b and x must be different slots");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    int rc = ensure_ready_for_apply(ctx);
+    if (rc) return rc;
+    if (!ctx->precond && (rc = precond_setup(ctx))) return rc;
+    return bicgstab_solve(ctx, ctx->slots[slot_b], ctx->slots[slot_x], atol, rtol, itmax, stats);
+}
+
+extern "C" int asgfem_solve_logprimal_host(asgfem_ctx* ctx, double* sol, const double* b, double atol, double rtol,
+                                           int64_t itmax, asgfem_stats* stats) {
+    CTX_OR_FAIL(ctx);
+    ASG_CHECK(ctx, sol && b, ASGFEM_EINVAL, "null host pointer");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    int rc = ensure_ready_for_apply(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_work_slots(ctx, 2))) return rc;
+    if ((rc = vec_to_device_layout(ctx, sol, ctx->slots[0]))) return rc;
+    if ((rc = vec_to_device_layout(ctx, b, ctx->slots[1]))) return rc;
+    if ((rc = vec_axpy(ctx, 1.0, ctx->slots[0], ctx->slots[1]))) return rc;  // b = deepcopy(sol) + b0   (:149-152)
+    if (!ctx->precond && (rc = precond_setup(ctx))) return rc;
+    if ((rc = bicgstab_solve(ctx, ctx->slots[1], ctx->slots[0], atol, rtol, itmax, stats))) return rc;
+    return vec_to_host_layout(ctx, ctx->slots[0], sol);
+}
+
 // ---- estimator ----------------------------------------------------------------------------------
 extern "C" int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,
                                               const int64_t* mi_ext, int32_t nq, const double* xref, const double* w,

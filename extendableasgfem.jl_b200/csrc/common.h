@@ -80,6 +80,7 @@ struct asgfem_ctx {
     int32_t* d_col = nullptr;
     int32_t M = -1;          // number of KLE matrices beyond the mean (K_0..K_M)
     double* d_vals = nullptr;  // (M+1) x nnz, CSR order
+    std::vector<double> h_precond_vals;  // optional SPD matrix for the preconditioner (CSR order); empty: matrix 0
     std::vector<uint8_t> h_bmask;
     uint8_t* d_bmask = nullptr;
     std::vector<int64_t> h_bdofs;
@@ -208,6 +209,7 @@ int precond_apply(asgfem_ctx* ctx, const double* r, double* z);
 // pcg.cu
 int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, double rtol, int64_t itmax,
               asgfem_stats* stats);
+int bicgstab_solve(asgfem_ctx* ctx, double* b, double* x, double atol, double rtol, int64_t itmax, asgfem_stats* stats);
 // assemble.cu
 int assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w);
 // estimate.cu

@@ -167,4 +167,110 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
     return 0;
 }
 
+// BiCGStab on the left-preconditioned system P^-1 S x = P^-1 b (device counterpart of the Krylov.gmres call of
+// solve_logpoisson_primal!, src/modelproblems/solvers_logpoisson_primal.jl:163): S = the tensorized operator with
+// nonsymmetric blocks, P = I (x) chol(A).  b is overwritten (boundary rows zeroed, then used as work space).
+int bicgstab_solve(asgfem_ctx* ctx, double* b, double* x, double atol, double rtol, int64_t itmax, asgfem_stats* stats) {
+    const int64_t n = ctx->n, ld = ctx->ld, total = n * ld;
+    const size_t bytes = sizeof(double) * (size_t)total;
+    if (itmax <= 0) itmax = 2 * n * ctx->N;
+    double *r = nullptr, *rh = nullptr, *p = nullptr, *v = nullptr, *t = nullptr, *w = nullptr;
+    auto cleanup = [&]() {
+        for (double* q : {r, rh, p, v, t, w})
+            if (q) cudaFree(q);
+    };
+    PCG_CUDA(cudaMalloc((void**)&r, bytes));
+    PCG_CUDA(cudaMalloc((void**)&rh, bytes));
+    PCG_CUDA(cudaMalloc((void**)&p, bytes));
+    PCG_CUDA(cudaMalloc((void**)&v, bytes));
+    PCG_CUDA(cudaMalloc((void**)&t, bytes));
+    PCG_CUDA(cudaMalloc((void**)&w, bytes));
+    Timer tall(ctx->stream), tpart(ctx->stream);
+    double ms_apply = 0, ms_prec = 0;
+    auto op = [&](const double* in, double* out) -> int {  // out = P^-1 S in
+        tpart.start();
+        int rc = apply_launch(ctx, in, w);
+        ms_apply += tpart.stop();
+        if (rc) return rc;
+        tpart.start();
+        rc = precond_apply(ctx, w, out);
+        ms_prec += tpart.stop();
+        return rc;
+    };
+    tall.start();
+    PCG_RC(vec_mask_rows(ctx, b));
+    // r = P^-1 (b - S x)
+    PCG_RC(apply_launch(ctx, x, w));
+    PCG_RC(vec_axpy(ctx, -1.0, w, b));
+    PCG_RC(precond_apply(ctx, b, r));
+    PCG_CUDA(cudaMemcpyAsync(rh, r, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    PCG_CUDA(cudaMemcpyAsync(p, r, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    double rr = 0;
+    PCG_RC(vec_dot(ctx, r, r, n, &rr));
+    const double r0 = std::sqrt(std::max(rr, 0.0));
+    const double eps = atol + rtol * r0;
+    double rho = rr, alpha = 1, omega = 1;
+    double ms_setup = tall.stop();
+    int64_t k = 0;
+    double rn = r0;
+    tall.start();
+    while (k < itmax && rn > eps) {
+        PCG_RC(op(p, v));
+        double rhv = 0;
+        PCG_RC(vec_dot(ctx, rh, v, n, &rhv));
+        if (rhv == 0.0 || !std::isfinite(rhv)) {
+            cleanup();
+            return fail(ctx, ASGFEM_ENUMERIC, "bicgstab: breakdown (shadow residual orthogonal to P^-1 S p)");
+        }
+        alpha = rho / rhv;
+        PCG_RC(vec_axpy(ctx, alpha, p, x));    // x += alpha p
+        PCG_RC(vec_axpy(ctx, -alpha, v, r));   // s = r - alpha v   (kept in r)
+        double ss = 0;
+        PCG_RC(vec_dot(ctx, r, r, n, &ss));
+        ++k;
+        rn = std::sqrt(std::max(ss, 0.0));
+        if (rn <= eps) break;
+        PCG_RC(op(r, t));
+        double ts = 0, tt = 0;
+        PCG_RC(vec_dot(ctx, t, r, n, &ts));
+        PCG_RC(vec_dot(ctx, t, t, n, &tt));
+        if (!(tt > 0.0) || !std::isfinite(tt)) {
+            cleanup();
+            return fail(ctx, ASGFEM_ENUMERIC, "bicgstab: breakdown (P^-1 S s = 0)");
+        }
+        omega = ts / tt;
+        PCG_RC(vec_axpy(ctx, omega, r, x));    // x += omega s
+        PCG_RC(vec_axpy(ctx, -omega, t, r));   // r = s - omega t
+        PCG_RC(vec_dot(ctx, r, r, n, &ss));
+        rn = std::sqrt(std::max(ss, 0.0));
+        double rho_new = 0;
+        PCG_RC(vec_dot(ctx, rh, r, n, &rho_new));
+        if (rho_new == 0.0 || omega == 0.0) {
+            if (rn <= eps) break;
+            cleanup();
+            return fail(ctx, ASGFEM_ENUMERIC, "bicgstab: breakdown (rho = 0 or omega = 0)");
+        }
+        const double beta = (rho_new / rho) * (alpha / omega);
+        PCG_RC(vec_axpy(ctx, -omega, v, p));   // p = r + beta (p - omega v)
+        PCG_RC(vec_xpay(ctx, r, beta, p));
+        rho = rho_new;
+    }
+    double ms_iter = tall.stop();
+    if (stats) {
+        stats->niter = k;
+        stats->solved = rn <= eps ? 1 : 0;
+        stats->_pad = 0;
+        stats->rz0 = r0;
+        stats->rzk = rn;
+        stats->residual = rn;  // norm of the (recursively updated) preconditioned residual
+        stats->ms_setup = ms_setup;
+        stats->ms_iterations = ms_iter;
+        stats->ms_apply = ms_apply;
+        stats->ms_precond = ms_prec;
+    }
+    PCG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+    return 0;
+}
+
 }  // namespace asgfem

@@ -548,8 +548,12 @@ int precond_setup(asgfem_ctx* ctx) {
     ASG_CHECK(ctx, ctx->N > 0, ASGFEM_ESTATE, "precond_setup: multi-indices not set");
     // download K_0 (device holds the authoritative copy, e.g. after device assembly)
     std::vector<double> k0((size_t)ctx->nnz);
-    ASG_CUDA(ctx, cudaMemcpyAsync(k0.data(), ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
-    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ctx->h_precond_vals.empty()) {  // asgfem_set_precond_matrix_csc: e.g. the Laplacian of the log-transformed problem
+        k0 = ctx->h_precond_vals;
+    } else {
+        ASG_CUDA(ctx, cudaMemcpyAsync(k0.data(), ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     CholFactor F;
     std::string err;
     // dof coordinates (if mesh and space are known) steer the nested dissection towards straight separators

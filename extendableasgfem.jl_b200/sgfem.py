@@ -5,6 +5,8 @@
 * solve_primal           solve_primal!(sol, A0, Am, b0, G, nmodes, bfac; atol, rtol)
                          src/modelproblems/solvers_poisson_primal.jl:130-169
 * solve                  solve!(PoissonProblemPrimal, sol, C; rhs, ...)   src/modelproblems/poisson_primal.jl:38-81
+* solve_logpoisson_primal  solve_logpoisson_primal!(sol, A, N0, Nm, b0, G, nmodes, bfac; atol, rtol)
+                         src/modelproblems/solvers_logpoisson_primal.jl:130-172 (matrices and load vectors from the caller)
 * mul / ldiv             LinearAlgebra.mul! (:86-124) / ldiv! (:46-78) on host vectors
 * estimate               estimate(PoissonProblemPrimal, sol, C; rhs, bonus_quadorder, tail_extension)
                          src/estimate.jl:260-418
@@ -64,13 +66,14 @@ class SGFEVector:
         return len(self.entries)
 
 
-def _install_matrices(ctx, A0, Am):
-    """A0, Am: scipy sparse matrices as a Julia caller holds FEMatrix.entries.cscmatrix."""
+def _install_matrices(ctx, A0, Am, extra=()):
+    """A0, Am: scipy sparse matrices as a Julia caller holds FEMatrix.entries.cscmatrix; `extra`: further matrices whose
+    entries must lie in the shared pattern (e.g. the preconditioner matrix of the log-transformed problem)."""
     mats = [sp.csc_matrix(A0)] + [sp.csc_matrix(A) for A in Am]
     n = mats[0].shape[0]
     union = mats[0].copy()
     union.data = np.ones_like(union.data)
-    for A in mats[1:]:
+    for A in mats[1:] + [sp.csc_matrix(E) for E in extra]:
         B = A.copy()
         B.data = np.ones_like(B.data)
         union = union + B
@@ -91,6 +94,25 @@ def solve_primal(sol: SGFEVector, A0, Am, b0, G=None, nmodes=None, bfac=1, atol=
     bdofs = sol.FES_space.bdofs + 1
     ctx.set_bdofs(bdofs)
     stats = ctx.solve_primal_host(sol.entries, np.asarray(b0, dtype=np.float64), atol, rtol, itmax)
+    return (bdofs, stats) if return_stats else bdofs
+
+
+def solve_logpoisson_primal(sol: SGFEVector, A, N0, Nm, b0, G=None, nmodes=None, bfac=1, atol=1.0e-14, rtol=1.0e-14,
+                            itmax=0, return_stats=False):
+    """Drop-in for solve_logpoisson_primal! (log-transformed primal problem): A = Laplacian, N0 / Nm = convection
+    matrices (scipy sparse, as the Julia caller holds FEMatrix.entries.cscmatrix), b0 = list of nmodes load vectors.
+    Overwrites sol.entries, returns bdofs.  The operator kernels are those of the primal problem with A + N0 as matrix 0
+    and N_e as matrices 1..M; the preconditioner is factorised from A alone; the Krylov method is BiCGStab on the device
+    instead of the reference's GMRES (same solution of the nonsingular system)."""
+    ctx = sol.TB.ctx
+    A = sp.csc_matrix(A)
+    _install_matrices(ctx, A + sp.csc_matrix(N0), Nm, extra=(A,))
+    A.sort_indices()
+    ctx.set_precond_matrix_csc(A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1, A.data)
+    bdofs = sol.FES_space.bdofs + 1
+    ctx.set_bdofs(bdofs)
+    b = np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1) for v in b0])
+    stats = ctx.solve_logprimal_host(sol.entries, b, atol, rtol, itmax)
     return (bdofs, stats) if return_stats else bdofs
 
 

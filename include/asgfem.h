@@ -159,6 +159,27 @@ typedef struct asgfem_stats {
 } asgfem_stats;
 int asgfem_pcg(asgfem_ctx* ctx, const double* b0, int32_t slot_x, double atol, double rtol, int64_t itmax,
                asgfem_stats* stats);
+/* ---- log-transformed primal problem ------------------------------------------------
+ * solve_logpoisson_primal!(sol, A, N0, Nm, b0, G, nmodes, bfac; atol, rtol)
+ *     (src/modelproblems/solvers_logpoisson_primal.jl:130-172; operator MySystemLogPrimal.mul! :87-127,
+ *      preconditioner MyPreconditionerLogPrimal = I (x) LU(A) :31-83)
+ * The operator has the tensor structure of the primal one: the caller installs A + N0 as matrix 0 and the convection
+ * matrices N_e as matrices 1..M (asgfem_set_stiffness*), nothing in the operator kernels assumes symmetric values.
+ * The preconditioner is built from the SPD Laplacian A alone, handed over here (CSC on a sub-pattern of the shared
+ * pattern, 1-based; colptr == NULL returns to the default: matrix 0).  Invalidates an existing factorisation. */
+int asgfem_set_precond_matrix_csc(asgfem_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const double* nzval);
+/* Nonsymmetric Krylov solve on the device: BiCGStab on the left-preconditioned system P^-1 S x = P^-1 b, stopping on
+ * ||P^-1 r_k|| <= atol + rtol ||P^-1 r_0|| (the quantity Krylov.gmres(...; ldiv = true, M = P) monitors, :163).  The
+ * reference uses GMRES; both converge to the solution of the same nonsingular system (checked against the direct solve
+ * of the assembled block system, solve_logpoisson_primal_full! :175-230).  slot_b: right-hand side (boundary rows are
+ * zeroed here), slot_x: warm start / solution.  stats: rz0 / rzk = preconditioned residual norms. */
+int asgfem_bicgstab(asgfem_ctx* ctx, int32_t slot_b, int32_t slot_x, double atol, double rtol, int64_t itmax,
+                    asgfem_stats* stats);
+/* whole seam on host vectors: sol (n*N, in: warm start, out: solution), b (n*N: the per-mode load vectors b0[m] stacked
+ * in the reference layout); the right-hand side is deepcopy(sol) + b with the boundary rows zeroed (:149-156). */
+int asgfem_solve_logprimal_host(asgfem_ctx* ctx, double* sol, const double* b, double atol, double rtol, int64_t itmax,
+                                asgfem_stats* stats);
+
 /* whole seam on host vectors: sol (n*N, in: warm start, out: solution), b0 (n) */
 int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const double* b0, double atol, double rtol,
                              int64_t itmax, asgfem_stats* stats);

@@ -67,11 +67,14 @@ function set_multiindices!(ctx::Context, OBT, multi_indices)
 end
 
 "uploads A0 and Am (FEMatrix objects of poisson_primal.jl:56-63) into the shared pattern"
-function set_matrices!(ctx::Context, A0, Am)
+function set_matrices!(ctx::Context, A0, Am; extra = ())
     csc0::SparseMatrixCSC{Float64, Int64} = A0.entries.cscmatrix
-    pattern = copy(csc0)
+    pattern = abs.(csc0)
     for A in Am            # union pattern (ExtendableSparse may have dropped exact zeros in some K_m)
         pattern += abs.(A.entries.cscmatrix)
+    end
+    for E in extra         # further CSC matrices that must fit the pattern (preconditioner matrix)
+        pattern += abs.(E)
     end
     n = size(pattern, 1)
     check(ctx, ccall((:asgfem_set_pattern_csc, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}),
@@ -110,6 +113,37 @@ function solve_primal!(sol::SGFEVector, A0, Am, b0, G, nmodes, bfac; atol = 1.0e
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Int64, Ref{Stats}),
         ctx.h, sol.entries, b0.entries, atol, rtol, 0, stats))
     @info "PCG on GPU: $(stats[].niter) iterations, solver residual = $(stats[].residual)"
+    return bdofs
+end
+
+# ---- seam 1b: log-transformed primal problem (SURVEY.md section 8(f), row f1) ------------------------------
+"""
+Drop-in replacement of `ExtendableASGFEM.solve_logpoisson_primal!` (solvers_logpoisson_primal.jl:130-172): same
+arguments, overwrites `sol.entries`, returns `bdofs`.  A + N0 is installed as matrix 0 and the convection matrices N_e as
+matrices 1..M of the same fused operator; the preconditioner is factorised from the Laplacian A alone; BiCGStab on the GPU.
+"""
+function solve_logpoisson_primal!(sol::SGFEVector, A, N0, Nm, b0, G, nmodes, bfac; atol = 1.0e-14, rtol = 1.0e-14, device = 0)
+    ctx = Context(device)
+    OBT = OrthogonalPolynomialType(sol.TB.ONB)
+    set_multiindices!(ctx, OBT, sol.TB.multi_indices)
+    cA::SparseMatrixCSC{Float64, Int64} = A.entries.cscmatrix
+    D = deepcopy(A)                       # diagonal block A + N0; abs.(A) keeps the entries of A in the union pattern
+    D.entries.cscmatrix .+= N0.entries.cscmatrix
+    set_matrices!(ctx, D, Nm; extra = (cA,))
+    check(ctx, ccall((:asgfem_set_precond_matrix_csc, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+        ctx.h, cA.colptr, cA.rowval, cA.nzval))
+    bdofs = boundary_dofs(sol.FES_space[1])
+    check(ctx, ccall((:asgfem_set_bdofs, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}), ctx.h, length(bdofs), bdofs))
+    b = zeros(Float64, length(sol.entries))          # per-mode load vectors stacked in the layout of sol.entries (:149-152)
+    n = div(length(b), nmodes)
+    for m in 1:nmodes
+        b[((m - 1) * n + 1):(m * n)] .= b0[m][1]
+    end
+    stats = Ref{Stats}()
+    check(ctx, ccall((:asgfem_solve_logprimal_host, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Int64, Ref{Stats}),
+        ctx.h, sol.entries, b, atol, rtol, 0, stats))
+    @info "BiCGStab on GPU: $(stats[].niter) iterations, preconditioned residual = $(stats[].residual)"
     return bdofs
 end
 

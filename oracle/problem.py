@@ -52,6 +52,28 @@ def synthetic(nx, order, N, M=20, assemble=True):
     return build(m, order, modes, poly.LEGENDRE, C, assemble=assemble)
 
 
+def logprimal_like(nrefs=3, order=2):
+    """Test problem with the STRUCTURE of the log-transformed primal system (solvers_logpoisson_primal.jl:14-22): Hermite
+    coupling G, SPD Laplacian-like A, nonsymmetric convection-like N0 and N_e on the shared pattern, one load vector per
+    mode.  The matrices of the real problem come from the caller's assembly (logpoisson_primal.jl:95-128, third-party
+    operators + expa_PCE_mop) and are data at the seam; here they are derived from the cosinus stiffness matrices:
+    N_e = 0.5 K_e + 0.25 skew(K_e), N0 = 0.1 skew(K_0), with skew(B) = triu(B, 1) - triu(B, 1)^T."""
+    import scipy.sparse as sp
+    m = mesh_mod.uniform_refine(mesh_mod.grid_unitsquare(), nrefs)
+    C = coefficient.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0)
+    P = build(m, order, [[0], [1, 0], [0, 1], [2, 0], [1, 1], [0, 0, 1]], poly.HERMITE, C)
+
+    def skew(B):
+        U = sp.triu(B, 1)
+        return (U - U.T).tocsr()
+
+    P.A = P.A0
+    P.N0 = (0.1 * skew(P.A0)).tocsr()
+    P.Nm = [(0.5 * K + 0.25 * skew(K)).tocsr() for K in P.Am]
+    P.b0m = [P.b0 * (0.5 ** j) * (1 + 0.1 * j) for j in range(P.N)]
+    return P
+
+
 def splitmix64_uniform(idx, seed=20240):
     """x = 2*u01(splitmix64(seed xor idx)) - 1, generated identically on host and device
     (SURVEY.md §8(d)); idx is the flat reference-layout index i + n*mu."""

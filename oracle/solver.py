@@ -228,3 +228,65 @@ def solve_full_primal(A0, Am, b0, G, nmodes, bdofs):
     big = S.assembled(penalty=1.0e60)
     bigb = make_rhs(np.zeros(n * nmodes), b0, bdofs, n, nmodes)
     return spla.spsolve(big.tocsc(), bigb)
+
+
+# ---- log-transformed primal problem -------------------------------------------------
+class SystemLogPrimal(SystemPrimal):
+    """MySystemLogPrimal (src/modelproblems/solvers_logpoisson_primal.jl:14-22) and its mul! (:87-127):
+    Ax[mu] = A x[mu] + N0 x[mu] + sum_{nu,e} G[(e-1)N+mu,nu] N_e x[nu]; boundary rows zeroed.  Same tensor structure as
+    the primal operator with the (nonsymmetric) convection matrices N_e in place of the K_e and A + N0 on the diagonal."""
+
+    def __init__(self, A, N0, Nm, G, bdofs, nmodes):
+        super().__init__(A + N0, Nm, G, bdofs, nmodes)
+        self.A = A.tocsr()
+        self.N0 = N0.tocsr()
+
+    def mul(self, x):
+        n, N = self.n, self.nmodes
+        M = len(self.Am)
+        Ax = np.zeros(n * N)
+        G = self.G
+        for mu in range(N):
+            blk = slice(mu * n, (mu + 1) * n)
+            Ax[blk] += self.A @ x[blk]    # :111
+            Ax[blk] += self.N0 @ x[blk]   # :112
+            entries = []
+            for e in range(M):
+                row = e * N + mu
+                for p in range(G.indptr[row], G.indptr[row + 1]):
+                    entries.append((G.indices[p], e, G.data[p]))
+            for nu, e, g in sorted(entries):  # for nu in 1:nmodes, e in 1:M (:115)
+                if g != 0:
+                    Ax[blk] += g * (self.Am[e] @ x[nu * n:(nu + 1) * n])
+            Ax[mu * n + self.bdofs] = 0       # :123-125
+        return Ax
+
+
+def make_rhs_log(sol0, b0, bdofs, n, N):
+    """solvers_logpoisson_primal.jl:149-156: b = deepcopy(sol); b[m] += b0[m] for EVERY mode; b[m][bdofs] = 0."""
+    b = sol0.copy() + np.concatenate([np.asarray(v, dtype=np.float64) for v in b0])
+    rows = (np.arange(N)[:, None] * n + np.asarray(bdofs)[None, :]).reshape(-1)
+    b[rows] = 0
+    return b
+
+
+def solve_logpoisson_primal(sol, A, N0, Nm, b0, G, nmodes, bdofs, atol=1.0e-14, rtol=1.0e-14):
+    """solve_logpoisson_primal! (:130-172): GMRES left-preconditioned with I (x) LU(A) (A with 1e60 on the boundary
+    diagonal, :31-45).  `sol` (warm start) is overwritten; returns stats."""
+    n = A.shape[0]
+    S = SystemLogPrimal(A, N0, Nm, G, bdofs, nmodes)
+    P = PreconditionerPrimal(A, bdofs, nmodes)
+    b = make_rhs_log(sol, b0, bdofs, n, nmodes)
+    x, stats = gmres(S, b, sol, P, atol=atol, rtol=rtol)
+    sol[:] = x
+    stats["residual"] = float(np.linalg.norm(S.mul(sol) - b))
+    return stats
+
+
+def solve_logpoisson_primal_full(A, N0, Nm, b0, G, nmodes, bdofs):
+    """solve_logpoisson_primal_full! (:175-230): assembled block matrix with the 1e60 boundary penalty, direct solve."""
+    n = A.shape[0]
+    S = SystemLogPrimal(A, N0, Nm, G, bdofs, nmodes)
+    big = S.assembled(penalty=1.0e60)
+    bigb = make_rhs_log(np.zeros(n * nmodes), b0, bdofs, n, nmodes)
+    return spla.spsolve(big.tocsc(), bigb)

@@ -467,3 +467,39 @@ def test_apply_rows_ranges_compose(c1):
     with pytest.raises(_lib.AsgfemError):
         ctx.apply_rows(0, 2, 5, 3)
     ctx.close()
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_logprimal_seam_matches_oracle(order):
+    """Row f1: solve_logpoisson_primal!(sol, A, N0, Nm, b0, G, nmodes, bfac) with Hermite coupling, nonsymmetric N_e and a
+    load vector per mode.  Operator vs the oracle's mul! (1e-12), device BiCGStab vs the direct solve of the assembled
+    block system (1e-10), preconditioner built from A alone."""
+    P = oproblem.logprimal_like(nrefs=3, order=order)
+    g = A.uniform_refine(A.grid_unitsquare(), 3)
+    fes = A.FESpace(g, order)
+    TB = A.TensorizedBasis(A.HermitePolynomials, P.multi_indices)
+    assert (TB.G != P.G).nnz == 0
+    sol = A.SGFEVector(fes, TB)
+    bdofs, stats = A.solve_logpoisson_primal(sol, P.A, P.N0, P.Nm, P.b0m, TB.G, TB.nmodes, 1, return_stats=True)
+    assert np.array_equal(bdofs, P.bdofs + 1)
+    assert stats["solved"] == 1
+    ref = osolver.solve_logpoisson_primal_full(P.A, P.N0, P.Nm, P.b0m, P.G, P.N, P.bdofs)
+    assert relerr(sol.entries, ref) < TOL_SOLVE
+    # operator parity on the installed matrices (A + N0 on the diagonal, N_e off it), every kernel variant
+    S = osolver.SystemLogPrimal(P.A, P.N0, P.Nm, P.G, P.bdofs, P.N)
+    x = np.random.default_rng(4).standard_normal(P.n * P.N)
+    y = S.mul(x)
+    ctx = TB.ctx
+    for variant in (1, 3, 4, 6, 7):
+        ctx.set_apply_variant(variant)
+        assert relerr(ctx.apply_host(x), y) < TOL_APPLY
+    # the preconditioner is A^-1 per mode, not (A + N0)^-1
+    import scipy.sparse.linalg as spla
+    keep = np.setdiff1d(np.arange(P.n), P.bdofs)
+    r = np.zeros(P.n * P.N)
+    r[:P.n][keep] = np.random.default_rng(5).standard_normal(len(keep))
+    z = A.ldiv(ctx, r)
+    zr = np.zeros(P.n)
+    zr[keep] = spla.spsolve(P.A.tocsc()[keep][:, keep], r[:P.n][keep])
+    assert relerr(z[:P.n], zr) < 1e-11
+    ctx.close()

@@ -76,3 +76,18 @@ def test_estimator_runs_and_is_consistent(c1):
     # eta4modes^2 = volume part + every interior face once; eta4cell counts interior faces twice
     assert np.all(em ** 2 <= ec.sum(axis=0) * (1 + 1e-12))
     assert np.all(ec.sum(axis=0) <= 2 * em ** 2 * (1 + 1e-12))
+
+
+def test_logprimal_oracle_definitions_agree():
+    """Row f1 (solvers_logpoisson_primal.jl): mul! == assembled block matrix, GMRES == direct solve of the full system."""
+    P = problem.logprimal_like(nrefs=2, order=1)
+    S = solver.SystemLogPrimal(P.A, P.N0, P.Nm, P.G, P.bdofs, P.N)
+    x = np.random.default_rng(2).standard_normal(P.n * P.N)
+    y = S.mul(x)
+    assert np.abs(y - S.assembled() @ x).max() <= 1e-13 * np.abs(y).max()
+    sol = np.zeros(P.n * P.N)
+    st = solver.solve_logpoisson_primal(sol, P.A, P.N0, P.Nm, P.b0m, P.G, P.N, P.bdofs)
+    assert st["solved"]
+    ref = solver.solve_logpoisson_primal_full(P.A, P.N0, P.Nm, P.b0m, P.G, P.N, P.bdofs)
+    assert np.linalg.norm(sol - ref) <= 1e-10 * np.linalg.norm(ref)
+    assert np.abs((S.N0 - S.N0.T)).max() > 0  # the test system really is nonsymmetric
