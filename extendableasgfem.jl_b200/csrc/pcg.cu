@@ -212,6 +212,7 @@ int bicgstab_solve(asgfem_ctx* ctx, double* b, double* x, double atol, double rt
     double rho = rr, alpha = 1, omega = 1;
     double ms_setup = tall.stop();
     int64_t k = 0;
+    int restarts = 0;
     double rn = r0;
     tall.start();
     while (k < itmax && rn > eps) {
@@ -245,10 +246,18 @@ int bicgstab_solve(asgfem_ctx* ctx, double* b, double* x, double atol, double rt
         rn = std::sqrt(std::max(ss, 0.0));
         double rho_new = 0;
         PCG_RC(vec_dot(ctx, rh, r, n, &rho_new));
-        if (rho_new == 0.0 || omega == 0.0) {
-            if (rn <= eps) break;
-            cleanup();
-            return fail(ctx, ASGFEM_ENUMERIC, "bicgstab: breakdown (rho = 0 or omega = 0)");
+        if (rn <= eps) break;
+        // (near-)breakdown: the shadow residual has become orthogonal to r, or the stabilisation step stagnated:
+        // restart from the current iterate with a new shadow residual
+        if (!(std::fabs(rho_new) > 1e-14 * rn * r0) || omega == 0.0 || !std::isfinite(rho_new)) {
+            if (++restarts > 50) {
+                cleanup();
+                return fail(ctx, ASGFEM_ENUMERIC, "bicgstab: repeated breakdown (rho = 0 or omega = 0)");
+            }
+            PCG_CUDA(cudaMemcpyAsync(rh, r, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            PCG_CUDA(cudaMemcpyAsync(p, r, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            rho = ss;
+            continue;
         }
         const double beta = (rho_new / rho) * (alpha / omega);
         PCG_RC(vec_axpy(ctx, -omega, v, p));   // p = r + beta (p - omega v)
