@@ -1,24 +1,34 @@
-// variant 7 of the fused SGFE operator: mode-stationary lanes with PACKED direction units.
+// variant 7 of the fused SGFE operator: mode-stationary lanes with PACKED direction units (default kernel).
 //
 //   Y[i, mu] = sum_k K_0[i,j_k] X[j_k,mu] + sum_{(m,nu) ~ mu} g sum_k K_m[i,j_k] X[j_k,nu]      (mul!, :101-117)
 //
-// Same two-phase scheme as variant 6 (apply_ts.cu): every lane OWNS modes (32 consecutive modes = one group, up to four
-// groups = slots per warp), keeps X[j_k, nu] of its modes in registers, forms T_m[nu] = sum_k K_m[i,j_k] X[j_k,nu] for
+// Same two-phase scheme as variant 6 (apply_ts.cu): every lane OWNS modes (32 consecutive modes = one group, four groups
+// = slots per warp, 16 warps), keeps X[j_k, nu] of its modes in registers, forms T_m[nu] = sum_k K_m[i,j_k] X[j_k,nu] for
 // the pairs (m, nu) that have a coupling, exchanges them through shared memory and gathers g * T_m[nu] into Y[i, mu].
 // Variant 6 evaluates a direction for all four groups of a warp as soon as one lane needs it: on the benchmark set
 // (total degree <= 3 in 20 dimensions + part of degree 4: 252 modes with all 20 directions, 1748 modes with <= 3) only
 // 29 % of the evaluated lanes are needed.  Here a group is one of two kinds, decided on the host:
 //
 //   dense   one unit per direction that any lane of the group needs; K_m[i, .] is the same for all lanes (broadcast
-//           loads), all 32 lanes store T (a full block of the exchange buffer, no predicate);
+//           16-byte loads), all 32 lanes store T into a full block of the exchange buffer (no predicate).  The block of
+//           the k-th unit is rotated by k lanes, so that the entries of ONE mode for consecutive directions - gathered by
+//           consecutive lanes of a sparse group - lie in different banks;
 //   sparse  every lane of the group needs at most Q directions: Q units, in unit q lane l handles ITS q-th direction.
-//           The K row is addressed per lane (16-byte loads, rows padded to an odd number of 16-byte granules so that
-//           different directions fall into different banks), the per-lane constants (K row offset, T index) live in
-//           Q registers per slot; lanes with fewer directions compute on K_0 and store to a dummy entry.
+//           The K row is addressed per lane (8-byte loads from a second copy of the K rows with an odd stride, so that
+//           rows of different directions start in different banks); the per-lane constants (K row offset, T index) live
+//           in Q registers per slot, the T blocks are first-fit packed; lanes with fewer directions compute on K_0 and
+//           store to a dummy entry.
 //
-// A unit is 7 (8) FMAs on register operands + 4 K loads + 1 store; the benchmark set needs 388 units per row instead of
-// the 1276 that variant 6 evaluates.  Units are processed several at a time (independent FMA chains).  Phase 2, the
-// metadata rings and the prefetch of the next row's K values / X rows are those of variant 6.
+// A unit is 7 (8) FMAs on register operands + the K loads + 1 store; the benchmark set needs 388 units per row instead of
+// the 1276 that variant 6 evaluates.  Units are processed several at a time (independent FMA chains).
+// Phase 2 gathers with per-lane lists whose ORDER is chosen on the host so that the lanes of a half-warp read 16
+// different banks.  Phase 2 of a dense group (a long list) does not need the X registers of the group, so it runs in a
+// warp with little phase-1 work as that warp's gather-only slot; the owner exports the mean term of the group through
+// the exchange buffer (one more list entry with weight 1).  One block barrier per row (double-buffered exchange), no
+// atomics, fixed summation order.  The CSR metadata rings (warp 0, cp.async two / three rows ahead, issued at the top of
+// the row), the cp.async staging of the next row's K values and the X loads of the next row issued before phase 2 hide
+// the global-memory latency behind the arithmetic of the current row.
+// Measured history and the rejected alternatives: DESIGN.md section 4, profiles/README.md.
 #include <algorithm>
 #include <numeric>
 
@@ -108,10 +118,10 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     P->slots = 4;
     if (const char* e = getenv("ASGFEM_TS2_SLOTS")) {
         int v = atoi(e);
-        if (v == 2 || v == 4 || v == 8) P->slots = v;
+        if (v == 4 || v == 8) P->slots = v;
     }
     const int TS2_SLOTS = P->slots;
-    const int maxW = TS2_SLOTS == 8 ? 8 : (TS2_SLOTS == 4 ? 16 : 32);
+    const int maxW = TS2_SLOTS == 8 ? 8 : 16;
     const int S_used = (G + maxW - 1) / maxW, W = (G + S_used - 1) / S_used;
     P->warps = W;
 
@@ -573,7 +583,7 @@ __device__ __forceinline__ void t2_units(const unsigned* wa, const double (&xa)[
 
 // S slots per warp; MULTI: rows longer than NS columns exist (processed in chunks, T accumulates in the exchange buffer)
 template <int NS, int Q, int S, bool MULTI>
-__global__ void __launch_bounds__(S == 8 ? 256 : (S == 4 ? 512 : 1024), 1) k_apply_ts2(Ts2Args a) {
+__global__ void __launch_bounds__(S == 8 ? 256 : 512, 1) k_apply_ts2(Ts2Args a) {
     constexpr int SLOTS = S;
     extern __shared__ __align__(16) unsigned char ts2_raw[];
     __shared__ __align__(512) double gt[64];
@@ -904,10 +914,8 @@ int apply_ts2_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
     do {                                  \
         if (P->slots == 8)                \
             LAUNCH_TS2_Q(NSV, 8, MV);     \
-        else if (P->slots == 4)           \
-            LAUNCH_TS2_Q(NSV, 4, MV);     \
         else                              \
-            LAUNCH_TS2_Q(NSV, 2, MV);     \
+            LAUNCH_TS2_Q(NSV, 4, MV);     \
     } while (0)
     if (P->nchunk_max > 1)
         LAUNCH_TS2_S(8, true);  // long rows: chunks of 8 columns
