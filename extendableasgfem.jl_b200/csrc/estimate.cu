@@ -433,7 +433,17 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
     std::vector<double> sums((size_t)(2 * N_ext));
     ASG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums.p, sizeof(double) * 2 * N_ext, cudaMemcpyDeviceToHost, ctx->stream));
 
-    // eta4cell to the host in the Julia layout (ncells x N_ext, column-major), chunk of columns at a time
+    // eta4cell to the host in the Julia layout (ncells x N_ext, column-major), chunk of columns at a time.  The caller's
+    // array is pageable; pinning it for the duration of the call turns the copies into direct DMA (large outputs only)
+    const size_t out_bytes = sizeof(double) * (size_t)ncells * (size_t)N_ext;
+    const bool pinned_out = out_bytes >= (64u << 20) && cudaHostRegister(eta4cell, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
+    if (!pinned_out) (void)cudaGetLastError();
+    struct Unpin {
+        void* p;
+        ~Unpin() {
+            if (p) cudaHostUnregister(p);
+        }
+    } unpin{pinned_out ? (void*)eta4cell : nullptr};
     int64_t jc_max = std::max<int64_t>(1, std::min<int64_t>(N_ext, (256ll << 20) / (8 * std::max<int64_t>(ncells, 1))));
     ASG_CUDA(ctx, cudaMalloc(&d_stage.p, sizeof(double) * ncells * jc_max));
     for (int64_t j0 = 0; j0 < N_ext; j0 += jc_max) {
