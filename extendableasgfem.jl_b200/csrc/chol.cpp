@@ -11,7 +11,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <cstdlib>
+#include <functional>
 #include <numeric>
+#include <thread>
 
 #include "common.h"
 
@@ -359,59 +363,137 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         return ASGFEM_ENOMEM;
     }
     std::vector<int64_t> cnext(Lcp.begin(), Lcp.end() - 1);
-    std::vector<double> x((size_t)n, 0.0);
-    std::fill(flag.begin(), flag.end(), -1);
-    for (int32_t k = 0; k < n; ++k) {
-        int32_t top;
-        ereach(k, top);
-        double d = 0.0;
-        for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
-            if (Ci[p] == k)
-                d += Cx[p];
-            else
-                x[Ci[p]] += Cx[p];
-        }
-        const double d_orig = d;
-        int64_t rp = F.Lp[k];
-        for (int32_t q = top; q < n; ++q) {
-            int32_t j = stack[q];
-            double lkj = x[j] / Lcx[Lcp[j]];
-            x[j] = 0.0;
-            for (int64_t p = Lcp[j] + 1; p < cnext[j]; ++p) x[Lci[p]] -= Lcx[p] * lkj;
-            d -= lkj * lkj;
-            int64_t at = cnext[j]++;
-            Lci[at] = k;
-            Lcx[at] = lkj;
-            F.Li[rp] = j;
-            F.Lx[rp] = lkj;
-            ++rp;
-        }
-        // a pivot that cancelled to rounding level means a (numerically) singular matrix, e.g. no Dirichlet dofs
-        if (!(d > 1.0e-12 * std::fabs(d_orig)) || !std::isfinite(d)) {
-            err = "K_0 restricted to the interior dofs is not positive definite (pivot " + std::to_string(k) + ")";
-            return ASGFEM_ENUMERIC;
-        }
-        double lkk = std::sqrt(d);
-        int64_t at = cnext[k]++;
-        Lci[at] = k;
-        Lcx[at] = lkk;
-        F.dinv[k] = 1.0 / lkk;
-        // rows of L in the output are sorted by column for coalesced/monotone access
-        // (ereach order is topological, not sorted)
+    // Rows of different nodes of the dissection tree at the same depth reach disjoint sets of columns (their subtrees),
+    // so the up-looking sweep runs level by level from the deepest nodes to the root with the nodes of a level in
+    // parallel (threads with private work vectors); the chunks of one separator stay in order inside one task.
+    struct Task {
+        int32_t lo, hi, depth;
+    };
+    std::vector<Task> tasks;
+    int32_t maxdepth = 0;
+    for (const BlockRec& b : F.blocks) {
+        if (!tasks.empty() && b.chunk > 0 && tasks.back().hi == b.start && tasks.back().depth == b.depth)
+            tasks.back().hi = b.start + b.len;
+        else
+            tasks.push_back({b.start, b.start + b.len, b.depth});
+        maxdepth = std::max(maxdepth, b.depth);
     }
-    for (int32_t k = 0; k < n; ++k) {
-        int64_t a = F.Lp[k], b = F.Lp[k + 1];
-        // sort (Li, Lx) of the row by column index
-        std::vector<std::pair<int32_t, double>> tmp;
-        tmp.reserve((size_t)(b - a));
-        for (int64_t p = a; p < b; ++p) tmp.push_back({F.Li[p], F.Lx[p]});
-        std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, double>& u, const std::pair<int32_t, double>& v) {
-            return u.first < v.first;
-        });
-        for (int64_t p = a; p < b; ++p) {
-            F.Li[p] = tmp[p - a].first;
-            F.Lx[p] = tmp[p - a].second;
+    std::vector<std::vector<int32_t>> level((size_t)maxdepth + 1);
+    for (int32_t t = 0; t < (int32_t)tasks.size(); ++t) level[(size_t)tasks[(size_t)t].depth].push_back(t);
+    int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (const char* e = std::getenv("ASGFEM_CHOL_THREADS")) nthreads = std::max(1, atoi(e));
+    if (n < 20000) nthreads = 1;
+    struct Work {
+        std::vector<double> x;
+        std::vector<int32_t> flag, stack;
+    };
+    std::vector<Work> work((size_t)nthreads);
+    for (Work& w : work) {
+        w.x.assign((size_t)n, 0.0);
+        w.flag.assign((size_t)n, -1);
+        w.stack.resize((size_t)n);
+    }
+    std::atomic<int32_t> bad_pivot{-1};
+    auto factor_rows = [&](Work& w, int32_t lo, int32_t hi) {
+        double* x = w.x.data();
+        int32_t* flag = w.flag.data();
+        int32_t* stack = w.stack.data();
+        for (int32_t k = lo; k < hi; ++k) {
+            // row pattern by row-subtree traversal (as in the counting pass)
+            int32_t top = n;
+            flag[k] = k;
+            for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+                int32_t i = Ci[p];
+                if (i > k) continue;
+                int32_t len = 0;
+                for (; flag[i] != k; i = parent[i]) {
+                    stack[len++] = i;
+                    flag[i] = k;
+                }
+                while (len > 0) stack[--top] = stack[--len];
+            }
+            double d = 0.0;
+            for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+                if (Ci[p] == k)
+                    d += Cx[p];
+                else
+                    x[Ci[p]] += Cx[p];
+            }
+            const double d_orig = d;
+            int64_t rp = F.Lp[k];
+            for (int32_t q = top; q < n; ++q) {
+                int32_t j = stack[q];
+                double lkj = x[j] / Lcx[Lcp[j]];
+                x[j] = 0.0;
+                for (int64_t p = Lcp[j] + 1; p < cnext[j]; ++p) x[Lci[p]] -= Lcx[p] * lkj;
+                d -= lkj * lkj;
+                int64_t at = cnext[j]++;
+                Lci[at] = k;
+                Lcx[at] = lkj;
+                F.Li[rp] = j;
+                F.Lx[rp] = lkj;
+                ++rp;
+            }
+            // a pivot that cancelled to rounding level means a (numerically) singular matrix, e.g. no Dirichlet dofs
+            if (!(d > 1.0e-12 * std::fabs(d_orig)) || !std::isfinite(d)) {
+                int32_t expect = -1;
+                bad_pivot.compare_exchange_strong(expect, k);
+                d = 1.0;  // keep going with a harmless value; the factorisation is rejected below
+            }
+            double lkk = std::sqrt(d);
+            int64_t at = cnext[k]++;
+            Lci[at] = k;
+            Lcx[at] = lkk;
+            F.dinv[k] = 1.0 / lkk;
         }
+    };
+    auto run_parallel = [&](int32_t ntask, const std::function<void(int, int32_t)>& body) {
+        const int nt = std::min<int>(nthreads, std::max<int32_t>(ntask, 1));
+        if (nt <= 1) {
+            for (int32_t t = 0; t < ntask; ++t) body(0, t);
+            return;
+        }
+        std::atomic<int32_t> next{0};
+        std::vector<std::thread> pool;
+        for (int th = 0; th < nt; ++th)
+            pool.emplace_back([&, th]() {
+                for (int32_t t = next.fetch_add(1); t < ntask; t = next.fetch_add(1)) body(th, t);
+            });
+        for (std::thread& th : pool) th.join();
+    };
+    if (nthreads == 1) {  // elimination order (best locality)
+        factor_rows(work[0], 0, n);
+        maxdepth = -1;
+    }
+    for (int32_t dpt = maxdepth; dpt >= 0; --dpt) {
+        const std::vector<int32_t>& lv = level[(size_t)dpt];
+        run_parallel((int32_t)lv.size(), [&](int th, int32_t t) {
+            const Task& tk = tasks[(size_t)lv[(size_t)t]];
+            factor_rows(work[(size_t)th], tk.lo, tk.hi);
+        });
+    }
+    if (bad_pivot.load() >= 0) {
+        err = "K_0 restricted to the interior dofs is not positive definite (pivot " + std::to_string(bad_pivot.load()) + ")";
+        return ASGFEM_ENUMERIC;
+    }
+    // rows of L in the output are sorted by column for coalesced/monotone access (ereach order is topological, not sorted)
+    {
+        const int32_t nchunk = (int32_t)std::min<int64_t>(n, 4 * (int64_t)nthreads);
+        run_parallel(nchunk, [&](int, int32_t c) {
+            const int32_t k0 = (int32_t)((int64_t)n * c / nchunk), k1 = (int32_t)((int64_t)n * (c + 1) / nchunk);
+            std::vector<std::pair<int32_t, double>> tmp;
+            for (int32_t k = k0; k < k1; ++k) {
+                const int64_t a = F.Lp[k], b = F.Lp[k + 1];
+                tmp.clear();
+                for (int64_t p = a; p < b; ++p) tmp.push_back({F.Li[p], F.Lx[p]});
+                std::sort(tmp.begin(), tmp.end(),
+                          [](const std::pair<int32_t, double>& u, const std::pair<int32_t, double>& v) { return u.first < v.first; });
+                for (int64_t p = a; p < b; ++p) {
+                    F.Li[p] = tmp[(size_t)(p - a)].first;
+                    F.Lx[p] = tmp[(size_t)(p - a)].second;
+                }
+            }
+        });
     }
     F.perm.resize((size_t)n);
     for (int32_t k = 0; k < n; ++k) F.perm[k] = full[perm[k]];
