@@ -503,3 +503,28 @@ def test_logprimal_seam_matches_oracle(order):
     zr[keep] = spla.spsolve(P.A.tocsc()[keep][:, keep], r[:P.n][keep])
     assert relerr(z[:P.n], zr) < 1e-11
     ctx.close()
+
+
+def test_apply_auto_variant_beyond_register_capacity():
+    """More modes than the mode-stationary kernels hold in registers (N > 2048, e.g. config 5 with 5000 multi-indices): the
+    automatic choice must fall back to a kernel without that limit and agree with the reference-order gather kernel."""
+    g = A.structured_unitsquare(17)
+    fes = A.FESpace(g, 1)
+    modes = A.graded_lex_multiindices(20, 2600)
+    TB = A.TensorizedBasis(A.LegendrePolynomials, modes)
+    sol = A.SGFEVector(fes, TB)
+    A.setup_device_problem(sol, A.StochasticCoefficientCosinus(tau=0.9, decay=2, mean=1, maxm=20))
+    ctx = TB.ctx
+    ctx.vec_alloc(3)
+    ctx.vec_fill_random(0, 7)
+    ctx.set_apply_variant(1)
+    ctx.apply(0, 1)
+    ctx.set_apply_variant(0)
+    ctx.apply(0, 2)
+    a, b = ctx.vec_download(1), ctx.vec_download(2)
+    assert relerr(b, a) < TOL_APPLY
+    from asgfem_b200 import _lib
+    with pytest.raises(_lib.AsgfemError):
+        ctx.set_apply_variant(7)
+        ctx.apply(0, 2)
+    ctx.close()
