@@ -465,8 +465,127 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         factor_rows(work[0], 0, n);
         maxdepth = -1;
     }
+    // Near the root a level has fewer nodes than threads and a node is one long separator S = [lo, hi).  Its rows are
+    // then swept in three phases: (A) every row against the columns of the descendants (j < lo; these columns hold
+    // only descendant rows at that time, so the rows of S are independent), (B) the Schur contributions of those
+    // columns to the S x S block (needs the L[S, j] of phase A, read-only), both in parallel over the rows, and (C) the
+    // up-looking sweep restricted to the columns of S, in order.
+    std::vector<int64_t> snap;
+    auto factor_separator = [&](int32_t lo, int32_t hi) {
+        const int32_t ns = hi - lo;
+        std::vector<double> Cd((size_t)ns * (size_t)ns, 0.0);  // row k - lo: entries of the columns lo..k (diagonal last)
+        std::vector<int64_t> rowD((size_t)ns, 0);
+        std::vector<std::vector<int32_t>> sreach((size_t)ns);
+        snap.assign(cnext.begin(), cnext.begin() + lo);        // end of the descendant part of the columns j < lo
+        run_parallel(ns, [&](int th, int32_t t) {               // ---- phase A
+            Work& w = work[(size_t)th];
+            double* x = w.x.data();
+            int32_t* flag = w.flag.data();
+            int32_t* stack = w.stack.data();
+            const int32_t k = lo + t;
+            int32_t top = n;
+            flag[k] = k;
+            for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+                int32_t i = Ci[p];
+                if (i > k) continue;
+                int32_t len = 0;
+                for (; flag[i] != k; i = parent[i]) {
+                    stack[len++] = i;
+                    flag[i] = k;
+                }
+                while (len > 0) stack[--top] = stack[--len];
+            }
+            double d = 0.0;
+            for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+                if (Ci[p] == k)
+                    d += Cx[p];
+                else
+                    x[Ci[p]] += Cx[p];
+            }
+            Cd[(size_t)t * ns + t] = d;  // A[k,k]; the products are subtracted in phase C order below
+            double dsub = 0.0;
+            int64_t rp = F.Lp[k];
+            for (int32_t q = top; q < n; ++q) {
+                const int32_t j = stack[q];
+                if (j >= lo) {
+                    sreach[(size_t)t].push_back(j);
+                    continue;
+                }
+                const double lkj = x[j] / Lcx[Lcp[j]];
+                x[j] = 0.0;
+                for (int64_t p = Lcp[j] + 1; p < snap[(size_t)j]; ++p) x[Lci[p]] -= Lcx[p] * lkj;
+                dsub += lkj * lkj;
+                F.Li[rp] = j;
+                F.Lx[rp] = lkj;
+                ++rp;
+            }
+            rowD[(size_t)t] = rp - F.Lp[k];
+            for (int32_t j : sreach[(size_t)t]) {
+                Cd[(size_t)t * ns + (j - lo)] = x[j];
+                x[j] = 0.0;
+            }
+            Cd[(size_t)t * ns + t] -= dsub;
+        });
+        for (int32_t t = 0; t < ns; ++t) {                      // L[S, j] into the columns, in row order
+            const int32_t k = lo + t;
+            for (int64_t rp = F.Lp[k]; rp < F.Lp[k] + rowD[(size_t)t]; ++rp) {
+                const int64_t at = cnext[F.Li[rp]]++;
+                Lci[at] = k;
+                Lcx[at] = F.Lx[rp];
+            }
+        }
+        run_parallel(ns, [&](int, int32_t t) {                  // ---- phase B
+            const int32_t k = lo + t;
+            double* c = &Cd[(size_t)t * ns];
+            for (int64_t rp = F.Lp[k]; rp < F.Lp[k] + rowD[(size_t)t]; ++rp) {
+                const int32_t j = F.Li[rp];
+                const double lkj = F.Lx[rp];
+                for (int64_t p = snap[(size_t)j]; p < cnext[j] && Lci[p] < k; ++p) c[Lci[p] - lo] -= Lcx[p] * lkj;
+            }
+        });
+        double* x = work[0].x.data();
+        for (int32_t t = 0; t < ns; ++t) {                      // ---- phase C
+            const int32_t k = lo + t;
+            for (int32_t j : sreach[(size_t)t]) x[j] = Cd[(size_t)t * ns + (j - lo)];
+            double d = Cd[(size_t)t * ns + t];
+            const double d_orig = std::fabs(d) + 1.0;
+            int64_t rp = F.Lp[k] + rowD[(size_t)t];
+            for (int32_t j : sreach[(size_t)t]) {
+                const double lkj = x[j] / Lcx[Lcp[j]];
+                x[j] = 0.0;
+                for (int64_t p = Lcp[j] + 1; p < cnext[j]; ++p) x[Lci[p]] -= Lcx[p] * lkj;
+                d -= lkj * lkj;
+                const int64_t at = cnext[j]++;
+                Lci[at] = k;
+                Lcx[at] = lkj;
+                F.Li[rp] = j;
+                F.Lx[rp] = lkj;
+                ++rp;
+            }
+            if (!(d > 1.0e-12 * (d_orig - 1.0)) || !std::isfinite(d)) {
+                int32_t expect = -1;
+                bad_pivot.compare_exchange_strong(expect, k);
+                d = 1.0;
+            }
+            const double lkk = std::sqrt(d);
+            const int64_t at = cnext[k]++;
+            Lci[at] = k;
+            Lcx[at] = lkk;
+            F.dinv[k] = 1.0 / lkk;
+        }
+    };
     for (int32_t dpt = maxdepth; dpt >= 0; --dpt) {
         const std::vector<int32_t>& lv = level[(size_t)dpt];
+        if (nthreads >= 4 && 2 * (int)lv.size() <= nthreads && getenv("ASGFEM_CHOL_NOSPLIT") == nullptr) {
+            for (int32_t t : lv) {
+                const Task& tk = tasks[(size_t)t];
+                if (tk.hi - tk.lo >= 96 && tk.hi - tk.lo <= 8192)
+                    factor_separator(tk.lo, tk.hi);
+                else
+                    factor_rows(work[0], tk.lo, tk.hi);
+            }
+            continue;
+        }
         run_parallel((int32_t)lv.size(), [&](int th, int32_t t) {
             const Task& tk = tasks[(size_t)lv[(size_t)t]];
             factor_rows(work[(size_t)th], tk.lo, tk.hi);
