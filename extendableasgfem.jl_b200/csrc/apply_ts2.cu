@@ -247,7 +247,7 @@ int apply_ts2_build(asgfem_ctx* ctx) {
             int64_t mu = 32ll * g + l;
             if (mu < N) jlen[(size_t)g] = std::max(jlen[(size_t)g], (int)(C.ptr[mu + 1] - C.ptr[mu]));
         }
-    auto even = [](int v) { return (v + 1) / 2 * 2; };
+    auto even = [](int v) { return v; };  // list lengths need no padding: the gather loop has tails of 2 and 1
     auto cost1 = [&](int g) -> int64_t {  // phase 1 (+ phase 2 for sparse groups, which stay with their owner)
         return sparse[(size_t)g] ? 16ll * Q + 9ll * even(jlen[(size_t)g]) + 20 : 16ll * nd4(g) + 20;
     };
@@ -325,7 +325,7 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     int64_t confl_before = 0, confl_after = 0;
     for (int g = 0; g < G; ++g) {
         const bool exp = exported[(size_t)g] >= 0;
-        const int jm = even(jlen[(size_t)g] + (exp ? 1 : 0));  // the gather loop is unrolled by 4 with a tail of 2
+        const int jm = jlen[(size_t)g] + (exp ? 1 : 0);  // the gather loop is unrolled by 4 with tails of 2 and 1
         jmax[(size_t)g] = jm;
         wbase[(size_t)g] = (int32_t)words.size();
         words.resize(words.size() + (size_t)jm * 32, 0u);
@@ -831,6 +831,11 @@ __global__ void __launch_bounds__(S == 8 ? 256 : 512, 1) k_apply_ts2(Ts2Args a) 
                 const double g1 = t2_lds_f64(gt32 + (w1 & 0x1f8u)), t1 = t2_lds_f64(T32 + (w1 >> 9));
                 r0 = fma(g0, t0, r0);
                 r1 = fma(g1, t1, r1);
+                wp += 256u;
+            }
+            if (jm & 1) {
+                const unsigned w0 = t2_lds_u32(wp);
+                r0 = fma(t2_lds_f64(gt32 + (w0 & 0x1f8u)), t2_lds_f64(T32 + (w0 >> 9)), r0);
             }
             return r0 + r1;
         };
