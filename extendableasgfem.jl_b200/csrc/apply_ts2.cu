@@ -248,10 +248,13 @@ int apply_ts2_build(asgfem_ctx* ctx) {
             if (mu < N) jlen[(size_t)g] = std::max(jlen[(size_t)g], (int)(C.ptr[mu + 1] - C.ptr[mu]));
         }
     auto even = [](int v) { return v; };  // list lengths need no padding: the gather loop has tails of 2 and 1
+    // relative cost of a unit and of a gather slot for the load balance of the warps
+    int64_t CU = 16, CG = 9;  // measured best of (16,9), (23,17), (20,20), (30,12): 51.2 / 51.6 / 53.3 / 51.5 ms
+    if (const char* e = getenv("ASGFEM_TS2_COST")) sscanf(e, "%lld,%lld", (long long*)&CU, (long long*)&CG);
     auto cost1 = [&](int g) -> int64_t {  // phase 1 (+ phase 2 for sparse groups, which stay with their owner)
-        return sparse[(size_t)g] ? 16ll * Q + 9ll * even(jlen[(size_t)g]) + 20 : 16ll * nd4(g) + 20;
+        return sparse[(size_t)g] ? CU * Q + CG * even(jlen[(size_t)g]) + 20 : CU * nd4(g) + 20;
     };
-    auto cost2 = [&](int g) -> int64_t { return 9ll * even(jlen[(size_t)g] + 1) + 10; };
+    auto cost2 = [&](int g) -> int64_t { return CG * even(jlen[(size_t)g] + 1) + 10; };
     std::vector<int> order((size_t)G);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost1(a) > cost1(b); });
@@ -280,8 +283,8 @@ int apply_ts2_build(asgfem_ctx* ctx) {
             for (int w = 0; w < W; ++w)
                 if (extra[(size_t)w] < 0 && (best < 0 || load[(size_t)w] < load[(size_t)best])) best = w;
             if (!allow || best < 0 || best == owner[(size_t)g] ||
-                load[(size_t)best] + cost2(g) >= load[(size_t)owner[(size_t)g]] + cost2(g) - 16) {
-                load[(size_t)owner[(size_t)g]] += cost2(g) - 9;  // no export: the list is one entry shorter
+                load[(size_t)best] + cost2(g) >= load[(size_t)owner[(size_t)g]] + cost2(g) - CU) {
+                load[(size_t)owner[(size_t)g]] += cost2(g) - CG;  // no export: the list is one entry shorter
                 continue;
             }
             extra[(size_t)best] = g;
