@@ -63,6 +63,7 @@ PROTOTYPES = {
     "asgfem_precond_apply_host": (c_i32, [vp, vp, vp]),
     "asgfem_pcg": (c_i32, [vp, vp, c_i32, c_f64, c_f64, c_i64, P(Stats)]),
     "asgfem_solve_primal_host": (c_i32, [vp, vp, vp, c_f64, c_f64, c_i64, P(Stats)]),
+    "asgfem_evaluate_samples": (c_i32, [vp, c_i32, c_i64, c_i64, c_i32, vp, vp]),
     "asgfem_set_precond_matrix_csc": (c_i32, [vp, vp, vp, vp]),
     "asgfem_bicgstab": (c_i32, [vp, c_i32, c_i32, c_f64, c_f64, c_i64, P(Stats)]),
     "asgfem_solve_logprimal_host": (c_i32, [vp, vp, vp, c_f64, c_f64, c_i64, P(Stats)]),

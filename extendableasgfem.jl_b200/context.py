@@ -229,6 +229,16 @@ class Context:
         self._ck(self.lib.asgfem_solve_primal_host(self.h, _ptr(sol), _ptr(b0), atol, rtol, itmax, C.byref(st)))
         return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
 
+    # ---- evaluation at samples ----------------------------------------------------------------------
+    def evaluate_samples(self, slot_u, vals):
+        """vals[s, m, :] = TB.vals[m] after set_sample!(TB, xi_s); returns the (nsamples, n) array of the evaluated
+        spatial coefficient vectors (row s = FEV entries for sample s)."""
+        vals = _f64(vals)
+        S, M, nvals = vals.shape
+        out = np.zeros((S, self.n))
+        self._ck(self.lib.asgfem_evaluate_samples(self.h, slot_u, S, M, nvals, _ptr(vals), _ptr(out)))
+        return out
+
     # ---- log-transformed primal problem ------------------------------------------------------------
     def set_precond_matrix_csc(self, colptr=None, rowval=None, nzval=None):
         """SPD matrix for the mean preconditioner (default: matrix 0); None returns to the default."""

@@ -736,6 +736,49 @@ extern "C" int asgfem_solve_logprimal_host(asgfem_ctx* ctx, double* sol, const d
     return vec_to_host_layout(ctx, ctx->slots[0], sol);
 }
 
+// ---- evaluation at samples ------------------------------------------------------------------------
+extern "C" int asgfem_evaluate_samples(asgfem_ctx* ctx, int32_t slot_u, int64_t nsamples, int64_t M_in, int32_t nvals,
+                                       const double* vals, double* out) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, slot_u)) return ASGFEM_EINVAL;
+    ASG_CHECK(ctx, ctx->N > 0 && ctx->n > 0, ASGFEM_ESTATE, "evaluate_samples: multi-indices / pattern not set");
+    ASG_CHECK(ctx, nsamples >= 1 && nvals >= 1 && vals && out, ASGFEM_EINVAL, "evaluate_samples: bad arguments");
+    const int64_t N = ctx->N, M = ctx->mis.M, n = ctx->n;
+    ASG_CHECK(ctx, M_in == M, ASGFEM_EINVAL, "evaluate_samples: M differs from the length of the multi-indices");
+    ASG_CHECK(ctx, ctx->mis.maxdeg() < nvals, ASGFEM_EINVAL, "evaluate_samples: nvals <= maximal polynomial degree of the set");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    // H_k(xi_s) = prod_m vals[s][m][mu_k[m]]   (evaluate(TB, k), tensorizedbasis.jl:244-252: product over m ascending)
+    const int64_t Spad = (nsamples + 7) / 8 * 8;
+    std::vector<double> R((size_t)N * (size_t)Spad, 0.0);
+    for (int64_t s = 0; s < nsamples; ++s) {
+        const double* v = vals + (size_t)s * (size_t)M * (size_t)nvals;
+        for (int64_t k = 0; k < N; ++k) {
+            double prod = 1.0;
+            for (int64_t m = 0; m < M; ++m) prod *= v[m * nvals + ctx->mis.mi[k * M + m]];
+            R[(size_t)k * Spad + s] = prod;
+        }
+    }
+    double *dR = nullptr, *dout = nullptr;
+    cudaError_t e1 = cudaMalloc((void**)&dR, sizeof(double) * R.size());
+    cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void**)&dout, sizeof(double) * (size_t)n * (size_t)nsamples) : e1;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        if (dR) cudaFree(dR);
+        (void)cudaGetLastError();
+        return fail(ctx, ASGFEM_ENOMEM, "evaluate_samples: out of device memory for the sample block");
+    }
+    int rc = 0;
+    cudaError_t e = cudaMemcpyAsync(dR, R.data(), sizeof(double) * R.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = vec_eval_samples(ctx, ctx->slots[slot_u], dR, nsamples, Spad, dout);
+    if (e == cudaSuccess && !rc)
+        e = cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)n * (size_t)nsamples, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dR);
+    cudaFree(dout);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, ASGFEM_ECUDA, std::string("evaluate_samples: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 // ---- estimator ----------------------------------------------------------------------------------
 extern "C" int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,
                                               const int64_t* mi_ext, int32_t nq, const double* xref, const double* w,

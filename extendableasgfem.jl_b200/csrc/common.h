@@ -202,6 +202,8 @@ int vec_xpay(asgfem_ctx* ctx, const double* x, double beta, double* y);  // y = 
 int vec_mask_rows(asgfem_ctx* ctx, double* x);                            // zero boundary rows
 int vec_pack_rows(asgfem_ctx* ctx, const double* v, int64_t nrows, const int64_t* d_rows, double* buf);
 int vec_unpack_rows(asgfem_ctx* ctx, double* v, int64_t nrows, const int64_t* d_rows, const double* buf);
+// out[s*n + i] = sum_k u[i*ld + k] * R[k*Spad + s]   (R: N x Spad on the device, zero padded to a multiple of 8 samples)
+int vec_eval_samples(asgfem_ctx* ctx, const double* u, const double* dR, int64_t S, int64_t Spad, double* dout);
 // sptrsv.cu
 int precond_setup(asgfem_ctx* ctx);
 void precond_free(asgfem_ctx* ctx);

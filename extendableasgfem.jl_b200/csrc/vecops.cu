@@ -355,4 +355,42 @@ int vec_unpack_rows(asgfem_ctx* ctx, double* v, int64_t nrows, const int64_t* d_
     return 0;
 }
 
+namespace {
+// warp = (dof row, tile of 8 samples): lanes stride over the modes, 8 accumulators, butterfly reduction
+__global__ void k_eval_samples(const double* __restrict__ u, int64_t n, int64_t ld, int N, const double* __restrict__ R,
+                               int64_t Spad, int64_t S, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t tile = blockIdx.y;
+    for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < n; row += (int64_t)gridDim.x * nw) {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const double* ur = u + row * ld;
+        for (int k = lane; k < N; k += 32) {
+            const double uk = ur[k];
+            const double2* r = reinterpret_cast<const double2*>(R + (int64_t)k * Spad + tile * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 v = r[j];
+                acc[2 * j] = fma(uk, v.x, acc[2 * j]);
+                acc[2 * j + 1] = fma(uk, v.y, acc[2 * j + 1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (lane == j && tile * 8 + j < S) out[(tile * 8 + j) * n + row] = acc[j];
+    }
+}
+}  // namespace
+
+int vec_eval_samples(asgfem_ctx* ctx, const double* u, const double* dR, int64_t S, int64_t Spad, double* dout) {
+    if (S <= 0 || ctx->n <= 0) return 0;
+    dim3 grid((unsigned)std::min<int64_t>((ctx->n + 7) / 8, 148 * 8), (unsigned)(Spad / 8));
+    k_eval_samples<<<grid, 256, 0, ctx->stream>>>(u, ctx->n, ctx->ld, (int)ctx->N, dR, Spad, S, dout);
+    ASG_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
 }  // namespace asgfem

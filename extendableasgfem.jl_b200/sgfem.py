@@ -7,6 +7,7 @@
 * solve                  solve!(PoissonProblemPrimal, sol, C; rhs, ...)   src/modelproblems/poisson_primal.jl:38-81
 * solve_logpoisson_primal  solve_logpoisson_primal!(sol, A, N0, Nm, b0, G, nmodes, bfac; atol, rtol)
                          src/modelproblems/solvers_logpoisson_primal.jl:130-172 (matrices and load vectors from the caller)
+* set_samples            set_sample!(SGFEV, S) for a batch of samples   src/sgfevector.jl:43-69
 * mul / ldiv             LinearAlgebra.mul! (:86-124) / ldiv! (:46-78) on host vectors
 * estimate               estimate(PoissonProblemPrimal, sol, C; rhs, bonus_quadorder, tail_extension)
                          src/estimate.jl:260-418
@@ -114,6 +115,16 @@ def solve_logpoisson_primal(sol: SGFEVector, A, N0, Nm, b0, G=None, nmodes=None,
     b = np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1) for v in b0])
     stats = ctx.solve_logprimal_host(sol.entries, b, atol, rtol, itmax)
     return (bdofs, stats) if return_stats else bdofs
+
+
+def set_samples(sol: SGFEVector, vals):
+    """Batched set_sample!(SGFEV, S) (src/sgfevector.jl:43-69): vals[s, m, :] = TB.vals[m] after set_sample!(TB, xi_s)
+    (tensorizedbasis.jl:226-236, the caller's polynomial tables).  Returns the (nsamples, n) array of evaluated spatial
+    coefficient vectors (row s = SGFEV.FEV entries for sample s); the sum over the modes runs on the device."""
+    ctx = sol.TB.ctx
+    ctx.vec_alloc(1)
+    ctx.vec_upload(0, sol.entries)
+    return ctx.evaluate_samples(0, vals)
 
 
 def setup_device_problem(sol: SGFEVector, C, bonus_quadorder_a=2):

@@ -180,6 +180,16 @@ int asgfem_bicgstab(asgfem_ctx* ctx, int32_t slot_b, int32_t slot_x, double atol
 int asgfem_solve_logprimal_host(asgfem_ctx* ctx, double* sol, const double* b, double atol, double rtol, int64_t itmax,
                                 asgfem_stats* stats);
 
+/* ---- evaluation at samples (the set_sample! half) ------------------------------------
+ * set_sample!(SGFEV::SGFEVector, S) (src/sgfevector.jl:43-69) for a batch of samples:
+ *     out[:, s] = sum_k H_k(xi_s) u_k,   H_k(xi) = prod_m vals[s][m][mu_k[m]]   (evaluate(TB, k), tensorizedbasis.jl:244-252)
+ * vals holds TB.vals after set_sample!(TB, xi_s; normalize = true) (tensorizedbasis.jl:226-236) for every sample: nsamples
+ * blocks of M (= length of the multi-indices) rows with nvals = maxorder + 1 entries each (row-major; the rows beyond the length of the sample are
+ * [1, 0, 0, ...] as the reference sets them).  The univariate polynomial values are the caller's data, like the
+ * quadrature tables.  slot_u: coefficient vector on the device; out: host, n x nsamples column-major. */
+int asgfem_evaluate_samples(asgfem_ctx* ctx, int32_t slot_u, int64_t nsamples, int64_t M, int32_t nvals,
+                            const double* vals, double* out);
+
 /* whole seam on host vectors: sol (n*N, in: warm start, out: solution), b0 (n) */
 int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const double* b0, double atol, double rtol,
                              int64_t itmax, asgfem_stats* stats);

@@ -147,6 +147,33 @@ function solve_logpoisson_primal!(sol::SGFEVector, A, N0, Nm, b0, G, nmodes, bfa
     return bdofs
 end
 
+# ---- seam 1c: evaluation of the SGFE solution at a batch of samples (set_sample! of sgfevector.jl:43-69) ---------
+"""
+`evaluate_samples(ctx, sol, samples)`: column s of the result = entries of `sol.FEV` after `set_sample!(sol, samples[:, s])`.
+The univariate basis values come from the package's own `set_sample!(TB, x; normalize = true)`; the sum over the modes
+runs on the GPU (the coefficient vector is uploaded once for all samples).
+"""
+function evaluate_samples(ctx::Context, sol::SGFEVector, samples::AbstractMatrix)
+    TB = sol.TB
+    M = maxlength_multiindices(TB)
+    nvals = length(TB.vals[1])
+    S = size(samples, 2)
+    vals = zeros(Float64, nvals, M, S)                # nvals fastest = the row-major [s][m][nvals] the library expects
+    for s in 1:S
+        v = set_sample!(TB, view(samples, :, s); normalize = true)
+        for m in 1:M
+            vals[:, m, s] .= v[m]
+        end
+    end
+    n = div(length(sol.entries), num_multiindices(sol))
+    out = zeros(Float64, n, S)
+    check(ctx, ccall((:asgfem_vec_alloc, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.h, 1))
+    check(ctx, ccall((:asgfem_vec_upload, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), ctx.h, 0, sol.entries))
+    check(ctx, ccall((:asgfem_evaluate_samples, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, Cint, Ptr{Float64}, Ptr{Float64}), ctx.h, 0, S, M, nvals, vals, out))
+    return out
+end
+
 # ---- seams 2/3: single applications on host vectors (used for parity checks, not for production) ----------
 struct GPUSystemPrimal
     ctx::Context

@@ -528,3 +528,40 @@ def test_apply_auto_variant_beyond_register_capacity():
         ctx.set_apply_variant(7)
         ctx.apply(0, 2)
     ctx.close()
+
+
+@pytest.mark.parametrize("family", [opoly.LEGENDRE, opoly.HERMITE])
+def test_evaluate_samples_matches_oracle(family):
+    """Row f4, set_sample! half (sgfevector.jl:43-69): u(x, xi_s) = sum_k H_k(xi_s) u_k for a batch of samples, with the
+    univariate values TB.vals of set_sample!(TB, xi) (tensorizedbasis.jl:226-236) as data, incl. samples shorter than M."""
+    modes = A.graded_lex_multiindices(6, 150)
+    g = A.structured_unitsquare(21)
+    fes = A.FESpace(g, 1)
+    TB = A.TensorizedBasis(family, modes)
+    sol = A.SGFEVector(fes, TB)
+    rng = np.random.default_rng(12)
+    sol.entries[:] = rng.standard_normal(sol.entries.shape)
+    n, N, M = fes.ndofs, TB.nmodes, 6
+    maxdeg = max(max(m) for m in modes)
+    oTB = otb.TensorizedBasis(family, M, maxdeg, maxdeg + 2, multi_indices=[list(m) for m in TB.multi_indices])
+    S = 13
+    samples = [rng.uniform(-1, 1, size=(M if s % 3 else 4)) for s in range(S)]  # every third sample is shorter than M
+    vals = np.zeros((S, M, oTB.ONB.maxorder + 1))
+    ref = np.zeros((S, n))
+    for s, xi in enumerate(samples):
+        for d in range(M):
+            if d < len(xi):
+                vals[s, d] = oTB.ONB.evaluate(xi[d], normalize=True)
+            else:
+                vals[s, d, 0] = 1.0
+        H = oTB.evaluate_all(xi, normalize=True)
+        ref[s] = H @ sol.entries.reshape(N, n)
+    ctx = TB.ctx
+    # minimal device problem: the evaluation needs the vector layout only (pattern of any matrix on the space)
+    A.setup_device_problem(sol, A.StochasticCoefficientCosinus(tau=0.9, decay=2, mean=1, maxm=M))
+    ctx.vec_alloc(1)
+    ctx.vec_upload(0, sol.entries)
+    got = ctx.evaluate_samples(0, vals)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    ctx.close()
