@@ -1,11 +1,12 @@
 """PCG solve timing on synthetic problems (device-assembled K_m, f = 1): prints one JSON line per size."""
 import json
+import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import asgfem_b200 as A
 
 

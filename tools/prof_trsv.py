@@ -1,5 +1,6 @@
+import os
 import sys
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
 import asgfem_b200 as A
 g = A.structured_unitsquare(513)
