@@ -42,13 +42,20 @@ def partition_rows(n, nparts, coords=None):
 
 
 class LocalProblem:
-    """Local numbering of rank `rank`: owned dofs first (ascending global id), then halo dofs grouped by owner."""
+    """Local numbering of rank `rank`: owned dofs first (rows without halo columns, then rows with halo columns, each
+    ascending in the global id), then halo dofs grouped by owner."""
 
     def __init__(self, rank, owner, indptr, indices):
         self.rank = rank
         n = len(owner)
-        self.owned = np.where(owner == rank)[0]
+        owned = np.where(owner == rank)[0]
+        # interior rows (all columns owned) first, rows that reference a halo column last: the operator on the first
+        # n_interior rows does not need the halo exchange and runs while it is in flight
+        touches_halo = np.array([np.any(owner[indices[indptr[i]:indptr[i + 1]]] != rank) for i in owned], dtype=bool) \
+            if len(owned) else np.zeros(0, dtype=bool)
+        self.owned = np.concatenate([owned[~touches_halo], owned[touches_halo]])
         self.n_owned = len(self.owned)
+        self.n_interior = int(np.count_nonzero(~touches_halo))
         cols = np.unique(np.concatenate([indices[indptr[i]:indptr[i + 1]] for i in self.owned])
                          if self.n_owned else np.zeros(0, dtype=np.int64))
         halo = cols[owner[cols] != rank]
@@ -100,21 +107,33 @@ class HaloExchange:
     def __init__(self, local: LocalProblem, backend, dist):
         self.local, self.backend, self.dist = local, backend, dist
 
-    def __call__(self, slot):
+    def start(self, slot):
+        """Packs and posts the sends / receives; returns the handle for `finish` (None: nothing to exchange)."""
         d = self.dist
         if d is None or d.get_world_size() == 1:
-            return
-        ops, recv_bufs = [], {}
+            return None
+        ops, recv_bufs, send_bufs = [], {}, []
         for q, rows in self.local.send.items():
-            ops.append(d.P2POp(d.isend, self.backend.pack_rows(slot, rows), q))
+            send_bufs.append(self.backend.pack_rows(slot, rows))
+            ops.append(d.P2POp(d.isend, send_bufs[-1], q))
         for q, rows in self.local.recv.items():
             recv_bufs[q] = self.backend.empty_rows(len(rows))
             ops.append(d.P2POp(d.irecv, recv_bufs[q], q))
-        for w in d.batch_isend_irecv(ops):
+        works = d.batch_isend_irecv(ops) if ops else []
+        return works, recv_bufs, send_bufs
+
+    def finish(self, slot, handle):
+        if handle is None:
+            return
+        works, recv_bufs, _send_bufs = handle
+        for w in works:
             w.wait()
         self.backend.sync()
         for q, rows in self.local.recv.items():
             self.backend.unpack_rows(slot, rows, recv_bufs[q])
+
+    def __call__(self, slot):
+        self.finish(slot, self.start(slot))
 
 
 class DistributedOperator:
@@ -123,8 +142,15 @@ class DistributedOperator:
         self.exchange = HaloExchange(local, backend, dist)
 
     def apply(self, sx, sy):
-        self.exchange(sx)
-        self.backend.apply(sx, sy)
+        """Y = A X on the owned rows: the rows without halo columns are applied while the halo rows of X travel."""
+        if not hasattr(self.backend, "apply_rows"):
+            self.exchange(sx)
+            self.backend.apply(sx, sy)
+            return
+        handle = self.exchange.start(sx)
+        self.backend.apply_rows(sx, sy, 0, self.local.n_interior)
+        self.exchange.finish(sx, handle)
+        self.backend.apply_rows(sx, sy, self.local.n_interior, self.local.n_owned)
 
     def dot(self, a, b):
         import torch
@@ -189,6 +215,10 @@ class ContextBackend:
 
     def apply(self, sx, sy):
         self.ctx.apply(sx, sy)
+
+    def apply_rows(self, sx, sy, row0, row1):
+        if row1 > row0:
+            self.ctx.apply_rows(sx, sy, row0, row1)
 
     def dot_owned(self, a, b):
         return self.ctx.vec_dot_owned(a, b)

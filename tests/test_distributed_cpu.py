@@ -68,6 +68,13 @@ class NumpyBackend:
         Y[self.L.n_owned:] = self.vec(sy)[self.L.n_owned:]  # halo rows are not written
         self.v[sy] = Y
 
+    def apply_rows(self, sx, sy, row0, row1):
+        """Rows [row0, row1) only, the others keep their content (asgfem_apply_rows)."""
+        keep = self.vec(sy).copy()
+        self.apply(sx, sy)
+        keep[row0:row1] = self.v[sy][row0:row1]
+        self.v[sy] = keep
+
     def dot_owned(self, a, b):
         n = self.L.n_owned
         return float(np.sum(self.vec(a)[:n] * self.vec(b)[:n]))
@@ -105,6 +112,7 @@ def _worker(rank, world, port, q):
         ref = S.mul(xg).reshape(P.N, P.n).T
         X = xg.reshape(P.N, P.n).T
         be.vec(0)[:L.n_owned] = X[L.owned]          # halo rows intentionally left at zero: exchange must fill them
+        assert 0 < L.n_interior < L.n_owned  # some rows run behind the exchange, some need the halo
         op.apply(0, 1)
         err_apply = np.abs(be.vec(1)[:L.n_owned] - ref[L.owned]).max() / np.abs(ref).max()
         nrm = op.dot(0, 0)
