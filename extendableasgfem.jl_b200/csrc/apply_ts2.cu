@@ -47,6 +47,7 @@ struct Ts2Plan {
     int D = 0;
     int nwords = 0, ndl = 0;
     int units = 0;  // evaluated units per row (statistics)
+    int grid_sms = 148;  // CTAs of the persistent grid (ASGFEM_TS2_GRID: fewer when collectives need SMs of their own)
     size_t smem_bytes = 0;
     int32_t* d_slotinfo = nullptr;  // [warps*(slots+1)*8] group (-1 unused), kind (1 dense, 2 sparse, 3 dense with exported
                                     // phase 2), #dense units, list base, words base, jmax, byte offset of the mean-term block
@@ -468,6 +469,7 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     rc |= dev_upload(ctx, &P->d_gtab, gtab);
     if (rc) return rc;
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (const char* e = getenv("ASGFEM_TS2_GRID")) P->grid_sms = std::max(1, std::min(148, atoi(e)));
     P->usable = true;
     if (getenv("ASGFEM_TS2_VERBOSE")) {
         int64_t lmin = 1 << 30, lmax = 0;
@@ -908,7 +910,7 @@ int apply_ts2_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
         int per_sm = 1;                                                                                               \
         ASG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));                   \
         per_sm = std::max(1, std::min(per_sm, 4));                                                                    \
-        int grid = (int)std::min<int64_t>(r1 - r0, 148ll * per_sm);                                                   \
+        int grid = (int)std::min<int64_t>(r1 - r0, (int64_t)P->grid_sms * per_sm);                                    \
         kern<<<grid, threads, smem, ctx->stream>>>(a);                                                                \
     } while (0)
 #define LAUNCH_TS2_Q(NSV, SV, MV)         \
