@@ -58,11 +58,12 @@ extern "C" int asgfem_destroy(asgfem_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     apply_free_plan(ctx);
+    apply_mma_free(ctx);
     precond_free(ctx);
     free_vec_storage(ctx);
     void* ptrs[] = {ctx->d_rowptr, ctx->d_col,  ctx->d_vals,      ctx->d_bmask,    ctx->d_cptr,  ctx->d_cm,
                     ctx->d_cnu,    ctx->d_cg,   ctx->d_stage,     ctx->d_partial,  ctx->d_coords, ctx->d_cellnodes,
-                    ctx->d_celldofs, ctx->d_decay, ctx->d_b1,     ctx->d_b2};
+                    ctx->d_celldofs, ctx->d_decay, ctx->d_b1,     ctx->d_b2,       ctx->d_pos,   ctx->d_inv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     cudaEventDestroy(ctx->ev0);
@@ -80,7 +81,7 @@ extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t 
     ASG_CHECK(ctx, N < 65536, ASGFEM_EINVAL, "set_multiindices: at most 65535 modes are supported");
     for (int64_t k = 0; k < N * M; ++k) ASG_CHECK(ctx, mi[k] >= 0, ASGFEM_EINVAL, "negative multi-index entry");
     if (set_device(ctx)) return ASGFEM_ECUDA;
-    if (!ctx->slots.empty() && N != ctx->N) free_vec_storage(ctx);  // vectors are sized by N
+    free_vec_storage(ctx);  // vectors are sized by the column count, and the column order changes with the set
     ctx->family = family;
     ctx->mis.N = N;
     ctx->mis.M = M;
@@ -89,15 +90,40 @@ extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t 
     build_coupling(ctx->mis, family, ctx->coup);
     coupling_weights(family, ctx->mis.maxdeg() + 1, ctx->gp, ctx->gm);
     ctx->N = N;
-    ctx->ld = (N + 15) / 16 * 16;
-    int rc = 0;
-    rc |= dev_upload(ctx, &ctx->d_cptr, ctx->coup.ptr);
-    rc |= dev_upload(ctx, &ctx->d_cm, ctx->coup.m);
-    rc |= dev_upload(ctx, &ctx->d_cnu, ctx->coup.nu);
-    rc |= dev_upload(ctx, &ctx->d_cg, ctx->coup.g);
+    apply_free_plan(ctx);
+    // device column order: chosen by the operator's mode-side plan; identity if the plan declines the set
+    int rc = apply_mma_layout(ctx);
+    if (rc) return rc;
+    if (!apply_mma_layout_ok(ctx)) {
+        ctx->ld = (N + 31) / 32 * 32;
+        ctx->h_pos.resize((size_t)N);
+        ctx->h_inv.assign((size_t)ctx->ld, -1);
+        for (int64_t k = 0; k < N; ++k) ctx->h_pos[(size_t)k] = ctx->h_inv[(size_t)k] = (int32_t)k;
+    } else {
+        ctx->ld = (int64_t)ctx->h_inv.size();
+    }
+    // coupling lists in column space (reference order of the entries of a mode kept)
+    const Coupling& C = ctx->coup;
+    std::vector<int32_t> cptr((size_t)ctx->ld + 1, 0), cm, cnu;
+    std::vector<double> cg;
+    for (int64_t c = 0; c < ctx->ld; ++c) {
+        const int32_t mode = ctx->h_inv[(size_t)c];
+        if (mode >= 0)
+            for (int32_t e = C.ptr[mode]; e < C.ptr[mode + 1]; ++e) {
+                cm.push_back(C.m[e]);
+                cnu.push_back(ctx->h_pos[(size_t)C.nu[e]]);
+                cg.push_back(C.g[e]);
+            }
+        cptr[(size_t)c + 1] = (int32_t)cm.size();
+    }
+    rc |= dev_upload(ctx, &ctx->d_cptr, cptr);
+    rc |= dev_upload(ctx, &ctx->d_cm, cm);
+    rc |= dev_upload(ctx, &ctx->d_cnu, cnu);
+    rc |= dev_upload(ctx, &ctx->d_cg, cg);
+    rc |= dev_upload(ctx, &ctx->d_pos, ctx->h_pos);
+    rc |= dev_upload(ctx, &ctx->d_inv, ctx->h_inv);
     if (rc) return rc;
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    apply_free_plan(ctx);
     return 0;
 }
 
@@ -537,7 +563,7 @@ static int ensure_ready_for_apply(asgfem_ctx* ctx) {
     for (int32_t m : ctx->coup.m)
         ASG_CHECK(ctx, m <= ctx->M, ASGFEM_EINVAL,
                   "apply: multi-indices couple in a direction m > number of stiffness matrices (maxlength_multiindices > length(Am))");
-    if (!ctx->plan) {
+    if (!ctx->apply_ready) {
         int rc = apply_build_plan(ctx);
         if (rc) return rc;
     }
@@ -546,7 +572,7 @@ static int ensure_ready_for_apply(asgfem_ctx* ctx) {
 
 extern "C" int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant) {
     CTX_OR_FAIL(ctx);
-    ASG_CHECK(ctx, variant >= 0 && variant <= 7, ASGFEM_EINVAL, "apply variant must be 0..7");
+    ASG_CHECK(ctx, variant == 0 || variant == 1 || variant == 8, ASGFEM_EINVAL, "apply variant must be 0, 1 or 8");
     ctx->apply_variant = variant;
     return 0;
 }
@@ -614,7 +640,7 @@ extern "C" int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax) {
     if (rc) return rc;
     if ((rc = ensure_work_slots(ctx, 2))) return rc;
     // upload, operator and download overlap block by block unless the kernel cannot work on row ranges
-    if (ctx->apply_variant != 2 && ctx->n_owned < 0 && x != Ax)
+    if (ctx->n_owned < 0 && x != Ax)
         return apply_host_pipelined(ctx, x, Ax, ctx->slots[0], ctx->slots[1]);
     if ((rc = vec_to_device_layout(ctx, x, ctx->slots[0]))) return rc;
     if ((rc = apply_launch(ctx, ctx->slots[0], ctx->slots[1]))) return rc;
@@ -749,13 +775,13 @@ extern "C" int asgfem_evaluate_samples(asgfem_ctx* ctx, int32_t slot_u, int64_t 
     if (set_device(ctx)) return ASGFEM_ECUDA;
     // H_k(xi_s) = prod_m vals[s][m][mu_k[m]]   (evaluate(TB, k), tensorizedbasis.jl:244-252: product over m ascending)
     const int64_t Spad = (nsamples + 7) / 8 * 8;
-    std::vector<double> R((size_t)N * (size_t)Spad, 0.0);
+    std::vector<double> R((size_t)ctx->ld * (size_t)Spad, 0.0);  // row = device column of the mode
     for (int64_t s = 0; s < nsamples; ++s) {
         const double* v = vals + (size_t)s * (size_t)M * (size_t)nvals;
         for (int64_t k = 0; k < N; ++k) {
             double prod = 1.0;
             for (int64_t m = 0; m < M; ++m) prod *= v[m * nvals + ctx->mis.mi[k * M + m]];
-            R[(size_t)k * Spad + s] = prod;
+            R[(size_t)ctx->h_pos[(size_t)k] * Spad + s] = prod;
         }
     }
     double *dR = nullptr, *dout = nullptr;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <array>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -56,7 +57,6 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
                      std::string& err);
 
 // ---- device-side plans --------------------------------------------------------------------------
-struct ApplyPlan;    // apply.cu
 struct PrecondPlan;  // sptrsv.cu
 struct EstimatePlan;
 
@@ -94,7 +94,12 @@ struct asgfem_ctx {
     int32_t* d_cm = nullptr;
     int32_t* d_cnu = nullptr;
     double* d_cg = nullptr;
-    int64_t N = 0, ld = 0;  // device vectors are row-major n x ld, ld = N rounded up to a multiple of 16
+    int64_t N = 0, ld = 0;  // device vectors are row-major n x ld, ld = number of device columns (multiple of 32)
+    // private column order of the device vectors, chosen for the operator (apply_mma.cu): mode mu lives in column
+    // h_pos[mu]; h_inv[c] = mode of column c or -1 (padding column, kept at zero)
+    std::vector<int32_t> h_pos, h_inv;
+    int32_t* d_pos = nullptr;
+    int32_t* d_inv = nullptr;
 
     // vectors
     std::vector<double*> slots;
@@ -125,12 +130,9 @@ struct asgfem_ctx {
     int apply_variant = 0;
     double last_apply_ms = 0;
     double last_estimate_ms = 0;
-    asgfem::ApplyPlan* plan = nullptr;
+    bool apply_ready = false;  // kernel tables of the operator built for the current pattern / multi-index set
     asgfem::PrecondPlan* precond = nullptr;
-    void* rowplan = nullptr;  // asgfem::RowPlan (apply_rows.cu)
-    void* dirplan = nullptr;  // asgfem::DirPlan (apply_dir.cu)
-    void* tsplan = nullptr;   // asgfem::TsPlan (apply_ts.cu)
-    void* ts2plan = nullptr;  // asgfem::Ts2Plan (apply_ts2.cu)
+    void* mmaplan = nullptr;  // asgfem::MmaPlan (apply_mma.cu)
 };
 
 namespace asgfem {
@@ -169,28 +171,15 @@ int dev_upload(asgfem_ctx* ctx, T** dptr, const std::vector<T>& h) {
 // apply.cu
 int apply_build_plan(asgfem_ctx* ctx);
 void apply_free_plan(asgfem_ctx* ctx);
-// rows [r0, r1) of Y (r1 < 0: all rows); row ranges are not available for the tiled variant 2
+// rows [r0, r1) of Y (r1 < 0: all rows)
 int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0 = 0, int64_t r1 = -1);
-// apply_rows.cu
-int apply_rows_build(asgfem_ctx* ctx);
-void apply_rows_free(asgfem_ctx* ctx);
-int apply_rows_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
-bool apply_rows_preferred(asgfem_ctx* ctx);
-// apply_dir.cu
-int apply_dir_build(asgfem_ctx* ctx, bool owned);
-void apply_dir_free(asgfem_ctx* ctx);
-int apply_dir_launch(asgfem_ctx* ctx, const double* x, double* y, bool owned, int64_t r0, int64_t r1);
-bool apply_dir_preferred(asgfem_ctx* ctx);
-// apply_ts.cu
-int apply_ts_build(asgfem_ctx* ctx);
-void apply_ts_free(asgfem_ctx* ctx);
-int apply_ts_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
-bool apply_ts_preferred(asgfem_ctx* ctx);
-// apply_ts2.cu
-int apply_ts2_build(asgfem_ctx* ctx);
-void apply_ts2_free(asgfem_ctx* ctx);
-int apply_ts2_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
-bool apply_ts2_preferred(asgfem_ctx* ctx);
+// apply_mma.cu
+int apply_mma_layout(asgfem_ctx* ctx);   // mode-side plan + device column order (set_multiindices)
+bool apply_mma_layout_ok(asgfem_ctx* ctx);
+int apply_mma_build(asgfem_ctx* ctx);    // kernel tables (first apply after the pattern is known)
+bool apply_mma_usable(asgfem_ctx* ctx);
+void apply_mma_free(asgfem_ctx* ctx);
+int apply_mma_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
 int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* dX, double* dY);

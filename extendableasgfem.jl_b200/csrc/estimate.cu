@@ -34,6 +34,7 @@ struct EstArgs {
     int64_t ld, ldE, ncells, nfaces;
     int N, N_ext, M_ext, order, nd, nq, nqf;
     const double* u;
+    const int32_t* pos;  // device column of active mode k (private column order of the vectors)
     const double* coords;
     const int32_t *cellnodes, *celldofs;
     const int32_t *cptr, *cm, *ck;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) k_est_volume(EstArgs a) {
             const int32_t* cd = a.celldofs + (int64_t)a.nd * cell;
             for (int k = threadIdx.x; k < a.N; k += blockDim.x) {
                 double s = 0.0;
-                for (int d = 0; d < a.nd; ++d) s += a.u[(int64_t)cd[d] * a.ld + k] * s_lapphi[d];
+                for (int d = 0; d < a.nd; ++d) s += a.u[(int64_t)cd[d] * a.ld + a.pos[k]] * s_lapphi[d];
                 lap[k] = s;
             }
         }
@@ -163,15 +164,16 @@ __global__ void __launch_bounds__(256) k_est_jumps(EstArgs a) {
         }
         __syncthreads();
         for (int k = threadIdx.x; k < a.N; k += blockDim.x) {
+            const int kc = a.pos[k];
             for (int pt = 0; pt < npt; ++pt) {
                 double gx = 0.0, gy = 0.0;
                 for (int d = 0; d < a.nd; ++d) {
-                    double u0 = a.u[(int64_t)s_dof[0][d] * a.ld + k];
+                    double u0 = a.u[(int64_t)s_dof[0][d] * a.ld + kc];
                     gx += u0 * s_g[0][pt][d][0];
                     gy += u0 * s_g[0][pt][d][1];
                 }
                 for (int d = 0; d < a.nd; ++d) {
-                    double u1 = a.u[(int64_t)s_dof[1][d] * a.ld + k];
+                    double u1 = a.u[(int64_t)s_dof[1][d] * a.ld + kc];
                     gx -= u1 * s_g[1][pt][d][0];
                     gy -= u1 * s_g[1][pt][d][1];
                 }
@@ -373,6 +375,7 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
 
     EstArgs a;
     a.ld = ctx->ld;
+    a.pos = ctx->d_pos;
     a.ldE = ldE;
     a.ncells = ncells;
     a.nfaces = nfaces;

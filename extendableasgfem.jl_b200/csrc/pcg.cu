@@ -14,12 +14,12 @@ namespace {
 
 // b[:, 0] += b0 ; rows at bdofs zeroed   (solvers_poisson_primal.jl:149-155)
 __global__ void k_make_rhs(double* __restrict__ b, const double* __restrict__ b0, const uint8_t* __restrict__ bmask,
-                           int64_t n, int64_t ld) {
+                           int64_t n, int64_t ld, int64_t col0) {
     int64_t total = n * ld;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t i = t / ld, mu = t - i * ld;
         double v = b[t];
-        if (mu == 0) v += b0[i];
+        if (mu == col0) v += b0[i];  // device column of mode 1 (the mean mode)
         b[t] = bmask[i] ? 0.0 : v;
     }
 }
@@ -106,7 +106,7 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
     tall.start();
     // b = deepcopy(sol); b[1] += b0; b[m][bdofs] = 0   -> stored in p for now
     PCG_CUDA(cudaMemcpyAsync(p, x, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_make_rhs<<<grid, 256, 0, ctx->stream>>>(p, b0, ctx->d_bmask, n, ld);
+    k_make_rhs<<<grid, 256, 0, ctx->stream>>>(p, b0, ctx->d_bmask, n, ld, (int64_t)ctx->h_pos[0]);
     // r = b - A x
     PCG_RC(apply_launch(ctx, x, q));
     PCG_CUDA(cudaMemcpyAsync(r, p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -58,7 +58,8 @@ struct PrecondPlan {
     int32_t* d_perm = nullptr;
     SmallDev small;
     std::vector<std::array<int, 3>> launches;  // (t0, t1, width class), forward order
-    double* d_work = nullptr;  // nred x ld
+    double* d_work = nullptr;  // nred x work_ld, (re)allocated by precond_apply when the column count of the vectors changes
+    int64_t work_ld = 0;
     int64_t lnz = 0;
 };
 
@@ -603,7 +604,6 @@ int precond_setup(asgfem_ctx* ctx) {
     if (rc) return rc;
     rc = dev_upload(ctx, &P->d_perm, F.perm);
     if (rc) return rc;
-    ASG_CUDA(ctx, cudaMalloc((void**)&P->d_work, sizeof(double) * (size_t)std::max<int64_t>(F.n, 1) * ctx->ld));
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -612,10 +612,18 @@ int precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
     PrecondPlan* P = ctx->precond;
     ASG_CHECK(ctx, P, ASGFEM_ESTATE, "precond_apply: setup missing");
     const int64_t ld = ctx->ld;
+    ASG_CHECK(ctx, ld > 0, ASGFEM_ESTATE, "precond_apply: multi-indices not set");
+    if (P->work_ld != ld) {  // the factor survives a change of the multi-index set, the work vector does not
+        if (P->d_work) cudaFree(P->d_work);
+        P->d_work = nullptr;
+        P->work_ld = 0;
+        ASG_CUDA(ctx, cudaMalloc((void**)&P->d_work, sizeof(double) * (size_t)std::max<int64_t>(P->nred, 1) * ld));
+        P->work_ld = ld;
+    }
     int blocks = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (P->nred * (ld / 2) + 255) / 256));
     if (P->nred > 0) {
         k_gather_perm<<<blocks, 256, 0, ctx->stream>>>(r, P->d_work, P->d_perm, P->nred, ld);
-        const int tiles = (int)((ctx->N + MT - 1) / MT);
+        const int tiles = (int)(ld / MT);  // all device columns (the column order is private, padding columns hold zeros)
         for (size_t k = 0; k < P->launches.size(); ++k)
             launch_small<false>(P->launches[k], tiles, ctx->stream, P->d_work, ld, P->small);
         for (size_t k = P->launches.size(); k-- > 0;)

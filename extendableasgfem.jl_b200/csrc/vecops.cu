@@ -1,7 +1,7 @@
 // SGFEVector storage and the PCG vector operations.
 //
-// Device layout (private): row-major n x ld, ld = N rounded up to 16, element (dof i, mode mu) at i*ld + mu;
-// the padding columns are kept at zero.  The boundary layout is the reference's flat entries vector
+// Device layout (private): row-major n x ld, element (dof i, mode mu) at i*ld + pos[mu] with the column order chosen by
+// the operator's plan (ctx->h_pos, apply_mma.cu), ld = number of columns (multiple of 32); padding columns are kept at zero.  The boundary layout is the reference's flat entries vector
 // (src/sgfevector.jl:97-101: block mu contiguous = column-major n x N); conversion happens here, on the
 // device, chunk by chunk through a staging buffer.
 #include <algorithm>
@@ -15,9 +15,9 @@ namespace {
 
 constexpr int TP = 32;
 
-// stage: mc x n (mode-major chunk of the reference layout) -> d[i*ld + mu0 + k]
+// stage: mc x n (mode-major chunk of the reference layout) -> d[i*ld + pos[mu0 + k]]
 __global__ void k_chunk_to_device(const double* __restrict__ stage, double* __restrict__ d, int64_t n, int64_t ld,
-                                  int64_t mu0, int mc) {
+                                  int64_t mu0, int mc, const int32_t* __restrict__ pos) {
     __shared__ double tile[TP][TP + 1];
     int64_t i0 = (int64_t)blockIdx.x * TP;
     int k0 = blockIdx.y * TP;
@@ -30,19 +30,19 @@ __global__ void k_chunk_to_device(const double* __restrict__ stage, double* __re
     for (int r = threadIdx.y; r < TP; r += blockDim.y) {
         int64_t i = i0 + r;
         int k = k0 + threadIdx.x;
-        if (i < n && k < mc) d[i * ld + mu0 + k] = tile[threadIdx.x][r];
+        if (i < n && k < mc) d[i * ld + pos[mu0 + k]] = tile[threadIdx.x][r];
     }
 }
 
 __global__ void k_chunk_to_host(const double* __restrict__ d, double* __restrict__ stage, int64_t n, int64_t ld,
-                                int64_t mu0, int mc) {
+                                int64_t mu0, int mc, const int32_t* __restrict__ pos) {
     __shared__ double tile[TP][TP + 1];
     int64_t i0 = (int64_t)blockIdx.x * TP;
     int k0 = blockIdx.y * TP;
     for (int r = threadIdx.y; r < TP; r += blockDim.y) {
         int64_t i = i0 + r;
         int k = k0 + threadIdx.x;
-        tile[r][threadIdx.x] = (i < n && k < mc) ? d[i * ld + mu0 + k] : 0.0;
+        tile[r][threadIdx.x] = (i < n && k < mc) ? d[i * ld + pos[mu0 + k]] : 0.0;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < TP; r += blockDim.y) {
@@ -60,11 +60,12 @@ __device__ __forceinline__ double splitmix_pm1(uint64_t idx, uint64_t seed) {
     return 2.0 * ((double)(z >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
 }
 
-__global__ void k_fill_random(double* __restrict__ d, int64_t n, int64_t N, int64_t ld, uint64_t seed) {
+__global__ void k_fill_random(double* __restrict__ d, int64_t n, int64_t ld, uint64_t seed, const int32_t* __restrict__ inv) {
     int64_t total = n * ld;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int64_t i = t / ld, mu = t - i * ld;
-        d[t] = mu < N ? splitmix_pm1((uint64_t)(i + n * mu), seed) : 0.0;
+        int64_t i = t / ld, c = t - i * ld;
+        const int64_t mu = inv[c];
+        d[t] = mu >= 0 ? splitmix_pm1((uint64_t)(i + n * mu), seed) : 0.0;
     }
 }
 
@@ -140,15 +141,17 @@ __global__ void k_mask_rows(double* __restrict__ x, const uint8_t* __restrict__ 
     }
 }
 
+// the exchange buffer is nrows x N in MODE order (both ends of an exchange may not share the private column order)
 __global__ void k_pack_rows(const double* __restrict__ v, int64_t ld, int64_t N, int64_t nrows,
-                            const int64_t* __restrict__ rows, double* __restrict__ buf, int pack) {
+                            const int64_t* __restrict__ rows, double* __restrict__ buf, int pack,
+                            const int32_t* __restrict__ pos) {
     for (int64_t r = blockIdx.x; r < nrows; r += gridDim.x) {
         int64_t i = rows[r] - 1;
         for (int64_t k = threadIdx.x; k < N; k += blockDim.x) {
             if (pack)
-                buf[r * N + k] = v[i * ld + k];
+                buf[r * N + k] = v[i * ld + pos[k]];
             else
-                const_cast<double*>(v)[i * ld + k] = buf[r * N + k];
+                const_cast<double*>(v)[i * ld + pos[k]] = buf[r * N + k];
         }
     }
 }
@@ -187,7 +190,7 @@ int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec) {
         ASG_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, host + n * mu0, sizeof(double) * n * c, cudaMemcpyHostToDevice,
                                       ctx->stream));
         dim3 grid((unsigned)((n + TP - 1) / TP), (unsigned)((c + TP - 1) / TP));
-        k_chunk_to_device<<<grid, dim3(TP, 8), 0, ctx->stream>>>(ctx->d_stage, dvec, n, ld, mu0, c);
+        k_chunk_to_device<<<grid, dim3(TP, 8), 0, ctx->stream>>>(ctx->d_stage, dvec, n, ld, mu0, c, ctx->d_pos);
     }
     ASG_CUDA(ctx, cudaGetLastError());
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -202,7 +205,7 @@ int vec_to_host_layout(asgfem_ctx* ctx, const double* dvec, double* host) {
     for (int64_t mu0 = 0; mu0 < N; mu0 += mc) {
         int c = (int)std::min<int64_t>(mc, N - mu0);
         dim3 grid((unsigned)((n + TP - 1) / TP), (unsigned)((c + TP - 1) / TP));
-        k_chunk_to_host<<<grid, dim3(TP, 8), 0, ctx->stream>>>(dvec, ctx->d_stage, n, ld, mu0, c);
+        k_chunk_to_host<<<grid, dim3(TP, 8), 0, ctx->stream>>>(dvec, ctx->d_stage, n, ld, mu0, c, ctx->d_pos);
         ASG_CUDA(ctx, cudaMemcpyAsync(host + n * mu0, ctx->d_stage, sizeof(double) * n * c, cudaMemcpyDeviceToHost,
                                       ctx->stream));
     }
@@ -270,7 +273,7 @@ int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* d
                                         (size_t)N, cudaMemcpyHostToDevice, P.sH));
         ASG_CUDA(ctx, cudaEventRecord(P.copied[s], P.sH));
         ASG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, P.copied[s], 0));
-        k_chunk_to_device<<<block_grid(rows), dim3(TP, 8), 0, ctx->stream>>>(P.in[s], dX + i0 * ld, rows, ld, 0, (int)N);
+        k_chunk_to_device<<<block_grid(rows), dim3(TP, 8), 0, ctx->stream>>>(P.in[s], dX + i0 * ld, rows, ld, 0, (int)N, ctx->d_pos);
         ASG_CUDA(ctx, cudaEventRecord(P.in_free[s], ctx->stream));
         while (next_apply < nb && dep[next_apply] <= b) {
             const int64_t a = next_apply++;
@@ -279,7 +282,7 @@ int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* d
             int rc = apply_launch(ctx, dX, dY, a0, a0 + arows);
             if (rc) return rc;
             if (a >= 2) ASG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, P.out_free[t], 0));
-            k_chunk_to_host<<<block_grid(arows), dim3(TP, 8), 0, ctx->stream>>>(dY + a0 * ld, P.out[t], arows, ld, 0, (int)N);
+            k_chunk_to_host<<<block_grid(arows), dim3(TP, 8), 0, ctx->stream>>>(dY + a0 * ld, P.out[t], arows, ld, 0, (int)N, ctx->d_pos);
             ASG_CUDA(ctx, cudaEventRecord(P.yready[t], ctx->stream));
             ASG_CUDA(ctx, cudaStreamWaitEvent(P.sD, P.yready[t], 0));
             ASG_CUDA(ctx, cudaMemcpy2DAsync(Ax + a0, sizeof(double) * n, P.out[t], sizeof(double) * arows,
@@ -313,7 +316,7 @@ int vec_dot(asgfem_ctx* ctx, const double* a, const double* b, int64_t nrows, do
 
 int vec_fill_random(asgfem_ctx* ctx, double* d, uint64_t seed) {
     int64_t total = ctx->n * ctx->ld;
-    k_fill_random<<<grid_for(total, 256), 256, 0, ctx->stream>>>(d, ctx->n, ctx->N, ctx->ld, seed);
+    k_fill_random<<<grid_for(total, 256), 256, 0, ctx->stream>>>(d, ctx->n, ctx->ld, seed, ctx->d_inv);
     ASG_CUDA(ctx, cudaGetLastError());
     return 0;
 }
@@ -342,7 +345,7 @@ int vec_mask_rows(asgfem_ctx* ctx, double* x) {
 int vec_pack_rows(asgfem_ctx* ctx, const double* v, int64_t nrows, const int64_t* d_rows, double* buf) {
     if (nrows == 0) return 0;
     k_pack_rows<<<(unsigned)std::min<int64_t>(nrows, 148 * 8), 256, 0, ctx->stream>>>(v, ctx->ld, ctx->N, nrows, d_rows,
-                                                                                     buf, 1);
+                                                                                     buf, 1, ctx->d_pos);
     ASG_CUDA(ctx, cudaGetLastError());
     return 0;
 }
@@ -350,7 +353,7 @@ int vec_pack_rows(asgfem_ctx* ctx, const double* v, int64_t nrows, const int64_t
 int vec_unpack_rows(asgfem_ctx* ctx, double* v, int64_t nrows, const int64_t* d_rows, const double* buf) {
     if (nrows == 0) return 0;
     k_pack_rows<<<(unsigned)std::min<int64_t>(nrows, 148 * 8), 256, 0, ctx->stream>>>(
-        v, ctx->ld, ctx->N, nrows, d_rows, const_cast<double*>(buf), 0);
+        v, ctx->ld, ctx->N, nrows, d_rows, const_cast<double*>(buf), 0, ctx->d_pos);
     ASG_CUDA(ctx, cudaGetLastError());
     return 0;
 }
@@ -388,7 +391,7 @@ __global__ void k_eval_samples(const double* __restrict__ u, int64_t n, int64_t 
 int vec_eval_samples(asgfem_ctx* ctx, const double* u, const double* dR, int64_t S, int64_t Spad, double* dout) {
     if (S <= 0 || ctx->n <= 0) return 0;
     dim3 grid((unsigned)std::min<int64_t>((ctx->n + 7) / 8, 148 * 8), (unsigned)(Spad / 8));
-    k_eval_samples<<<grid, 256, 0, ctx->stream>>>(u, ctx->n, ctx->ld, (int)ctx->N, dR, Spad, S, dout);
+    k_eval_samples<<<grid, 256, 0, ctx->stream>>>(u, ctx->n, ctx->ld, (int)ctx->ld, dR, Spad, S, dout);
     ASG_CUDA(ctx, cudaGetLastError());
     return 0;
 }
