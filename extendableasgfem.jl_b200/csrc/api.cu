@@ -104,8 +104,13 @@ extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t 
     }
     // coupling lists in column space (reference order of the entries of a mode kept)
     const Coupling& C = ctx->coup;
-    std::vector<int32_t> cptr((size_t)ctx->ld + 1, 0), cm, cnu;
-    std::vector<double> cg;
+    Coupling& CC = ctx->coup_col;
+    CC.ptr.assign((size_t)ctx->ld + 1, 0);
+    CC.m.clear();
+    CC.nu.clear();
+    CC.g.clear();
+    std::vector<int32_t>&cptr = CC.ptr, &cm = CC.m, &cnu = CC.nu;
+    std::vector<double>& cg = CC.g;
     for (int64_t c = 0; c < ctx->ld; ++c) {
         const int32_t mode = ctx->h_inv[(size_t)c];
         if (mode >= 0)
@@ -572,7 +577,7 @@ static int ensure_ready_for_apply(asgfem_ctx* ctx) {
 
 extern "C" int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant) {
     CTX_OR_FAIL(ctx);
-    ASG_CHECK(ctx, variant == 0 || variant == 1 || variant == 8, ASGFEM_EINVAL, "apply variant must be 0, 1 or 8");
+    ASG_CHECK(ctx, variant == 0 || variant == 1 || variant == 7 || variant == 8, ASGFEM_EINVAL, "apply variant must be 0, 1, 7 or 8");
     ctx->apply_variant = variant;
     return 0;
 }

@@ -43,10 +43,15 @@ k_apply_gather(int64_t row0, int64_t nrows, int64_t ld, int64_t nnz, const int64
     y[i * ld + c] = acc;
 }
 
-void apply_free_plan(asgfem_ctx* ctx) { ctx->apply_ready = false; }
+void apply_free_plan(asgfem_ctx* ctx) {
+    ctx->apply_ready = false;
+    apply_ts2_free(ctx);
+}
 
 int apply_build_plan(asgfem_ctx* ctx) {
     int rc = apply_mma_build(ctx);
+    if (rc) return rc;
+    rc = apply_ts2_build(ctx);
     if (rc) return rc;
     ctx->apply_ready = true;
     return 0;
@@ -60,11 +65,15 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_
     }
     r1 = std::min(r1, nrows_all);
     int variant = ctx->apply_variant;
-    if (variant == 0) variant = apply_mma_usable(ctx) ? 8 : 1;
+    // automatic choice by measurement (config 4, B200): packed mode-stationary DFMA kernel 51 ms, MMA kernel 72-82 ms
+    if (variant == 0) variant = apply_ts2_preferred(ctx) ? 7 : apply_mma_usable(ctx) ? 8 : 1;
     if (r1 <= r0) return 0;
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (variant == 8) {
         int rc = apply_mma_launch(ctx, x, y, r0, r1);
+        if (rc) return rc;
+    } else if (variant == 7) {
+        int rc = apply_ts2_launch(ctx, x, y, r0, r1);
         if (rc) return rc;
     } else {
         int bx = (int)std::min<int64_t>(128, ((ctx->ld + 31) / 32) * 32);

@@ -43,6 +43,7 @@ constexpr int MMA_WARPS = 16;
 constexpr int MMA_THREADS = MMA_WARPS * 32;
 constexpr uint32_t NOSTORE = 0xFFFFu;
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int MMA_MAXP = 3, MMA_MAXROWW = 1280, MMA_MAXW = 64;  // capacity of the kernel parameter block
 
 struct PairSteps {
     int blockE = -1, blockO = -1;
@@ -73,6 +74,9 @@ struct MmaPlan {
     uint32_t mb_doubles = 0;
     size_t smem_bytes = 0;
     uint32_t* d_blob = nullptr;
+    double* d_zero = nullptr;  // one row of zeros: X row of the unused neighbour slots
+    std::vector<uint32_t> h_step, h_crec, h_gcol;  // warp-uniform tables: passed as kernel parameters (constant bank)
+    std::vector<double> h_roww, h_wtab;
     int grid = 148;
     double dmma_per_row = 0;
 };
@@ -83,6 +87,7 @@ void apply_mma_free(asgfem_ctx* ctx) {
     MmaPlan* P = mp_of(ctx);
     if (!P) return;
     if (P->d_blob) cudaFree(P->d_blob);
+    if (P->d_zero) cudaFree(P->d_zero);
     delete P;
     ctx->mmaplan = nullptr;
 }
@@ -242,6 +247,123 @@ int apply_mma_layout(asgfem_ctx* ctx) {
     if (P->pairs.size() % 2) P->pairs.push_back(PairSteps());
     P->ncols = (int)P->pairs.size() * 16;
 
+    // ---- bank-aware order of the modes inside their blocks ---------------------------------------------------------------
+    // The mailbox entry of consumer column c lies in 8-byte bank c % 16 = 2 * (slot in its block) + (odd block of its pair),
+    // whatever group / row it is in.  A store instruction = (block, D-set, column parity): its 32 lanes (8 directions x 4
+    // modes) write to the consumers of their items, and costs as many wavefronts as the most loaded bank holds entries.
+    // Local search: swap two modes of a block, or the two blocks of a pair, while the summed cost of the stores goes down.
+    {
+        const size_t nb = P->blocks.size();
+        std::vector<int> block_of((size_t)N, -1), slot_of((size_t)N, -1), half_of(nb, 0), pair_of(nb, -1);
+        for (size_t b = 0; b < nb; ++b)
+            for (int sl = 0; sl < 8; ++sl)
+                if (P->blocks[b][(size_t)sl] >= 0) block_of[(size_t)P->blocks[b][(size_t)sl]] = (int)b, slot_of[(size_t)P->blocks[b][(size_t)sl]] = sl;
+        for (size_t q = 0; q < P->pairs.size(); ++q) {
+            if (P->pairs[q].blockE >= 0) half_of[(size_t)P->pairs[q].blockE] = 0, pair_of[(size_t)P->pairs[q].blockE] = (int)q;
+            if (P->pairs[q].blockO >= 0) half_of[(size_t)P->pairs[q].blockO] = 1, pair_of[(size_t)P->pairs[q].blockO] = (int)q;
+        }
+        // primary consumer of (mode, direction), and the producers (mode, direction) feeding a mode
+        std::vector<std::vector<std::pair<int, int>>> feeds((size_t)N);  // consumer -> (producer mode, direction)
+        for (int64_t nu = 0; nu < N; ++nu)
+            for (auto& it : P->prod[(size_t)nu])
+                if (it.primary) feeds[(size_t)it.consumer].push_back({(int)nu, it.dir});
+        auto consumer_of = [&](int mode, int dir) {
+            for (auto& it : P->prod[(size_t)mode])
+                if (it.primary && it.dir == dir) return it.consumer;
+            return -1;
+        };
+        auto store_cost = [&](int b, int k, int par) {
+            int cnt[16] = {0}, best = 0;
+            const auto& ds = P->dsets[(size_t)P->block_dsets[(size_t)b][(size_t)k]];
+            for (int c = 0; c < 4; ++c) {
+                const int mode = P->blocks[(size_t)b][(size_t)(2 * c + par)];
+                if (mode < 0) continue;
+                for (int r = 0; r < 8; ++r) {
+                    if (ds[(size_t)r] < 0) continue;
+                    const int cons = consumer_of(mode, ds[(size_t)r]);
+                    if (cons < 0) continue;
+                    best = std::max(best, ++cnt[2 * slot_of[(size_t)cons] + half_of[(size_t)block_of[(size_t)cons]]]);
+                }
+            }
+            return best;
+        };
+        auto stores_into = [&](int mode, std::vector<std::array<int, 3>>& out) {  // stores that deliver to mode
+            for (auto& f : feeds[(size_t)mode]) {
+                const int b = block_of[(size_t)f.first];
+                for (size_t k = 0; k < P->block_dsets[(size_t)b].size(); ++k) {
+                    const auto& ds = P->dsets[(size_t)P->block_dsets[(size_t)b][k]];
+                    if (std::find(ds.begin(), ds.end(), f.second) != ds.end()) out.push_back({b, (int)k, slot_of[(size_t)f.first] & 1});
+                }
+            }
+        };
+        auto total_of = [&](std::vector<std::array<int, 3>>& st) {
+            std::sort(st.begin(), st.end());
+            st.erase(std::unique(st.begin(), st.end()), st.end());
+            long t = 0;
+            for (auto& x : st) t += store_cost(x[0], x[1], x[2]);
+            return t;
+        };
+        long before_all = 0;
+        for (size_t b = 0; b < nb; ++b)
+            for (size_t k = 0; k < P->block_dsets[b].size(); ++k) before_all += store_cost((int)b, (int)k, 0) + store_cost((int)b, (int)k, 1);
+        for (int sweep = 0; sweep < 4; ++sweep) {
+            long gain = 0;
+            for (size_t b = 0; b < nb; ++b) {
+                for (int s1 = 0; s1 < 8; ++s1)
+                    for (int s2 = s1 + 1; s2 < 8; ++s2) {
+                        const int m1 = P->blocks[b][(size_t)s1], m2 = P->blocks[b][(size_t)s2];
+                        if (m1 < 0 && m2 < 0) continue;
+                        auto affected = [&](std::vector<std::array<int, 3>>& st) {
+                            st.clear();
+                            for (size_t k = 0; k < P->block_dsets[b].size(); ++k) st.push_back({(int)b, (int)k, 0}), st.push_back({(int)b, (int)k, 1});
+                            if (m1 >= 0) stores_into(m1, st);
+                            if (m2 >= 0) stores_into(m2, st);
+                        };
+                        std::vector<std::array<int, 3>> st;
+                        affected(st);
+                        const long c0 = total_of(st);
+                        std::swap(P->blocks[b][(size_t)s1], P->blocks[b][(size_t)s2]);
+                        if (m1 >= 0) slot_of[(size_t)m1] = s2;
+                        if (m2 >= 0) slot_of[(size_t)m2] = s1;
+                        affected(st);  // the parity of the producers' stores may have changed
+                        const long c1 = total_of(st);
+                        if (c1 < c0) {
+                            gain += c0 - c1;
+                        } else {
+                            std::swap(P->blocks[b][(size_t)s1], P->blocks[b][(size_t)s2]);
+                            if (m1 >= 0) slot_of[(size_t)m1] = s1;
+                            if (m2 >= 0) slot_of[(size_t)m2] = s2;
+                        }
+                    }
+            }
+            for (size_t q = 0; q < P->pairs.size(); ++q) {
+                PairSteps& ps = P->pairs[q];
+                if (ps.blockE < 0 || ps.blockO < 0) continue;
+                std::vector<std::array<int, 3>> st;
+                for (int half = 0; half < 2; ++half)
+                    for (int mode : P->blocks[(size_t)(half ? ps.blockO : ps.blockE)])
+                        if (mode >= 0) stores_into(mode, st);
+                const long c0 = total_of(st);
+                std::swap(ps.blockE, ps.blockO);
+                half_of[(size_t)ps.blockE] = 0, half_of[(size_t)ps.blockO] = 1;
+                const long c1 = total_of(st);
+                if (c1 < c0) {
+                    gain += c0 - c1;
+                } else {
+                    std::swap(ps.blockE, ps.blockO);
+                    half_of[(size_t)ps.blockE] = 0, half_of[(size_t)ps.blockO] = 1;
+                }
+            }
+            if (gain == 0) break;
+        }
+        if (getenv("ASGFEM_MMA_VERBOSE")) {
+            long after_all = 0, nst = 0;
+            for (size_t b = 0; b < nb; ++b)
+                for (size_t k = 0; k < P->block_dsets[b].size(); ++k) after_all += store_cost((int)b, (int)k, 0) + store_cost((int)b, (int)k, 1), nst += 2;
+            fprintf(stderr, "[mma] mailbox stores: %ld instructions, bank cost %ld -> %ld wavefronts per row\n", nst, before_all, after_all);
+        }
+    }
+
     // ---- device column order ---------------------------------------------------------------------------------------
     ctx->h_pos.assign((size_t)N, -1);
     ctx->h_inv.assign((size_t)P->ncols, -1);
@@ -304,7 +426,9 @@ int apply_mma_build(asgfem_ctx* ctx) {
     MmaPlan* P = mp_of(ctx);
     if (!P || !P->layout_ok) return 0;
     if (P->d_blob) cudaFree(P->d_blob);
+    if (P->d_zero) cudaFree(P->d_zero);
     P->d_blob = nullptr;
+    P->d_zero = nullptr;
     P->usable = false;
     const int64_t nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
     const int M = ctx->M, Mp = M + 1;
@@ -583,22 +707,12 @@ int apply_mma_build(asgfem_ctx* ctx) {
         // blob
         auto align4 = [](uint32_t v) { return (v + 3u) & ~3u; };
         uint32_t at = 0;
-        P->off_crec = at;  // 32-byte records first
-        at = align4(at + (uint32_t)crec.size() * 4u);
-        P->off_tailw = at;
-        at = align4(at + (uint32_t)roww.size() * 2u + 4u);
-        P->off_wtab = at;
-        at = align4(at + (uint32_t)wtab.size() * 2u);
         P->off_sw = at;
         at = align4(at + (uint32_t)sw.size());
         P->off_dtab = at;
         at = align4(at + (uint32_t)dtab.size());
-        P->off_step = at;
-        at = align4(at + (uint32_t)stepdesc.size());
         P->off_extra = at;
         at = align4(at + (uint32_t)extra.size() + 4u);
-        const uint32_t off_gcol = at;
-        at = align4(at + (uint32_t)gcol.size());
         P->nwords = at;
         const size_t smem = (size_t)at * 4 + ks_bytes + 2ull * mb_max * 8ull + 16;
         if (getenv("ASGFEM_MMA_VERBOSE")) {
@@ -612,17 +726,29 @@ int apply_mma_build(asgfem_ctx* ctx) {
         }
         if (smem > (size_t)SMEM_LIMIT) continue;  // more passes: smaller mailboxes
         std::vector<uint32_t> blob((size_t)at, 0u);
-        std::memcpy(&blob[P->off_crec], crec.data(), crec.size() * sizeof(ConsRec));
-        if (!roww.empty()) std::memcpy(&blob[P->off_tailw], roww.data(), roww.size() * 8);
-        std::memcpy(&blob[P->off_wtab], wtab.data(), wtab.size() * 8);
         std::memcpy(&blob[P->off_sw], sw.data(), sw.size() * 4);
         std::memcpy(&blob[P->off_dtab], dtab.data(), dtab.size() * 4);
-        std::memcpy(&blob[P->off_step], stepdesc.data(), stepdesc.size() * 4);
         if (!extra.empty()) std::memcpy(&blob[P->off_extra], extra.data(), extra.size() * 4);
-        std::memcpy(&blob[off_gcol], gcol.data(), gcol.size() * 4);
-        P->off_gcol = off_gcol;
+        // warp-uniform tables with the fixed strides of the kernel parameter block
+        if (npass > MMA_MAXP || roww.size() > (size_t)MMA_MAXROWW || wtab.size() > (size_t)MMA_MAXW) continue;
+        P->h_step.assign((size_t)MMA_MAXP * W * 8 * 4, 0u);
+        P->h_crec.assign((size_t)MMA_MAXP * W * 8 * 4, 0u);
+        P->h_gcol.assign((size_t)W * 8, 0xFFFFFFFFu);
+        for (int pass = 0; pass < npass; ++pass)
+            for (int w = 0; w < W; ++w) {
+                for (int st = 0; st < NS; ++st)
+                    std::memcpy(&P->h_step[(((size_t)pass * W + w) * 8 + st) * 4], &stepdesc[(((size_t)pass * W + w) * NS + st) * 4], 16);
+                for (int g = 0; g < NG; ++g)
+                    std::memcpy(&P->h_crec[(((size_t)pass * W + w) * 8 + g) * 4], &crec[((size_t)pass * W + w) * NG + g], 16);
+            }
+        for (int w = 0; w < W; ++w)
+            for (int g = 0; g < NG; ++g) P->h_gcol[(size_t)w * 8 + g] = gcol[(size_t)w * NG + g];
+        P->h_roww = roww;
+        P->h_wtab = wtab;
         ASG_CUDA(ctx, cudaMalloc((void**)&P->d_blob, blob.size() * 4));
         ASG_CUDA(ctx, cudaMemcpyAsync(P->d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ASG_CUDA(ctx, cudaMalloc((void**)&P->d_zero, sizeof(double) * (size_t)ctx->ld));
+        ASG_CUDA(ctx, cudaMemsetAsync(P->d_zero, 0, sizeof(double) * (size_t)ctx->ld, ctx->stream));
         ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         P->P = npass;
         P->NS = NS;
@@ -658,9 +784,19 @@ struct MmaArgs {
     const int32_t* col;
     const uint8_t* bmask;
     const uint32_t* blob;
+    const double* zero_row;
     int64_t nnz, ld, r0, r1;
-    int Mp, P, zero_after_read;
-    uint32_t nwords, off_step, off_sw, off_dtab, off_crec, off_tailw, off_extra, off_wtab, off_gcol, mb_doubles;
+    int Mp, P, zero_after_read, debug_skip;  // debug_skip: 1 = no products, 2 = no consumer sums (timing experiments only)
+    uint32_t nwords, off_sw, off_dtab, off_extra, mb_doubles;
+};
+
+// warp-uniform tables: kernel parameter (constant bank), so that their loads stay off the shared-memory pipe
+struct MmaTables {
+    uint4 step[MMA_MAXP * MMA_WARPS * 8];  // [pass][warp][8]: colbase bytes | D-sets | store word offset | -
+    uint4 crec[MMA_MAXP * MMA_WARPS * 8];  // [pass][warp][8]: ConsRec
+    double roww[MMA_MAXROWW];
+    double wtab[MMA_MAXW];
+    uint32_t gcol[MMA_WARPS * 8];
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -677,7 +813,7 @@ struct ConsRecD {  // device view of ConsRec
 };
 
 template <int KS, int NS, int NG>
-__global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
+__global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a, const __grid_constant__ MmaTables tab) {
     extern __shared__ __align__(16) unsigned char sm[];
     constexpr int KSTR = 4 * KS + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -702,17 +838,15 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
     const unsigned char* dtab_l = sm + a.off_dtab * 4u + q * 4;   // + D-set * 32: byte offset of this lane's K row
     const unsigned char* sw_l = sm + a.off_sw * 4u + lane * 8;     // + step * 256: store words of this lane
     const unsigned char* ks_l = sm + ks_off + kk * 8;              // + buffer + row offset + 32 s: A fragment entries
-    const uint4* stepd = reinterpret_cast<const uint4*>(sm + a.off_step * 4u) + warp * NS;
-    const ConsRecD* crec = reinterpret_cast<const ConsRecD*>(sm + a.off_crec * 4u) + warp * NG;
-    const unsigned char* roww = sm + a.off_tailw * 4u;
-    const double* wtab = reinterpret_cast<const double*>(sm + a.off_wtab * 4u);
+    const uint4* stepd = tab.step + warp * 8;
+    const uint4* crec = tab.crec + warp * 8;
     const unsigned char* extra_l = sm + a.off_extra * 4u + lane * 4;
     unsigned char* mb0 = sm + mb_off;
 
     uint32_t ycol[NG];  // byte offset of this thread's column of group g inside a row of Y (0xFFFFFFFF: unused slot)
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-        const uint32_t c = reinterpret_cast<const uint32_t*>(sm + a.off_gcol * 4u)[warp * NG + g];
+        const uint32_t c = tab.gcol[warp * 8 + g];
         ycol[g] = c == 0xFFFFFFFFu ? c : c + (uint32_t)lane * 8u;
     }
 
@@ -729,15 +863,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
                 dst[m * KSTR + sk_k] = 0.0;
         }
     };
-    // X rows this lane reads for a dof row: slot 4s + kk (beyond the row: the row itself, multiplied by K = 0)
+    // X rows this lane LOADS for a dof row.  The B fragment wants lane 4 q + kk to hold columns (2q, 2q+1) of the X row of
+    // slot 4s + kk, i.e. the four lanes of a quad read four different rows - the L1 data stage then spends one wavefront per
+    // 32-byte sector (measured: 16 per load instruction).  So lane l loads the 16 bytes (l & 7) of the row of slot
+    // 4s + (l >> 3) (eight consecutive lanes = one 128-byte line, 4 wavefronts) and the fragments are permuted with
+    // shuffles when they are used (lane 4q + kk <- lane 8 kk + q).  Slots beyond the row read a row of zeros.
+    const int lrow = lane >> 3, lchunk = lane & 7;
+    const int frag_src = (kk << 3) | q;
     auto row_ptrs = [&](int64_t row, const char* (&xr)[KS]) {
         const int64_t p0 = a.rowptr[row];
         const int len = (int)(a.rowptr[row + 1] - p0);
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
-            const int slot = 4 * s + kk;
-            const int64_t j = slot < len ? (int64_t)a.col[p0 + slot] : row;
-            xr[s] = reinterpret_cast<const char*>(a.x + j * a.ld + 2 * q);
+            const int slot = 4 * s + lrow;
+            xr[s] = reinterpret_cast<const char*>((slot < len ? a.x + (int64_t)a.col[p0 + slot] * a.ld : a.zero_row) + 2 * lchunk);
         }
     };
 
@@ -747,13 +886,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
     for (int g = 0; g < NG; ++g) acc[g] = 0.0;
 
     auto load_b = [&](int pass, const char* const (&xr)[KS]) {
-        const uint4* sd = stepd + pass * (MMA_WARPS * NS);
+        const uint4* sd = stepd + pass * (MMA_WARPS * 8);
 #pragma unroll
         for (int st = 0; st < NS; ++st) {
             const uint4 d = sd[st];
             if (d.y != 0) {
 #pragma unroll
-                for (int s = 0; s < KS; ++s) B[st][s] = *reinterpret_cast<const double2*>(xr[s] + d.x);
+                for (int s = 0; s < KS; ++s)
+                    B[st][s] = *reinterpret_cast<const double2*>(xr[s] + d.x);
             }
         }
     };
@@ -791,11 +931,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
             // ---- produce: NS steps = (pair of home blocks, D-set of each); outputs go to the mailbox of this stage -----------
             unsigned char* mb = mb0 + par * mb_bytes;
             const unsigned char* ksrc = ks_l + kb * kbuf_bytes;
-            const uint4* sd = stepd + pass * (MMA_WARPS * NS);
+            const uint4* sd = stepd + pass * (MMA_WARPS * 8);
 #pragma unroll
             for (int st = 0; st < NS; st += 2) {
                 const uint4 d0 = sd[st], d1 = sd[st + 1];
-                if (d0.y != 0) {  // warp-uniform; used step slots come first, an unused partner computes zeros and stores nothing
+                if (d0.y != 0 && !(a.debug_skip & 1)) {  // warp-uniform; used step slots come first, an unused partner computes zeros and stores nothing
                     const uint4 dd[2] = {d0, d1};
                     double aE[2][KS], aO[2][KS];
                     uint2 w[2];
@@ -817,8 +957,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
                     for (int s = 0; s < KS; ++s)
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
-                            dmma(c[u][0], c[u][1], aE[u][s], B[st + u][s].x);
-                            dmma(c[u][2], c[u][3], aO[u][s], B[st + u][s].y);
+                            const double bx = __shfl_sync(0xffffffffu, B[st + u][s].x, frag_src);
+                            const double by = __shfl_sync(0xffffffffu, B[st + u][s].y, frag_src);
+                            dmma(c[u][0], c[u][1], aE[u][s], bx);
+                            dmma(c[u][2], c[u][3], aO[u][s], by);
                         }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
@@ -831,19 +973,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
                 }
             }
             // ---- B fragments of the next stage --------------------------------------------------------------------------
-            if (nrow < re) load_b(npass, xr);
+            if (nrow < re && !(a.debug_skip & 4)) load_b(npass, xr);
         }
         } else {
         if (have_prev) {
             // ---- consume the previous stage from the other mailbox: weighted column sums of the groups of this warp ----------
             unsigned char* mb = mb0 + (par ^ 1u) * mb_bytes;
-            const ConsRecD* cr = crec + cpass * (MMA_WARPS * NG);
+            const uint4* cr = crec + cpass * (MMA_WARPS * 8);
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                const ConsRecD h = cr[g];
+                const uint4 hh = cr[g];
+                const ConsRecD h = {hh.x, hh.y, hh.z, hh.w};
                 const unsigned char* src = mb + h.base + lane * 8;
-                const unsigned char* wr = roww + (h.roww & 0xFFFFFu);
-                const uint32_t npair = h.roww >> 20;
+                const unsigned char* wr = reinterpret_cast<const unsigned char*>(tab.roww) + (h.roww & 0xFFFFFu);
+                const uint32_t npair = (a.debug_skip & 2) ? 0u : h.roww >> 20;
                 double t0 = acc[g], t1 = 0.0;
                 uint32_t r = npair;
                 while (r >= 4) {  // 8 mailbox rows per trip: independent loads first
@@ -880,7 +1023,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
                 const unsigned char* ex = extra_l + h.extra0;
                 for (uint32_t e = 0; e < h.nextra; ++e) {
                     const uint32_t word = *reinterpret_cast<const uint32_t*>(ex + e * 128);
-                    t1 = fma(wtab[word >> 16], *reinterpret_cast<const double*>(mb + (word & 0xFFFFu) * 8u), t1);
+                    t1 = fma(tab.wtab[word >> 16], *reinterpret_cast<const double*>(mb + (word & 0xFFFFu) * 8u), t1);
                 }
                 acc[g] = t0 + t1;
             }
@@ -890,9 +1033,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
                 __syncthreads();
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const ConsRecD h = cr[g];
-                    unsigned char* dst = mb + h.base + lane * 8;
-                    for (uint32_t r = 0; r < 2 * (h.roww >> 20); ++r) *reinterpret_cast<double*>(dst + r * 256) = 0.0;
+                    const uint4 hh = cr[g];
+                    unsigned char* dst = mb + hh.x + lane * 8;
+                    for (uint32_t r = 0; r < 2 * (hh.y >> 20); ++r) *reinterpret_cast<double*>(dst + r * 256) = 0.0;
                 }
             }
             if (cpass == a.P - 1) {
@@ -918,7 +1061,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a) {
 }
 
 template <int KS, int NS, int NG>
-int launch_mma(asgfem_ctx* ctx, MmaPlan* P, const MmaArgs& a) {
+int launch_mma(asgfem_ctx* ctx, MmaPlan* P, const MmaArgs& a, const MmaTables& tab) {
     static bool configured = false;
     if (!configured) {
         ASG_CUDA(ctx, cudaFuncSetAttribute(k_apply_mma<KS, NS, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -926,16 +1069,16 @@ int launch_mma(asgfem_ctx* ctx, MmaPlan* P, const MmaArgs& a) {
     }
     const int64_t nr = a.r1 - a.r0;
     const int grid = (int)std::min<int64_t>(P->grid, nr);
-    k_apply_mma<KS, NS, NG><<<grid, MMA_THREADS, P->smem_bytes, ctx->stream>>>(a);
+    k_apply_mma<KS, NS, NG><<<grid, MMA_THREADS, P->smem_bytes, ctx->stream>>>(a, tab);
     ASG_CUDA(ctx, cudaGetLastError());
     return 0;
 }
 
 template <int KS, int NS>
-int launch_mma_ng(asgfem_ctx* ctx, MmaPlan* P, const MmaArgs& a) {
-    if (P->NG <= 2) return launch_mma<KS, NS, 2>(ctx, P, a);
-    if (P->NG <= 4) return launch_mma<KS, NS, 4>(ctx, P, a);
-    return launch_mma<KS, NS, 8>(ctx, P, a);
+int launch_mma_ng(asgfem_ctx* ctx, MmaPlan* P, const MmaArgs& a, const MmaTables& tab) {
+    if (P->NG <= 2) return launch_mma<KS, NS, 2>(ctx, P, a, tab);
+    if (P->NG <= 4) return launch_mma<KS, NS, 4>(ctx, P, a, tab);
+    return launch_mma<KS, NS, 8>(ctx, P, a, tab);
 }
 
 }  // namespace
@@ -951,31 +1094,36 @@ int apply_mma_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
     a.col = ctx->d_col;
     a.bmask = ctx->d_bmask;
     a.blob = P->d_blob;
+    a.zero_row = P->d_zero;
     a.nnz = ctx->nnz;
     a.ld = ctx->ld;
     a.r0 = r0;
     a.r1 = r1;
     a.Mp = ctx->M + 1;
     a.P = P->P;
+    a.debug_skip = getenv("ASGFEM_MMA_SKIP") ? atoi(getenv("ASGFEM_MMA_SKIP")) : 0;
     a.zero_after_read = P->P > 2 ? 1 : 0;  // a mailbox buffer serves passes with different layouts: padding must stay zero
     a.nwords = P->nwords;
-    a.off_step = P->off_step;
     a.off_sw = P->off_sw;
     a.off_dtab = P->off_dtab;
-    a.off_crec = P->off_crec;
-    a.off_tailw = P->off_tailw;
     a.off_extra = P->off_extra;
-    a.off_wtab = P->off_wtab;
-    a.off_gcol = P->off_gcol;
     a.mb_doubles = P->mb_doubles;
+    static MmaTables tab;  // 28 KB: filled per launch from the plan (host copies only)
+    std::memcpy(tab.step, P->h_step.data(), sizeof(tab.step));
+    std::memcpy(tab.crec, P->h_crec.data(), sizeof(tab.crec));
+    std::memset(tab.roww, 0, sizeof(tab.roww));
+    std::memcpy(tab.roww, P->h_roww.data(), P->h_roww.size() * 8);
+    std::memset(tab.wtab, 0, sizeof(tab.wtab));
+    std::memcpy(tab.wtab, P->h_wtab.data(), P->h_wtab.size() * 8);
+    std::memcpy(tab.gcol, P->h_gcol.data(), sizeof(tab.gcol));
     switch (P->KS * 16 + P->NS) {
-        case 2 * 16 + 2: return launch_mma_ng<2, 2>(ctx, P, a);
-        case 2 * 16 + 4: return launch_mma_ng<2, 4>(ctx, P, a);
-        case 2 * 16 + 6: return launch_mma_ng<2, 6>(ctx, P, a);
-        case 2 * 16 + 8: return launch_mma_ng<2, 8>(ctx, P, a);
-        case 4 * 16 + 2: return launch_mma_ng<4, 2>(ctx, P, a);
-        case 4 * 16 + 4: return launch_mma_ng<4, 4>(ctx, P, a);
-        case 6 * 16 + 2: return launch_mma_ng<6, 2>(ctx, P, a);
+        case 2 * 16 + 2: return launch_mma_ng<2, 2>(ctx, P, a, tab);
+        case 2 * 16 + 4: return launch_mma_ng<2, 4>(ctx, P, a, tab);
+        case 2 * 16 + 6: return launch_mma_ng<2, 6>(ctx, P, a, tab);
+        case 2 * 16 + 8: return launch_mma_ng<2, 8>(ctx, P, a, tab);
+        case 4 * 16 + 2: return launch_mma_ng<4, 2>(ctx, P, a, tab);
+        case 4 * 16 + 4: return launch_mma_ng<4, 4>(ctx, P, a, tab);
+        case 6 * 16 + 2: return launch_mma_ng<6, 2>(ctx, P, a, tab);
         default: return fail(ctx, ASGFEM_ESTATE, "MMA operator: no kernel instance for this shape");
     }
 }

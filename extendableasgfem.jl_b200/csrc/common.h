@@ -89,6 +89,7 @@ struct asgfem_ctx {
     int family = 0;
     asgfem::MultiIndexSet mis;
     asgfem::Coupling coup;
+    asgfem::Coupling coup_col;  // the same lists in device column space: "mode" c = column c (ld entries, padding columns empty)
     std::vector<double> gp, gm;
     int32_t* d_cptr = nullptr;
     int32_t* d_cm = nullptr;
@@ -133,6 +134,7 @@ struct asgfem_ctx {
     bool apply_ready = false;  // kernel tables of the operator built for the current pattern / multi-index set
     asgfem::PrecondPlan* precond = nullptr;
     void* mmaplan = nullptr;  // asgfem::MmaPlan (apply_mma.cu)
+    void* ts2plan = nullptr;  // asgfem::Ts2Plan (apply_ts2.cu)
 };
 
 namespace asgfem {
@@ -180,6 +182,11 @@ int apply_mma_build(asgfem_ctx* ctx);    // kernel tables (first apply after the
 bool apply_mma_usable(asgfem_ctx* ctx);
 void apply_mma_free(asgfem_ctx* ctx);
 int apply_mma_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
+// apply_ts2.cu
+int apply_ts2_build(asgfem_ctx* ctx);
+void apply_ts2_free(asgfem_ctx* ctx);
+int apply_ts2_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
+bool apply_ts2_preferred(asgfem_ctx* ctx);
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
 int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* dX, double* dY);

@@ -201,6 +201,29 @@ __global__ void k_shfl(double* out, long long* cyc) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// ---- F2: 4 SHFL.32 + 2 LDS.64 (stride 1) per iteration: do shuffles take shared-memory pipe cycles?
+__global__ void k_shfl_lds(double* out, long long* cyc) {
+  extern __shared__ double sm[];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = i;
+  __syncthreads();
+  unsigned base = smem_u32(sm) + (threadIdx.x & 31) * 8;
+  int v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3;
+  double acc = 0;
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; i++) {
+    v0 = __shfl_xor_sync(0xffffffffu, v0, 1); v1 = __shfl_xor_sync(0xffffffffu, v1, 2);
+    v2 = __shfl_xor_sync(0xffffffffu, v2, 4); v3 = __shfl_xor_sync(0xffffffffu, v3, 8);
+    double a, b;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(base));
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b) : "r"(base + 512));
+    acc += a + b;
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + v0 + v1 + v2 + v3;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 // ---- G: STS.64 stride 1 + LDS.64 stride 1 (exchange pattern)
 __global__ void k_xchg(double* out, long long* cyc) {
   extern __shared__ double sm[];
@@ -240,7 +263,7 @@ int main() {
   CK(cudaMalloc(&xin, sizeof(double) * 1024 * 4 * 7));
   CK(cudaMemset(xin, 0, sizeof(double) * 1024 * 4 * 7));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  const int smem = 65536;
+  const int smem = 32768;
 #define RUN(name, per_thread_ops, unit, launch) \
   for (int rep = 0; rep < 2; rep++) { CK(cudaEventRecord(e0)); launch; CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize()); CK(cudaGetLastError()); \
     if (rep) { float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); double c = med_cycles(cyc, nsm); \
@@ -273,6 +296,7 @@ int main() {
   for (int nw : {8, 16, 32}) {
     RUN("STS.64 + LDS.64 stride 1 (pairs)", 4.0 * ITERS / 32, "pair", (k_xchg<<<nsm, nw * 32, 131072>>>(out, cyc)));
     RUN("SHFL 64-bit", 4.0 * ITERS / 32, "shfl64", (k_shfl<<<nsm, nw * 32>>>(out, cyc)));
+    RUN("4 SHFL.32 + 2 LDS.64 stride 1 (iterations)", 1.0 * ITERS / 32, "iter", (k_shfl_lds<<<nsm, nw * 32, smem>>>(out, cyc)));
   }
   for (int nw : {8, 16}) {
     RUN("unit: 7 LDS.64 bcast + 7 DFMA, 1 mode/lane", 21.0 * 7 * 1 * (ITERS / 4), "FMA", (k_unit<1, 0><<<nsm, nw * 32, smem>>>(out, cyc, xin)));
