@@ -75,6 +75,7 @@ struct MmaPlan {
     size_t smem_bytes = 0;
     uint32_t* d_blob = nullptr;
     double* d_zero = nullptr;  // one row of zeros: X row of the unused neighbour slots
+    int32_t* d_rowmeta = nullptr;  // per row 4 + 4 KS ints: first CSR position (int64), length, Dirichlet flag, columns (ELL)
     std::vector<uint32_t> h_step, h_crec, h_gcol;  // warp-uniform tables: passed as kernel parameters (constant bank)
     std::vector<double> h_roww, h_wtab;
     int grid = 148;
@@ -88,6 +89,7 @@ void apply_mma_free(asgfem_ctx* ctx) {
     if (!P) return;
     if (P->d_blob) cudaFree(P->d_blob);
     if (P->d_zero) cudaFree(P->d_zero);
+    if (P->d_rowmeta) cudaFree(P->d_rowmeta);
     delete P;
     ctx->mmaplan = nullptr;
 }
@@ -427,8 +429,10 @@ int apply_mma_build(asgfem_ctx* ctx) {
     if (!P || !P->layout_ok) return 0;
     if (P->d_blob) cudaFree(P->d_blob);
     if (P->d_zero) cudaFree(P->d_zero);
+    if (P->d_rowmeta) cudaFree(P->d_rowmeta);
     P->d_blob = nullptr;
     P->d_zero = nullptr;
+    P->d_rowmeta = nullptr;
     P->usable = false;
     const int64_t nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
     const int M = ctx->M, Mp = M + 1;
@@ -446,7 +450,8 @@ int apply_mma_build(asgfem_ctx* ctx) {
     if (NG > 8) return 0;
     NG = NG <= 2 ? 2 : NG <= 4 ? 4 : 8;  // the kernel instances
     P->NG = NG;
-    const size_t ks_bytes = 2ull * (size_t)(Mp + 1) * (size_t)KSTR * 8ull;
+    // K buffers: 2 (two or more passes) or 3 (one pass); ring of 8 row records
+    auto ks_bytes_of = [&](int npass) { return (size_t)(npass >= 2 ? 2 : 3) * (size_t)(Mp + 1) * (size_t)KSTR * 8ull + 8ull * (4 + 4 * KS) * 4ull; };
     auto wbits = [](double w) {
         uint64_t b;
         std::memcpy(&b, &w, 8);
@@ -714,7 +719,7 @@ int apply_mma_build(asgfem_ctx* ctx) {
         P->off_extra = at;
         at = align4(at + (uint32_t)extra.size() + 4u);
         P->nwords = at;
-        const size_t smem = (size_t)at * 4 + ks_bytes + 2ull * mb_max * 8ull + 16;
+        const size_t smem = (size_t)at * 4 + ks_bytes_of(npass) + 2ull * mb_max * 8ull + 16;
         if (getenv("ASGFEM_MMA_VERBOSE")) {
             size_t items = 0;
             for (auto& pr : P->prod) items += pr.size();
@@ -747,6 +752,22 @@ int apply_mma_build(asgfem_ctx* ctx) {
         P->h_wtab = wtab;
         ASG_CUDA(ctx, cudaMalloc((void**)&P->d_blob, blob.size() * 4));
         ASG_CUDA(ctx, cudaMemcpyAsync(P->d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        {
+            // row records: what the kernel needs of the CSR structure of a row, in one contiguous piece (fetched two rows ahead)
+            const int ME = 4 + 4 * KS;
+            std::vector<int32_t> meta((size_t)nrows * ME, 0);
+            for (int64_t i = 0; i < nrows; ++i) {
+                int32_t* m = &meta[(size_t)i * ME];
+                const int64_t p0 = ctx->h_rowptr[i];
+                std::memcpy(m, &p0, 8);
+                m[2] = (int32_t)(ctx->h_rowptr[i + 1] - p0);
+                m[3] = ctx->h_bmask.empty() ? 0 : ctx->h_bmask[(size_t)i];
+                for (int k = 0; k < m[2]; ++k) m[4 + k] = ctx->h_col[(size_t)(p0 + k)];
+            }
+            ASG_CUDA(ctx, cudaMalloc((void**)&P->d_rowmeta, meta.size() * 4));
+            ASG_CUDA(ctx, cudaMemcpyAsync(P->d_rowmeta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         ASG_CUDA(ctx, cudaMalloc((void**)&P->d_zero, sizeof(double) * (size_t)ctx->ld));
         ASG_CUDA(ctx, cudaMemsetAsync(P->d_zero, 0, sizeof(double) * (size_t)ctx->ld, ctx->stream));
         ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -785,6 +806,7 @@ struct MmaArgs {
     const uint8_t* bmask;
     const uint32_t* blob;
     const double* zero_row;
+    const int32_t* rowmeta;
     int64_t nnz, ld, r0, r1;
     int Mp, P, zero_after_read, debug_skip;  // debug_skip: 1 = no products, 2 = no consumer sums (timing experiments only)
     uint32_t nwords, off_sw, off_dtab, off_extra, mb_doubles;
@@ -812,26 +834,39 @@ struct ConsRecD {  // device view of ConsRec
     uint32_t base, roww, extra0, nextra;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <int KS, int NS, int NG>
 __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a, const __grid_constant__ MmaTables tab) {
     extern __shared__ __align__(16) unsigned char sm[];
     constexpr int KSTR = 4 * KS + 4;
+    constexpr int ME = 4 + 4 * KS;  // ints per row record
+    constexpr int RING = 8;         // row records in flight
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = lane >> 2, kk = lane & 3;
+    const int LA = a.P >= 2 ? 1 : 2;  // rows of lookahead: data issued in stage t is complete at the end of stage t + 1
+    const int KB = LA + 1;            // K buffers
     const uint32_t kbuf_bytes = (uint32_t)(a.Mp + 1) * KSTR * 8u;  // one K buffer (directions 0..M and the null row)
-    const uint32_t ks_off = a.nwords * 4u, mb_off = ks_off + 2u * kbuf_bytes, mb_bytes = a.mb_doubles * 8u;
+    const uint32_t meta_off = a.nwords * 4u, ks_off = meta_off + RING * ME * 4u, mb_off = ks_off + KB * kbuf_bytes,
+                   mb_bytes = a.mb_doubles * 8u;
 
     // rows of this CTA: r0 + blockIdx.x + k * gridDim.x.  The CTAs walk the mesh side by side, so the X rows of the
     // neighbouring mesh lines (read again a few hundred rows later) are still in L2.
     const int64_t rstep = gridDim.x;
-    const int64_t rb = a.r0 + (int64_t)blockIdx.x, re = a.r1;
-    if (rb >= re) return;
+    const int64_t rb = a.r0 + (int64_t)blockIdx.x;
+    if (rb >= a.r1) return;
+    const int64_t nri = (a.r1 - rb + rstep - 1) / rstep;  // rows of this CTA
 
     {
         uint32_t* blob = reinterpret_cast<uint32_t*>(sm);
         for (uint32_t i = tid; i < a.nwords; i += MMA_THREADS) blob[i] = a.blob[i];
-        double* z = reinterpret_cast<double*>(sm + ks_off);
-        for (uint32_t i = tid; i < (2u * kbuf_bytes + 2u * mb_bytes) / 8u; i += MMA_THREADS) z[i] = 0.0;
+        double* z = reinterpret_cast<double*>(sm + meta_off);
+        for (uint32_t i = tid; i < (RING * ME * 4u + KB * kbuf_bytes + 2u * mb_bytes) / 8u; i += MMA_THREADS) z[i] = 0.0;
     }
     __syncthreads();
 
@@ -842,6 +877,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a, c
     const uint4* crec = tab.crec + warp * 8;
     const unsigned char* extra_l = sm + a.off_extra * 4u + lane * 4;
     unsigned char* mb0 = sm + mb_off;
+    int32_t* meta = reinterpret_cast<int32_t*>(sm + meta_off);
 
     uint32_t ycol[NG];  // byte offset of this thread's column of group g inside a row of Y (0xFFFFFFFF: unused slot)
 #pragma unroll
@@ -850,17 +886,22 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a, c
         ycol[g] = c == 0xFFFFFFFFu ? c : c + (uint32_t)lane * 8u;
     }
 
-    // K rows of a dof row -> Ks[buf][m][k] (k >= length of the row: 0); one element per thread and trip
+    // row record ri (first CSR position, length, columns) -> ring slot ri % RING, asynchronously
+    auto meta_fetch = [&](int64_t ri) {
+        if (tid < ME / 4) cp_async16(meta + (ri % RING) * ME + tid * 4, a.rowmeta + (rb + ri * rstep) * ME + tid * 4);
+    };
+    // K rows of row ri -> Ks[ri % KB][m][k] (k >= length of the row: 0); needs the row record; one element per thread and trip
     const int sk_m = tid / (4 * KS), sk_k = tid - sk_m * (4 * KS);
-    auto stage_k = [&](int64_t row, int buf) {
-        const int64_t p0 = a.rowptr[row];
-        const int len = (int)(a.rowptr[row + 1] - p0);
-        double* dst = reinterpret_cast<double*>(sm + ks_off + buf * kbuf_bytes);
-        for (int m = sk_m; m < a.Mp; m += MMA_THREADS / (4 * KS)) {
+    auto stage_k = [&](int64_t ri) {
+        const int32_t* m = meta + (ri % RING) * ME;
+        const int64_t p0 = *reinterpret_cast<const int64_t*>(m);
+        const int len = m[2];
+        double* dst = reinterpret_cast<double*>(sm + ks_off + (uint32_t)(ri % KB) * kbuf_bytes);
+        for (int mm = sk_m; mm < a.Mp; mm += MMA_THREADS / (4 * KS)) {
             if (sk_k < len)
-                cp_async8(dst + m * KSTR + sk_k, a.vals + (int64_t)m * a.nnz + p0 + sk_k);
+                cp_async8(dst + mm * KSTR + sk_k, a.vals + (int64_t)mm * a.nnz + p0 + sk_k);
             else
-                dst[m * KSTR + sk_k] = 0.0;
+                dst[mm * KSTR + sk_k] = 0.0;
         }
     };
     // X rows this lane LOADS for a dof row.  The B fragment wants lane 4 q + kk to hold columns (2q, 2q+1) of the X row of
@@ -870,13 +911,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a, c
     // shuffles when they are used (lane 4q + kk <- lane 8 kk + q).  Slots beyond the row read a row of zeros.
     const int lrow = lane >> 3, lchunk = lane & 7;
     const int frag_src = (kk << 3) | q;
-    auto row_ptrs = [&](int64_t row, const char* (&xr)[KS]) {
-        const int64_t p0 = a.rowptr[row];
-        const int len = (int)(a.rowptr[row + 1] - p0);
+    auto row_ptrs = [&](int64_t ri, const char* (&xr)[KS]) {
+        const int32_t* m = meta + (ri % RING) * ME;
+        const int len = m[2];
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             const int slot = 4 * s + lrow;
-            xr[s] = reinterpret_cast<const char*>((slot < len ? a.x + (int64_t)a.col[p0 + slot] * a.ld : a.zero_row) + 2 * lchunk);
+            xr[s] = reinterpret_cast<const char*>((slot < len ? a.x + (int64_t)m[4 + slot] * a.ld : a.zero_row) + 2 * lchunk);
         }
     };
 
@@ -892,171 +933,178 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_apply_mma(const MmaArgs a, c
             const uint4 d = sd[st];
             if (d.y != 0) {
 #pragma unroll
-                for (int s = 0; s < KS; ++s)
-                    B[st][s] = *reinterpret_cast<const double2*>(xr[s] + d.x);
+                for (int s = 0; s < KS; ++s) B[st][s] = *reinterpret_cast<const double2*>(xr[s] + d.x);
             }
         }
     };
 
-    // prologue: K rows and B fragments of the first stage
-    stage_k(rb, 0);
+    // prologue: row records of the first 2 LA rows, K rows of the first LA rows, B fragments of the first stage
+    for (int64_t j = 0; j < 2 * LA && j < nri; ++j) meta_fetch(j);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int64_t j = 0; j < LA && j < nri; ++j) stage_k(j);
     {
         const char* xr[KS];
-        row_ptrs(rb, xr);
+        row_ptrs(0, xr);
         load_b(0, xr);
     }
     cp_async_wait_all();
     __syncthreads();
 
-    int pass = 0, kb = 0;
-    int64_t row = rb;
+    int pass = 0;
+    int64_t ri = 0;
     uint32_t par = 0;  // parity of the stage = mailbox buffer
     bool have_prev = false;
     int cpass = 0;
-    int64_t crow = rb;
-    while (row < re || have_prev) {
-        const bool produce = row < re;
+    int64_t cri = 0;
+    while (ri < nri || have_prev) {
+        const bool produce = ri < nri;
         // odd warps consume first: the shared-memory reads of one half of the warps overlap the fp64 products of the other
         for (int phase = 0; phase < 2; ++phase) {
-        if (phase == (warp & 1)) {
-        if (produce) {
-            if (pass == 0 && row + rstep < re) stage_k(row + rstep, kb ^ 1);
-            // pointers of the next stage's row (the index loads are in flight during the products)
-            int npass = pass + 1;
-            int64_t nrow = row;
-            if (npass == a.P) npass = 0, nrow += rstep;
-            const char* xr[KS];
-            if (nrow < re) row_ptrs(nrow, xr);
+            if (phase == (warp & 1)) {
+                if (produce) {
+                    if (pass == 0) {
+                        if (ri + 2 * LA < nri) meta_fetch(ri + 2 * LA);
+                        if (ri + LA < nri) stage_k(ri + LA);
+                    }
+                    // pointers of the next stage's row
+                    int npass = pass + 1;
+                    int64_t nxt = ri;
+                    if (npass == a.P) npass = 0, ++nxt;
+                    const char* xr[KS];
+                    if (nxt < nri) row_ptrs(nxt, xr);
 
-            // ---- produce: NS steps = (pair of home blocks, D-set of each); outputs go to the mailbox of this stage -----------
-            unsigned char* mb = mb0 + par * mb_bytes;
-            const unsigned char* ksrc = ks_l + kb * kbuf_bytes;
-            const uint4* sd = stepd + pass * (MMA_WARPS * 8);
+                    // ---- produce: NS steps = (pair of home blocks, D-set of each); outputs go to the mailbox of this stage ---
+                    unsigned char* mb = mb0 + par * mb_bytes;
+                    const unsigned char* ksrc = ks_l + (uint32_t)(ri % KB) * kbuf_bytes;
+                    const uint4* sd = stepd + pass * (MMA_WARPS * 8);
 #pragma unroll
-            for (int st = 0; st < NS; st += 2) {
-                const uint4 d0 = sd[st], d1 = sd[st + 1];
-                if (d0.y != 0 && !(a.debug_skip & 1)) {  // warp-uniform; used step slots come first, an unused partner computes zeros and stores nothing
-                    const uint4 dd[2] = {d0, d1};
-                    double aE[2][KS], aO[2][KS];
-                    uint2 w[2];
+                    for (int st = 0; st < NS; st += 2) {
+                        const uint4 d0 = sd[st], d1 = sd[st + 1];
+                        if (d0.y != 0 && !(a.debug_skip & 1)) {  // warp-uniform; an unused partner slot computes zeros, stores nothing
+                            const uint4 dd[2] = {d0, d1};
+                            double aE[2][KS], aO[2][KS];
+                            uint2 w[2];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const uint32_t oE = *reinterpret_cast<const uint32_t*>(dtab_l + (dd[u].y & 0xFFFFu) * 32u);
-                        const uint32_t oO = *reinterpret_cast<const uint32_t*>(dtab_l + (dd[u].y >> 16) * 32u);
+                            for (int u = 0; u < 2; ++u) {
+                                const uint32_t oE = *reinterpret_cast<const uint32_t*>(dtab_l + (dd[u].y & 0xFFFFu) * 32u);
+                                const uint32_t oO = *reinterpret_cast<const uint32_t*>(dtab_l + (dd[u].y >> 16) * 32u);
 #pragma unroll
-                        for (int s = 0; s < KS; ++s) {
-                            aE[u][s] = *reinterpret_cast<const double*>(ksrc + oE + 32 * s);
-                            aO[u][s] = *reinterpret_cast<const double*>(ksrc + oO + 32 * s);
+                                for (int s = 0; s < KS; ++s) {
+                                    aE[u][s] = *reinterpret_cast<const double*>(ksrc + oE + 32 * s);
+                                    aO[u][s] = *reinterpret_cast<const double*>(ksrc + oO + 32 * s);
+                                }
+                                w[u] = *reinterpret_cast<const uint2*>(sw_l + dd[u].z);
+                            }
+                            double c[2][4];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.0;
+#pragma unroll
+                            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const double bx = __shfl_sync(0xffffffffu, B[st + u][s].x, frag_src);
+                                    const double by = __shfl_sync(0xffffffffu, B[st + u][s].y, frag_src);
+                                    dmma(c[u][0], c[u][1], aE[u][s], bx);
+                                    dmma(c[u][2], c[u][3], aO[u][s], by);
+                                }
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const uint32_t a0 = w[u].x & 0xFFFFu, a1 = w[u].x >> 16, a2 = w[u].y & 0xFFFFu, a3 = w[u].y >> 16;
+                                if (a0 != NOSTORE) *reinterpret_cast<double*>(mb + a0 * 8u) = c[u][0];
+                                if (a1 != NOSTORE) *reinterpret_cast<double*>(mb + a1 * 8u) = c[u][1];
+                                if (a2 != NOSTORE) *reinterpret_cast<double*>(mb + a2 * 8u) = c[u][2];
+                                if (a3 != NOSTORE) *reinterpret_cast<double*>(mb + a3 * 8u) = c[u][3];
+                            }
                         }
-                        w[u] = *reinterpret_cast<const uint2*>(sw_l + dd[u].z);
                     }
-                    double c[2][4];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.0;
-#pragma unroll
-                    for (int s = 0; s < KS; ++s)
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const double bx = __shfl_sync(0xffffffffu, B[st + u][s].x, frag_src);
-                            const double by = __shfl_sync(0xffffffffu, B[st + u][s].y, frag_src);
-                            dmma(c[u][0], c[u][1], aE[u][s], bx);
-                            dmma(c[u][2], c[u][3], aO[u][s], by);
-                        }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const uint32_t a0 = w[u].x & 0xFFFFu, a1 = w[u].x >> 16, a2 = w[u].y & 0xFFFFu, a3 = w[u].y >> 16;
-                        if (a0 != NOSTORE) *reinterpret_cast<double*>(mb + a0 * 8u) = c[u][0];
-                        if (a1 != NOSTORE) *reinterpret_cast<double*>(mb + a1 * 8u) = c[u][1];
-                        if (a2 != NOSTORE) *reinterpret_cast<double*>(mb + a2 * 8u) = c[u][2];
-                        if (a3 != NOSTORE) *reinterpret_cast<double*>(mb + a3 * 8u) = c[u][3];
-                    }
+                    // ---- B fragments of the next stage ------------------------------------------------------------------
+                    if (nxt < nri && !(a.debug_skip & 4)) load_b(npass, xr);
                 }
-            }
-            // ---- B fragments of the next stage --------------------------------------------------------------------------
-            if (nrow < re && !(a.debug_skip & 4)) load_b(npass, xr);
-        }
-        } else {
-        if (have_prev) {
-            // ---- consume the previous stage from the other mailbox: weighted column sums of the groups of this warp ----------
-            unsigned char* mb = mb0 + (par ^ 1u) * mb_bytes;
-            const uint4* cr = crec + cpass * (MMA_WARPS * 8);
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const uint4 hh = cr[g];
-                const ConsRecD h = {hh.x, hh.y, hh.z, hh.w};
-                const unsigned char* src = mb + h.base + lane * 8;
-                const unsigned char* wr = reinterpret_cast<const unsigned char*>(tab.roww) + (h.roww & 0xFFFFFu);
-                const uint32_t npair = (a.debug_skip & 2) ? 0u : h.roww >> 20;
-                double t0 = acc[g], t1 = 0.0;
-                uint32_t r = npair;
-                while (r >= 4) {  // 8 mailbox rows per trip: independent loads first
-                    double v[8];
-                    double2 w2[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        w2[u] = *reinterpret_cast<const double2*>(wr + u * 16);
-                        v[2 * u] = *reinterpret_cast<const double*>(src + u * 512);
-                        v[2 * u + 1] = *reinterpret_cast<const double*>(src + u * 512 + 256);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        t0 = fma(w2[u].x, v[2 * u], t0);
-                        t1 = fma(w2[u].y, v[2 * u + 1], t1);
-                    }
-                    wr += 64, src += 2048, r -= 4;
-                }
-                if (r & 2) {
-                    const double2 wa = *reinterpret_cast<const double2*>(wr), wb = *reinterpret_cast<const double2*>(wr + 16);
-                    const double v0 = *reinterpret_cast<const double*>(src), v1 = *reinterpret_cast<const double*>(src + 256),
-                                 v2 = *reinterpret_cast<const double*>(src + 512), v3 = *reinterpret_cast<const double*>(src + 768);
-                    t0 = fma(wa.x, v0, t0);
-                    t1 = fma(wa.y, v1, t1);
-                    t0 = fma(wb.x, v2, t0);
-                    t1 = fma(wb.y, v3, t1);
-                    wr += 32, src += 1024;
-                }
-                if (r & 1) {
-                    const double2 wa = *reinterpret_cast<const double2*>(wr);
-                    t0 = fma(wa.x, *reinterpret_cast<const double*>(src), t0);
-                    t1 = fma(wa.y, *reinterpret_cast<const double*>(src + 256), t1);
-                }
-                const unsigned char* ex = extra_l + h.extra0;
-                for (uint32_t e = 0; e < h.nextra; ++e) {
-                    const uint32_t word = *reinterpret_cast<const uint32_t*>(ex + e * 128);
-                    t1 = fma(tab.wtab[word >> 16], *reinterpret_cast<const double*>(mb + (word & 0xFFFFu) * 8u), t1);
-                }
-                acc[g] = t0 + t1;
-            }
-            if (a.zero_after_read) {
-                // more than two passes: a buffer serves passes with different layouts, so the entries read here are zeroed
-                // again (after all consumers, incl. the extra lists of other warps, are through)
-                __syncthreads();
+            } else if (have_prev) {
+                // ---- consume the previous stage from the other mailbox: weighted column sums of the groups of this warp ------
+                const int64_t crow = rb + cri * rstep;
+                const bool last = cpass == a.P - 1;
+                uint8_t bm = 0;
+                if (last) bm = a.bmask[crow];  // in flight during the sums
+                unsigned char* mb = mb0 + (par ^ 1u) * mb_bytes;
+                const uint4* cr = crec + cpass * (MMA_WARPS * 8);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const uint4 hh = cr[g];
-                    unsigned char* dst = mb + hh.x + lane * 8;
-                    for (uint32_t r = 0; r < 2 * (hh.y >> 20); ++r) *reinterpret_cast<double*>(dst + r * 256) = 0.0;
-                }
-            }
-            if (cpass == a.P - 1) {
-                const bool bm = a.bmask[crow] != 0;
-                unsigned char* yr = reinterpret_cast<unsigned char*>(a.y + crow * a.ld);
+                    const ConsRecD h = {hh.x, hh.y, hh.z, hh.w};
+                    const unsigned char* src = mb + h.base + lane * 8;
+                    const unsigned char* wr = reinterpret_cast<const unsigned char*>(tab.roww) + (h.roww & 0xFFFFFu);
+                    const uint32_t npair = (a.debug_skip & 2) ? 0u : h.roww >> 20;
+                    double t0 = acc[g], t1 = 0.0;
+                    uint32_t r = npair;
+                    while (r >= 4) {  // 8 mailbox rows per trip: independent loads first
+                        double v[8];
+                        double2 w2[4];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    if (ycol[g] != 0xFFFFFFFFu) *reinterpret_cast<double*>(yr + ycol[g]) = bm ? 0.0 : acc[g];
-                    acc[g] = 0.0;
+                        for (int u = 0; u < 4; ++u) {
+                            w2[u] = *reinterpret_cast<const double2*>(wr + u * 16);
+                            v[2 * u] = *reinterpret_cast<const double*>(src + u * 512);
+                            v[2 * u + 1] = *reinterpret_cast<const double*>(src + u * 512 + 256);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            t0 = fma(w2[u].x, v[2 * u], t0);
+                            t1 = fma(w2[u].y, v[2 * u + 1], t1);
+                        }
+                        wr += 64, src += 2048, r -= 4;
+                    }
+                    if (r & 2) {
+                        const double2 wa = *reinterpret_cast<const double2*>(wr), wb = *reinterpret_cast<const double2*>(wr + 16);
+                        const double v0 = *reinterpret_cast<const double*>(src), v1 = *reinterpret_cast<const double*>(src + 256),
+                                     v2 = *reinterpret_cast<const double*>(src + 512), v3 = *reinterpret_cast<const double*>(src + 768);
+                        t0 = fma(wa.x, v0, t0);
+                        t1 = fma(wa.y, v1, t1);
+                        t0 = fma(wb.x, v2, t0);
+                        t1 = fma(wb.y, v3, t1);
+                        wr += 32, src += 1024;
+                    }
+                    if (r & 1) {
+                        const double2 wa = *reinterpret_cast<const double2*>(wr);
+                        t0 = fma(wa.x, *reinterpret_cast<const double*>(src), t0);
+                        t1 = fma(wa.y, *reinterpret_cast<const double*>(src + 256), t1);
+                    }
+                    const unsigned char* ex = extra_l + h.extra0;
+                    for (uint32_t e = 0; e < h.nextra; ++e) {
+                        const uint32_t word = *reinterpret_cast<const uint32_t*>(ex + e * 128);
+                        t1 = fma(tab.wtab[word >> 16], *reinterpret_cast<const double*>(mb + (word & 0xFFFFu) * 8u), t1);
+                    }
+                    acc[g] = t0 + t1;
+                }
+                if (a.zero_after_read) {
+                    // more than two passes: a buffer serves passes with different layouts, so the entries read here are zeroed
+                    // again (after all consumers, incl. the extra lists of other warps, are through)
+                    __syncthreads();
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const uint4 hh = cr[g];
+                        unsigned char* dst = mb + hh.x + lane * 8;
+                        for (uint32_t r = 0; r < 2 * (hh.y >> 20); ++r) *reinterpret_cast<double*>(dst + r * 256) = 0.0;
+                    }
+                }
+                if (last) {
+                    unsigned char* yr = reinterpret_cast<unsigned char*>(a.y + crow * a.ld);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        if (ycol[g] != 0xFFFFFFFFu) *reinterpret_cast<double*>(yr + ycol[g]) = bm ? 0.0 : acc[g];
+                        acc[g] = 0.0;
+                    }
                 }
             }
         }
-        }
-        }
-        cp_async_wait_all();
+        cp_async_commit();
+        cp_async_wait_1();  // everything but the copies issued in this stage has landed
         __syncthreads();
         have_prev = produce;
         cpass = pass;
-        crow = row;
+        cri = ri;
         par ^= 1u;
-        if (produce && ++pass == a.P) pass = 0, row += rstep, kb ^= 1;
+        if (produce && ++pass == a.P) pass = 0, ++ri;
     }
 }
 
@@ -1095,6 +1143,7 @@ int apply_mma_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
     a.bmask = ctx->d_bmask;
     a.blob = P->d_blob;
     a.zero_row = P->d_zero;
+    a.rowmeta = P->d_rowmeta;
     a.nnz = ctx->nnz;
     a.ld = ctx->ld;
     a.r0 = r0;

@@ -67,53 +67,6 @@ __global__ void k_lds(double* out, long long* cyc) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-// ---- C: the dense-unit inner loop: K operand by broadcast loads, X in registers, NM modes per lane share the K operand.
-//         LD128: 0 = 7 LDS.64 per unit, 1 = 3 LDS.128 + 1 LDS.64
-template <int NM, int LD128>
-__global__ void k_unit(double* out, long long* cyc, const double* xin) {
-  extern __shared__ double sm[];
-  for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = 1.0 / (1 + i);
-  __syncthreads();
-  double x[NM][7];
-#pragma unroll
-  for (int s = 0; s < NM; s++)
-#pragma unroll
-    for (int k = 0; k < 7; k++) x[s][k] = xin[(threadIdx.x * NM + s) * 7 + k];
-  double acc[NM];
-#pragma unroll
-  for (int s = 0; s < NM; s++) acc[s] = 0;
-  unsigned base = smem_u32(sm);
-  long long t0 = clock64();
-  for (int i = 0; i < ITERS / 4; i++) {
-#pragma unroll
-    for (int m = 0; m < 21; m++) {
-      double kk[8];
-      unsigned a = base + m * 64;
-      if (LD128) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(kk[2 * q]), "=d"(kk[2 * q + 1]) : "r"(a + q * 16));
-      } else {
-#pragma unroll
-        for (int q = 0; q < 7; q++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(kk[q]) : "r"(a + q * 8));
-      }
-#pragma unroll
-      for (int s = 0; s < NM; s++) {
-        double t = kk[0] * x[s][0];
-#pragma unroll
-        for (int k = 1; k < 7; k++) t = fma(kk[k], x[s][k], t);
-        acc[s] += t;
-      }
-    }
-  }
-  long long t1 = clock64();
-  __syncthreads();
-  double r = 0;
-#pragma unroll
-  for (int s = 0; s < NM; s++) r += acc[s];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
-  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
-}
-
 // ---- D: DMMA m8n8k4, NA independent accumulators per warp
 template <int NA>
 __global__ void k_dmma(double* out, long long* cyc, double a, double b) {
@@ -297,13 +250,6 @@ int main() {
     RUN("STS.64 + LDS.64 stride 1 (pairs)", 4.0 * ITERS / 32, "pair", (k_xchg<<<nsm, nw * 32, 131072>>>(out, cyc)));
     RUN("SHFL 64-bit", 4.0 * ITERS / 32, "shfl64", (k_shfl<<<nsm, nw * 32>>>(out, cyc)));
     RUN("4 SHFL.32 + 2 LDS.64 stride 1 (iterations)", 1.0 * ITERS / 32, "iter", (k_shfl_lds<<<nsm, nw * 32, smem>>>(out, cyc)));
-  }
-  for (int nw : {8, 16}) {
-    RUN("unit: 7 LDS.64 bcast + 7 DFMA, 1 mode/lane", 21.0 * 7 * 1 * (ITERS / 4), "FMA", (k_unit<1, 0><<<nsm, nw * 32, smem>>>(out, cyc, xin)));
-    RUN("unit: 4 LDS.128 bcast + 7 DFMA, 1 mode/lane", 21.0 * 7 * 1 * (ITERS / 4), "FMA", (k_unit<1, 1><<<nsm, nw * 32, smem>>>(out, cyc, xin)));
-    RUN("unit: 7 LDS.64 bcast + 14 DFMA, 2 modes/lane", 21.0 * 7 * 2 * (ITERS / 4), "FMA", (k_unit<2, 0><<<nsm, nw * 32, smem>>>(out, cyc, xin)));
-    RUN("unit: 4 LDS.128 bcast + 14 DFMA, 2 modes/lane", 21.0 * 7 * 2 * (ITERS / 4), "FMA", (k_unit<2, 1><<<nsm, nw * 32, smem>>>(out, cyc, xin)));
-    RUN("unit: 4 LDS.128 bcast + 28 DFMA, 4 modes/lane", 21.0 * 7 * 4 * (ITERS / 4), "FMA", (k_unit<4, 1><<<nsm, nw * 32, smem>>>(out, cyc, xin)));
   }
   return 0;
 }
