@@ -28,10 +28,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NX = 1024
+NX = int(os.environ.get("ASGFEM_BENCH_NX", 1024))  # test hook: smaller mesh for a quick functional check of the script
 N_MODES = 2000
 M_KLE = 20
 SEED = 20240
+WORKLOAD = ("configs[3]: synthetic 1024x1024 P1 mesh (1,048,576 dofs) x 2000 graded-lex Legendre multi-indices, "
+            "M=20 cosinus KLE")
+# fp64 FMA rate measured on this pool's B200 with tools/ubench_fp64.cu (profiles/r02_ubench_fp64.txt): 58.4 DFMA per clock
+# and SM with 16-32 resident warps (DMMA m8n8k4: 64.0, same pipe), 148 SMs at the 1965 MHz the bench runs at
+FP64_FMA_PER_CLK_SM = 58.4
 
 
 def measured_peaks():
@@ -241,6 +246,10 @@ def run_gpu(args):
         kms = float(np.mean(kernel_ms))
         bytes_alg = algorithmic_bytes(n_owned, N_MODES, nnz, M_KLE)
         achieved = bytes_alg / (kms * 1e-3) / 1e9
+        flops = 2 * nnz * (N_MODES + 2 * 5266)
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp64_peak = FP64_FMA_PER_CLK_SM * 2 * 148 * sm_mhz * 1e6
+        t_fp64_ms = flops / fp64_peak * 1e3
         traffic = None
         tp = os.path.join(ROOT, "profiles", "apply_traffic.json")
         if os.path.exists(tp):
@@ -249,10 +258,10 @@ def run_gpu(args):
             "metric": "SGFE matvec GDoF/s (dofs x modes)", "value": round(value, 3), "unit": "GDoF/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[3]: synthetic 1024x1024 P1 mesh (1,048,576 dofs) x 2000 graded-lex "
-                                   "Legendre multi-indices, M=20 cosinus KLE, K_m assembled on device"
-                                   + (f"; weak scaling: one such strip per rank of a 1024x{1024 * world} mesh, "
-                                      "halo rows exchanged per step (NCCL send/recv) behind the interior rows" if world > 1 else ""),
+            "config": {"workload": WORKLOAD,
+                       "assembly": "K_m assembled on the device",
+                       "multi_gpu": (f"weak scaling: one such strip per rank of a 1024x{1024 * world} mesh, halo rows "
+                                     "exchanged per step (NCCL send/recv) behind the interior rows" if world > 1 else None),
                        "n_dofs_per_gpu": n_owned, "n_multiindices": N_MODES, "kle_terms": M_KLE, "nnz": nnz,
                        "kernel_variant": args.variant or "auto",
                        "l2_policy": "inputs (16.8 GB per vector) far larger than the 126 MB L2; no flush needed",
@@ -260,7 +269,11 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": round(kms, 4), "algorithmic_bytes": bytes_alg,
-                         "flops": 2 * nnz * (N_MODES + 2 * 5266)},
+                         "flops": flops, "t_hbm_ms": round(bytes_alg / peak / 1e6, 3), "t_fp64_ms": round(t_fp64_ms, 3),
+                         "fp64_peak_tflops_measured": round(fp64_peak / 1e12, 2),
+                         "frac_of_max_bound": round(max(bytes_alg / peak / 1e6, t_fp64_ms) / kms, 4),
+                         "note": "the path sits on the fp64 / HBM ridge: t_hbm = algorithmic bytes / measured copy "
+                                 "bandwidth, t_fp64 = necessary flops / measured DFMA rate (tools/ubench_fp64.cu)"},
             "gpu_launches": args.steps * (1 + (2 + 2 * len(halo) if world > 1 else 0)),
             "clocks": clocks,
         }
@@ -386,7 +399,16 @@ def run_gpu(args):
         except Exception as e:  # pragma: no cover
             out["logprimal"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_reference(A, ctx, fes, budget_s=15.0)
+        prob = CpuProblem.from_context(ctx, fes)
+        out["cpu_baseline"] = cpu_reference(prob, budget_s=12.0)
+        one = cpu_reference(prob, budget_s=6.0, nthreads=1)
+        out["cpu_baseline"]["value_1thread"] = one["value"]
+        out["cpu_baseline"]["sample_1thread"] = one["sample"]
+        if "pcg" in out and "iterations" in out["pcg"]:
+            try:
+                out["pcg"]["cpu_solve"] = cpu_pcg_estimate(prob, out["pcg"]["iterations"])
+            except Exception as e:  # pragma: no cover
+                out["pcg"]["cpu_solve"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(out))
     ctx.close()
@@ -397,20 +419,50 @@ def run_gpu(args):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle/cpu_ref.c) on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference(A, ctx, fes, budget_s=15.0, steps=1, warmup=0):
-    """Times oracle/cpu_ref.c (C restatement of mul!, N + nnz(G) CSC sweeps) on a column sample of the workload.
-    K_m values come from the device assembly (or are assembled here by a throw-away context)."""
-    lib_path = os.path.join(ROOT, "oracle", "libcpu_ref.so")
-    lib = C.CDLL(lib_path)
-    nthreads = os.cpu_count() or 1
-    n = fes.ndofs
-    colptr, rowval = ctx.pattern_csc()
-    colptr = np.ascontiguousarray(colptr - 1, dtype=np.int64)
-    rowval = np.ascontiguousarray(rowval - 1, dtype=np.int32)
+class CpuProblem:
+    """Host arrays of the workload for the CPU arm: shared CSC pattern (0-based), (M+1) value planes, boundary dofs."""
+
+    def __init__(self, n, colptr, rowval, vals, bdofs):
+        self.n, self.colptr, self.rowval, self.vals, self.bdofs = n, colptr, rowval, vals, bdofs
+
+    @staticmethod
+    def from_context(ctx, fes):
+        colptr, rowval = ctx.pattern_csc()
+        vals = np.empty((M_KLE + 1, len(rowval)))
+        for m in range(M_KLE + 1):
+            vals[m] = ctx.get_stiffness(m)
+        return CpuProblem(fes.ndofs, np.ascontiguousarray(colptr - 1, dtype=np.int64),
+                          np.ascontiguousarray(rowval - 1, dtype=np.int32), vals, np.ascontiguousarray(fes.bdofs, dtype=np.int64))
+
+    @staticmethod
+    def from_oracle():
+        """Assembles K_0..K_M with the oracle's CPU finite-element code (oracle/fem.py): nothing of the product is loaded."""
+        import scipy.sparse as sp
+        from oracle import problem as oproblem
+        P = oproblem.synthetic(NX, 1, 4, M_KLE)  # the matrices do not depend on the number of modes
+        A0 = sp.csc_matrix(P.A0)
+        A0.sort_indices()
+        vals = np.empty((M_KLE + 1, A0.nnz))
+        vals[0] = A0.data
+        for m, Am in enumerate(P.Am, start=1):
+            B = sp.csc_matrix(Am)
+            B.sort_indices()
+            if B.nnz != A0.nnz or not np.array_equal(B.indices, A0.indices):  # exact zeros dropped: onto the pattern of K_0
+                B = sp.csc_matrix(B + sp.csc_matrix((np.zeros(A0.nnz), A0.indices, A0.indptr), shape=A0.shape))
+                B.sort_indices()
+                assert np.array_equal(B.indptr, A0.indptr) and np.array_equal(B.indices, A0.indices)
+            vals[m] = B.data
+        return CpuProblem(P.n, A0.indptr.astype(np.int64), A0.indices.astype(np.int32), vals,
+                          np.ascontiguousarray(P.bdofs, dtype=np.int64))
+
+
+def cpu_reference(prob, budget_s=15.0, steps=1, warmup=0, nthreads=None, ns_fixed=None):
+    """Times oracle/cpu_ref.c (C restatement of mul!, N + nnz(G) CSC sweeps) on a column sample of the workload: every
+    step applies the operator restricted to the first Ns multi-indices on the full mesh."""
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "libcpu_ref.so"))
+    nthreads = nthreads or len(os.sched_getaffinity(0)) or 1
+    n, colptr, rowval, vals = prob.n, prob.colptr, prob.rowval, prob.vals
     nnz = len(rowval)
-    vals = np.empty((M_KLE + 1, nnz))
-    for m in range(M_KLE + 1):
-        vals[m] = ctx.get_stiffness(m)
     from oracle import multiindices as omi
     from oracle import polynomials as opoly
     full = omi.graded_lex_multiindices(M_KLE, N_MODES)
@@ -436,24 +488,28 @@ def cpu_reference(A, ctx, fes, budget_s=15.0, steps=1, warmup=0):
         return (np.array(cptr, dtype=np.int32), np.array(cm, dtype=np.int32), np.array(cnu, dtype=np.int32),
                 np.array(cg, dtype=np.float64))
 
-    bd = np.ascontiguousarray(fes.bdofs, dtype=np.int64)
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    bd = prob.bdofs
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    state = {}
 
     def run(Ns):
-        cptr, cm, cnu, cg = coupling(Ns)
-        x = np.random.default_rng(0).uniform(-1, 1, n * Ns)
-        y = np.empty_like(x)
+        if state.get("Ns") != Ns:
+            state["Ns"], state["c"] = Ns, coupling(Ns)
+            state["x"] = np.random.default_rng(0).uniform(-1, 1, n * Ns)
+            state["y"] = np.empty(n * Ns)
+        cptr, cm, cnu, cg = state["c"]
         t0 = time.perf_counter()
         lib.cpu_ref_mul(C.c_int64(n), C.c_int64(Ns), C.c_int64(nnz), p(colptr), p(rowval), p(vals), p(cptr), p(cm),
-                        p(cnu), p(cg), C.c_int64(len(bd)), p(bd), p(x), p(y), C.c_int(nthreads))
+                        p(cnu), p(cg), C.c_int64(len(bd)), p(bd), p(state["x"]), p(state["y"]), C.c_int(nthreads))
         return time.perf_counter() - t0, Ns + len(cm)
 
-    t_probe, sw_probe = run(max(2 * nthreads, 16))  # probe: a handful of modes
-    t_probe2, sw_probe2 = run(200)                  # second probe at a representative density of couplings
-    per_sweep = t_probe2 / sw_probe2
-    target_sweeps = budget_s / per_sweep
-    full_sweeps_per_mode = sweeps_full / N_MODES
-    Ns = int(np.clip(target_sweeps / full_sweeps_per_mode, 64, N_MODES))
+    if ns_fixed:
+        Ns = ns_fixed
+    else:
+        run(max(2 * nthreads, 16))                     # probe: a handful of modes (touches the matrices)
+        t_probe2, sw_probe2 = run(200 if nthreads > 1 else 24)  # at a representative density of couplings
+        per_sweep = t_probe2 / sw_probe2
+        Ns = int(np.clip(budget_s / per_sweep / (sweeps_full / N_MODES), 16, N_MODES))
     ts = []
     for k in range(warmup + steps):
         t, sweeps = run(Ns)
@@ -464,32 +520,70 @@ def cpu_reference(A, ctx, fes, budget_s=15.0, steps=1, warmup=0):
     t_full_equiv = t / sweeps * sweeps_full
     value = n * N_MODES / t_full_equiv / 1e9
     return {"value": round(value, 4), "unit": "GDoF/s", "cores": nthreads, "kind": "port",
-            "sample": f"first {Ns} of the 2000 multi-indices on the full 1,048,576-dof mesh: {sweeps} CSC sweeps in "
-                      f"{t:.2f} s with {nthreads} OpenMP threads, scaled linearly to the {sweeps_full} sweeps of one "
-                      "full application (reference loop solvers_poisson_primal.jl:101-122; the reference itself is "
-                      "single-threaded Julia, not installed here)",
-            "seconds_per_full_apply_equiv": round(t_full_equiv, 2)}
+            "sample": f"first {Ns} of the 2000 multi-indices on the full {n:,}-dof mesh: {sweeps} CSC sweeps per step in "
+                      f"{t:.2f} s with {nthreads} OpenMP thread(s), {len(ts)} timed step(s), scaled linearly to the "
+                      f"{sweeps_full} sweeps of one full application (reference loop solvers_poisson_primal.jl:101-122; the "
+                      "reference itself is single-threaded Julia, not installed here)",
+            "seconds_per_full_apply_equiv": round(t_full_equiv, 2), "ns": Ns, "seconds_per_step": round(t, 3)}
+
+
+def cpu_pcg_estimate(prob, iterations, budget_rhs=6):
+    """CPU time of the reference solve path per Krylov iteration, single-threaded as the reference is: the mean
+    preconditioner is one sparse direct solve with the factorised K_0 per multi-index (ldiv!, solvers_poisson_primal.jl:46-78;
+    the reference factorises with UMFPACK, here scipy's SuperLU), the operator is the CSC sweep loop of cpu_ref.c.  Timed on a
+    sample of right-hand sides and scaled to the 2000 modes; returns None if scipy is missing."""
+    try:
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+    except Exception:
+        return None
+    n = prob.n
+    K0 = sp.csc_matrix((prob.vals[0], prob.rowval, prob.colptr), shape=(n, n))
+    keep = np.ones(n, dtype=bool)
+    keep[prob.bdofs] = False
+    idx = np.where(keep)[0]
+    Kii = K0[idx][:, idx].tocsc()
+    t0 = time.perf_counter()
+    lu = spla.splu(Kii, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options={"SymmetricMode": True})
+    t_fac = time.perf_counter() - t0
+    rhs = np.random.default_rng(1).standard_normal((len(idx), budget_rhs))
+    t0 = time.perf_counter()
+    lu.solve(rhs)
+    t_solve = (time.perf_counter() - t0) / budget_rhs
+    op1 = cpu_reference(prob, budget_s=6.0, nthreads=1)
+    per_it = t_solve * N_MODES + op1["seconds_per_full_apply_equiv"]
+    return {"factor_s": round(t_fac, 2), "precond_s_per_mode": round(t_solve, 4),
+            "precond_s_per_iteration": round(t_solve * N_MODES, 1),
+            "operator_s_per_iteration": op1["seconds_per_full_apply_equiv"],
+            "seconds_per_iteration": round(per_it, 1), "iterations": int(iterations),
+            "solve_s_equiv": round(t_fac + per_it * iterations, 1), "cores": 1,
+            "sample": f"SuperLU factorisation of the Dirichlet-reduced K_0 ({len(idx)} dofs) and {budget_rhs} triangular solve pairs, "
+                      f"operator on {op1['ns']} modes; per-iteration cost scaled to 2000 modes and multiplied with the iteration "
+                      "count of the device solve (same preconditioner, same stopping rule)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    import asgfem_b200 as A
     try:
-        ctx, fes, n_owned, _ = build_local_problem(A, 0, 1)  # K_m values come from the device assembly
+        prob = CpuProblem.from_oracle()  # CPU assembly: the product library is not loaded in this arm
     except Exception as e:
         print(json.dumps({"impl": "reference", "unavailable": f"cannot assemble inputs: {str(e)[:150]}"}))
         return
-    res = cpu_reference(A, ctx, fes, budget_s=12.0, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
-    ctx.close()
+    # every step is the same bounded sample; sized so that steps + warmup fit a few minutes
+    budget = max(0.5, min(8.0, 150.0 / max(args.steps + args.warmup, 1)))
+    res = cpu_reference(prob, budget_s=budget, steps=args.steps, warmup=args.warmup)
+    res1 = cpu_reference(prob, budget_s=6.0, steps=1, warmup=0, nthreads=1)
+    res["value_1thread"] = res1["value"]
+    res["sample_1thread"] = res1["sample"]
     world = int(os.environ.get("WORLD_SIZE", 1))
     out = {"impl": "reference", "metric": "SGFE matvec GDoF/s (dofs x modes)", "value": res["value"], "unit": "GDoF/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(res["seconds_per_full_apply_equiv"] * 1e3, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "configs[3]: synthetic 1024x1024 P1 mesh x 2000 graded-lex Legendre multi-indices, "
-                                  "M=20 (CPU arm: bounded column sample, see cpu_baseline.sample)"},
+           "config": {"workload": WORKLOAD, "assembly": "K_m assembled on the host (oracle/fem.py)",
+                      "sample_ms_per_step": round(res["seconds_per_step"] * 1e3, 1)},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -501,7 +595,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--variant", type=int, default=0, help="operator kernel: 0 auto, 1 gather, 2 tiled")
+    ap.add_argument("--variant", type=int, default=0,
+                    help="operator kernel: 0 auto, 1 reference-order gather, 7 packed mode-stationary DFMA, 8 block MMA")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcg", action="store_true")

@@ -105,6 +105,34 @@ def test_apply_matches_oracle(c1, mid, variant):
         ctx.close()
 
 
+@pytest.mark.parametrize("nx,order,N,M", [(33, 1, 2000, 20), (17, 1, 2048, 40), (9, 2, 300, 10), (13, 2, 2000, 20)])
+def test_apply_matches_oracle_on_bench_sets(nx, order, N, M):
+    """The benchmark's own multi-index set (2000 graded-lex Legendre modes, M = 20) and the shapes next to it (2048 modes /
+    M = 40; P2 rows with up to 19 entries) against the ORACLE (SystemPrimal.mul = mul!, solvers_poisson_primal.jl:86-124),
+    not against another CUDA kernel: every kernel that accepts the shape must agree to 1e-12."""
+    P = oproblem.synthetic(nx, order, N, M)
+    S = osolver.SystemPrimal(P.A0, P.Am, P.G, P.bdofs, P.N)
+    x = np.random.default_rng(11).standard_normal(P.n * P.N)
+    ref = S.mul(x)
+    ctx = make_ctx(P)
+    ran = []
+    from asgfem_b200 import _lib
+    for variant in (0, 1, 7, 8):
+        ctx.set_apply_variant(variant)
+        ctx.vec_upload(0, x)
+        try:
+            ctx.apply(0, 1)
+        except _lib.AsgfemError as e:  # a kernel may decline a shape; it must say so
+            assert variant in (7, 8) and "not available" in str(e)
+            continue
+        ran.append(variant)
+        got = ctx.vec_download(1)
+        assert relerr(got, ref) < TOL_APPLY
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    assert 0 in ran and 1 in ran
+    ctx.close()
+
+
 @pytest.mark.parametrize("variant", [0, 1, 7, 8])
 def test_apply_host_pipelined_row_blocks(c1, mid, variant, monkeypatch):
     """The mul! seam overlaps upload / operator / download block by block; small blocks force the multi-block
