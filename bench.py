@@ -145,15 +145,21 @@ def build_local_problem(A, rank, world):
     ctx.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
     xref, w = A.quadrature_rule(2)
     ctx.assemble_stiffness(M_KLE, xref, w)
-    ctx.set_bdofs(bdofs + 1)
     if world > 1:
+        # halo rows are not part of this rank's system: flagged like Dirichlet rows, so that the rank-local mean
+        # preconditioner is the exact inverse of the owned interior block (block-Jacobi) and work vectors stay zero there
+        ctx.set_bdofs(np.union1d(bdofs, np.arange(n_owned, n_ext)) + 1)
         ctx.set_owned_rows(n_owned)
+    else:
+        ctx.set_bdofs(bdofs + 1)
     halo = {}
     if y_lo > 0:  # lower neighbour: send my first owned row, receive its last owned row into my lower halo
         halo[rank - 1] = (np.arange(0, NX) + 1, n_owned + np.arange(0, NX) + 1)
     if y_hi < ny_tot:
         off = n_owned + (NX if y_lo > 0 else 0)
         halo[rank + 1] = (np.arange(n_owned - NX, n_owned) + 1, off + np.arange(0, NX) + 1)
+    # owned rows [interior0, interior1) reference no halo column
+    ctx.interior = (NX if y_lo > 0 else 0, n_owned - NX if y_hi < ny_tot else n_owned)
     return ctx, fes, n_owned, halo
 
 
@@ -179,36 +185,32 @@ def run_gpu(args):
     nnz = len(ctx.pattern_csc()[1])
     t_setup = time.time() - t_setup
 
-    bufs = {}
+    sym = None
     if world > 1:
-        for nb in halo:
-            bufs[nb] = (torch.empty(NX * N_MODES, dtype=torch.float64, device="cuda"),
-                        torch.empty(NX * N_MODES, dtype=torch.float64, device="cuda"))
+        # NCCL inside the library: one C call per application (pack -> ncclSend/Recv -> interior rows -> unpack -> rows
+        # along the cuts), inner products all-reduced
+        ids = [A.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+        ctx.set_halo({q: s_ - 1 for q, (s_, r_) in halo.items()}, {q: r_ - 1 for q, (s_, r_) in halo.items()}, *ctx.interior)
+        # size-independent check of the sharded operator: it is symmetric on vectors that vanish on the Dirichlet rows,
+        # <A u, v> = <u, A v> with u = A x1, v = A x2 - any wrong or missing halo row breaks this
+        ctx.vec_alloc(4)
+        ctx.vec_fill_random(0, SEED + 100 + rank)
+        ctx.vec_fill_random(2, SEED + 200 + rank)
+        ctx.apply(0, 1)
+        ctx.apply(2, 3)
+        ctx.apply(1, 0)
+        ctx.apply(3, 2)
+        d1, d2 = ctx.vec_dot_global(0, 3), ctx.vec_dot_global(1, 2)
+        sym = abs(d1 - d2) / max(abs(d1), 1e-300)
+        ctx.vec_alloc(2)
+        ctx.vec_fill_random(0, SEED + rank)
 
     def step():
-        """One operator application.  N > 1: the rows of the first / last owned mesh line reference halo columns; all other
-        rows are applied while the halo exchange (NCCL send/recv on torch's stream) is in flight."""
-        if world == 1:
-            ctx.apply(0, 1)
-            return ctx.last_apply_ms()
-        ops = []
-        for nb, (send_rows, recv_rows) in halo.items():
-            sb, rb = bufs[nb]
-            ctx.pack_rows(0, send_rows, sb.data_ptr())
-            ops.append(dist.P2POp(dist.isend, sb, nb))
-            ops.append(dist.P2POp(dist.irecv, rb, nb))
-        works = dist.batch_isend_irecv(ops)
-        ctx.apply_rows(0, 1, NX, n_owned - NX)  # interior rows: owned columns only
-        ms = ctx.last_apply_ms()
-        for w in works:
-            w.wait()
-        torch.cuda.synchronize()
-        for nb, (send_rows, recv_rows) in halo.items():
-            ctx.unpack_rows(0, recv_rows, bufs[nb][1].data_ptr())
-        ctx.apply_rows(0, 1, 0, NX)
-        ms += ctx.last_apply_ms()
-        ctx.apply_rows(0, 1, n_owned - NX, n_owned)
-        return ms + ctx.last_apply_ms()
+        """One operator application (N > 1: of the row shard, halo exchange overlapped with the interior rows)."""
+        ctx.apply(0, 1)
+        return ctx.last_apply_ms()
 
     for _ in range(args.warmup):
         step()
@@ -261,7 +263,9 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD,
                        "assembly": "K_m assembled on the device",
                        "multi_gpu": (f"weak scaling: one such strip per rank of a 1024x{1024 * world} mesh, halo rows "
-                                     "exchanged per step (NCCL send/recv) behind the interior rows" if world > 1 else None),
+                                     "exchanged per step inside the library (ncclSend/ncclRecv on a communication stream) "
+                                     "behind the interior rows" if world > 1 else None),
+                       "sharded_operator_symmetry_defect": sym,
                        "n_dofs_per_gpu": n_owned, "n_multiindices": N_MODES, "kle_terms": M_KLE, "nnz": nnz,
                        "kernel_variant": args.variant or "auto",
                        "l2_policy": "inputs (16.8 GB per vector) far larger than the 126 MB L2; no flush needed",
@@ -274,7 +278,7 @@ def run_gpu(args):
                          "frac_of_max_bound": round(max(bytes_alg / peak / 1e6, t_fp64_ms) / kms, 4),
                          "note": "the path sits on the fp64 / HBM ridge: t_hbm = algorithmic bytes / measured copy "
                                  "bandwidth, t_fp64 = necessary flops / measured DFMA rate (tools/ubench_fp64.cu)"},
-            "gpu_launches": args.steps * (1 + (2 + 2 * len(halo) if world > 1 else 0)),
+            "gpu_launches": args.steps * (1 + (2 + len(halo) if world > 1 else 0)),
             "clocks": clocks,
         }
     # ---- end-to-end leg through the host-buffer seam (mul! on host vectors), N = 1 only ------------------
@@ -309,6 +313,35 @@ def run_gpu(args):
         out["e2e"] = {"value": None, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                       "note": "end-to-end leg is measured at N=1 only"}
     # ---- PCG solve time (second half of the BASELINE metric): f = 1, zero start, atol = rtol = 1e-14 -------------
+    if world > 1 and not args.no_pcg:
+        # sharded solve: rank-local mean preconditioner (block-Jacobi over the strips), all-reduced inner products
+        try:
+            t0 = time.perf_counter()
+            ctx.precond_setup()
+            t_fac = time.perf_counter() - t0
+            ctx.vec_alloc(1)
+            ctx.vec_zero(0)
+            b0 = fes.rhs()
+            b0[n_owned:] = 0.0
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            st = ctx.pcg(b0, 0, 1e-14, 1e-10, 300)
+            torch.cuda.synchronize()
+            t_solve = time.perf_counter() - t0
+            t = torch.tensor([t_solve], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                out["pcg"] = {"solve_s": round(float(t.item()), 3), "iterations": int(st["niter"]), "solved": bool(st["solved"]),
+                              "factor_s_host": round(t_fac, 2),
+                              "ms_per_iteration": round(st["ms_iterations"] / max(st["niter"], 1), 2),
+                              "ms_operator_total": round(st["ms_apply"], 1), "ms_preconditioner_total": round(st["ms_precond"], 1),
+                              "rtol": 1e-10,
+                              "note": "sharded PCG inside the library: block-Jacobi mean preconditioner (every rank factorises "
+                                      "its strip of K_0), halo exchange + all-reduce over NCCL; max over ranks"}
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                out["pcg"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_pcg:
         try:
             t0 = time.perf_counter()
@@ -326,6 +359,23 @@ def run_gpu(args):
                           "ms_operator_total": round(st["ms_apply"], 1), "ms_preconditioner_total": round(st["ms_precond"], 1),
                           "residual": st["residual"],
                           "note": "mean-preconditioned CG on the device (solve_primal! seam), K_0 factorised once on the host"}
+            # end to end through the reference-shaped seam: solve_primal!(sol, ...) with HOST vectors - factorisation of K_0,
+            # upload of the warm start (16.8 GB), PCG, download of the solution, all inside the timed call
+            try:
+                ctx.set_bdofs(fes.bdofs + 1)  # drops the factorisation: the call below pays for it again
+                ctx.vec_alloc(1)
+                solh = torch.zeros(n_local * N_MODES, dtype=torch.float64, pin_memory=True)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                st2 = ctx.solve_primal_host(solh.numpy(), b0, 1e-14, 1e-14, 500)
+                t_e2e = time.perf_counter() - t0
+                out["pcg"]["e2e_solve"] = {"seconds": round(t_e2e, 2), "iterations": int(st2["niter"]), "solved": bool(st2["solved"]),
+                                           "h2d_bytes": 8 * n_local * N_MODES, "d2h_bytes": 8 * n_local * N_MODES,
+                                           "path": "asgfem_solve_primal_host: host Cholesky of K_0 + H2D of sol + device PCG + D2H of "
+                                                   "sol (pinned host vector in the reference layout)"}
+                del solh
+            except Exception as e:  # pragma: no cover
+                out["pcg"]["e2e_solve"] = {"error": str(e)[:200]}
         except Exception as e:  # pragma: no cover
             out["pcg"] = {"error": str(e)[:200]}
     # ---- residual estimator (second half of the hot path, src/estimate.jl:260-418) on a configs[1]-like level -------

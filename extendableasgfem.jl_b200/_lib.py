@@ -73,6 +73,11 @@ PROTOTYPES = {
     "asgfem_pack_rows": (c_i32, [vp, c_i32, c_i64, vp, vp]),
     "asgfem_unpack_rows": (c_i32, [vp, c_i32, c_i64, vp, vp]),
     "asgfem_vec_dot_owned": (c_i32, [vp, c_i32, c_i32, P(c_f64)]),
+    "asgfem_comm_unique_id": (c_i32, [vp]),
+    "asgfem_comm_init": (c_i32, [vp, c_i32, c_i32, vp]),
+    "asgfem_comm_destroy": (c_i32, [vp]),
+    "asgfem_set_halo": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp, c_i64, c_i64]),
+    "asgfem_vec_dot_global": (c_i32, [vp, c_i32, c_i32, P(c_f64)]),
 }
 
 _lib = None

@@ -164,6 +164,42 @@ class Context:
         self._ck(self.lib.asgfem_vec_dot_owned(self.h, a, b, C.byref(out)))
         return out.value
 
+    def vec_dot_global(self, a, b):
+        out = C.c_double()
+        self._ck(self.lib.asgfem_vec_dot_global(self.h, a, b, C.byref(out)))
+        return out.value
+
+    # ---- NCCL inside the library (one process per GPU) ----------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (rank 0 creates it, the host layer broadcasts it)."""
+        lib = _lib.load()
+        buf = (C.c_char * 128)()
+        rc = lib.asgfem_comm_unique_id(buf)
+        if rc != 0:
+            raise _lib.AsgfemError(rc, lib.asgfem_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, uid):
+        self._ck(self.lib.asgfem_comm_init(self.h, nranks, rank, C.c_char_p(uid)))
+
+    def comm_destroy(self):
+        self._ck(self.lib.asgfem_comm_destroy(self.h))
+
+    def set_halo(self, send, recv, interior0, interior1):
+        """send / recv: dict neighbour rank -> 0-based local row ids (owned rows to send, halo rows to fill)."""
+        ranks = sorted(set(send) | set(recv))
+        sp, rp, srows, rrows = [0], [0], [], []
+        for q in ranks:
+            srows.extend(int(r) + 1 for r in send.get(q, []))
+            rrows.extend(int(r) + 1 for r in recv.get(q, []))
+            sp.append(len(srows))
+            rp.append(len(rrows))
+        a = lambda v, t: np.ascontiguousarray(np.array(v, dtype=t))  # noqa: E731
+        rk, spa, rpa, sra, rra = a(ranks, np.int32), a(sp, np.int64), a(rp, np.int64), a(srows, np.int64), a(rrows, np.int64)
+        self._ck(self.lib.asgfem_set_halo(self.h, len(ranks), rk.ctypes.data, spa.ctypes.data, sra.ctypes.data, rpa.ctypes.data,
+                                          rra.ctypes.data, int(interior0), int(interior1)))
+
     def vec_axpy(self, alpha, x, y):
         self._ck(self.lib.asgfem_vec_axpy(self.h, alpha, x, y))
 

@@ -60,6 +60,7 @@ extern "C" int asgfem_destroy(asgfem_ctx* ctx) {
     apply_free_plan(ctx);
     apply_mma_free(ctx);
     precond_free(ctx);
+    dist_free(ctx);
     free_vec_storage(ctx);
     void* ptrs[] = {ctx->d_rowptr, ctx->d_col,  ctx->d_vals,      ctx->d_bmask,    ctx->d_cptr,  ctx->d_cm,
                     ctx->d_cnu,    ctx->d_cg,   ctx->d_stage,     ctx->d_partial,  ctx->d_coords, ctx->d_cellnodes,
@@ -589,6 +590,24 @@ extern "C" int asgfem_apply(asgfem_ctx* ctx, int32_t sx, int32_t sy) {
     if (set_device(ctx)) return ASGFEM_ECUDA;
     int rc = ensure_ready_for_apply(ctx);
     if (rc) return rc;
+    if (dist_active(ctx)) {
+        // row-sharded operation: halo exchange overlapped with the rows that need no halo column (dist.cu)
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ASG_CUDA(ctx, cudaEventCreate(&e0));
+        ASG_CUDA(ctx, cudaEventCreate(&e1));
+        ASG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        rc = dist_apply(ctx, ctx->slots[sx], ctx->slots[sy]);
+        if (!rc) {
+            cudaEventRecord(e1, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            ctx->last_apply_ms = ms;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return rc;
+    }
     rc = apply_launch(ctx, ctx->slots[sx], ctx->slots[sy]);
     if (rc) return rc;
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -827,6 +846,46 @@ extern "C" int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, i
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return estimate_poisson_primal(ctx, ctx->slots[slot_u], N_ext, M_ext, mi_ext, nq, xref, w, f_at_qp, nqf, sf, wf,
                                    eta4cell, eta4modes);
+}
+
+// ---- multi-GPU: NCCL inside the library ------------------------------------------------------------
+extern "C" int asgfem_comm_unique_id(void* id128) {
+    if (!id128) return ASGFEM_EINVAL;
+    std::string err;
+    int rc = dist_unique_id(id128, err);
+    if (rc) g_create_error = err;
+    return rc;
+}
+
+extern "C" int asgfem_comm_init(asgfem_ctx* ctx, int32_t nranks, int32_t rank, const void* id128) {
+    CTX_OR_FAIL(ctx);
+    ASG_CHECK(ctx, nranks >= 1 && rank >= 0 && rank < nranks && id128, ASGFEM_EINVAL, "comm_init: bad arguments");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    return dist_init(ctx, nranks, rank, id128);
+}
+
+extern "C" int asgfem_comm_destroy(asgfem_ctx* ctx) {
+    CTX_OR_FAIL(ctx);
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    cudaStreamSynchronize(ctx->stream);
+    dist_free(ctx);
+    return 0;
+}
+
+extern "C" int asgfem_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const int64_t* send_ptr,
+                               const int64_t* send_rows, const int64_t* recv_ptr, const int64_t* recv_rows,
+                               int64_t interior_row0, int64_t interior_row1) {
+    CTX_OR_FAIL(ctx);
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    return dist_set_halo(ctx, nneigh, ranks, send_ptr, send_rows, recv_ptr, recv_rows, interior_row0, interior_row1);
+}
+
+extern "C" int asgfem_vec_dot_global(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, a) || check_slot(ctx, b)) return ASGFEM_EINVAL;
+    ASG_CHECK(ctx, out, ASGFEM_EINVAL, "null output");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    return dist_dot(ctx, ctx->slots[a], ctx->slots[b], out);
 }
 
 // ---- multi-GPU helpers --------------------------------------------------------------------------

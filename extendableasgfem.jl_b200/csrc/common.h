@@ -135,6 +135,7 @@ struct asgfem_ctx {
     asgfem::PrecondPlan* precond = nullptr;
     void* mmaplan = nullptr;  // asgfem::MmaPlan (apply_mma.cu)
     void* ts2plan = nullptr;  // asgfem::Ts2Plan (apply_ts2.cu)
+    void* distplan = nullptr;  // asgfem::DistPlan (dist.cu): NCCL communicator + halo plan
 };
 
 namespace asgfem {
@@ -187,6 +188,16 @@ int apply_ts2_build(asgfem_ctx* ctx);
 void apply_ts2_free(asgfem_ctx* ctx);
 int apply_ts2_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
 bool apply_ts2_preferred(asgfem_ctx* ctx);
+// dist.cu
+int dist_unique_id(void* id128, std::string& err);
+int dist_init(asgfem_ctx* ctx, int nranks, int rank, const void* id128);
+void dist_free(asgfem_ctx* ctx);
+bool dist_active(asgfem_ctx* ctx);
+int dist_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const int64_t* send_ptr, const int64_t* send_rows,
+                  const int64_t* recv_ptr, const int64_t* recv_rows, int64_t interior0, int64_t interior1);
+int dist_apply(asgfem_ctx* ctx, const double* x, double* y);               // = apply_launch without a communicator
+int dist_dot(asgfem_ctx* ctx, const double* a, const double* b, double* out);  // owned rows, summed over the ranks
+int dist_max(asgfem_ctx* ctx, double* v);
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
 int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* dX, double* dY);

@@ -1,0 +1,252 @@
+// Row-sharded multi-GPU operation inside the library: NCCL communicator per context, halo exchange
+// of X rows overlapped with the operator on the rows that need no halo column, all-reduced inner products.
+// The reference has no distributed path (dead `using Distributed`, src/ExtendableASGFEM.jl:3); the seams are those of the
+// single-GPU path - mul! (solvers_poisson_primal.jl:86-124) and the Krylov driver (:130-169) - on the rows of one rank.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2, or the copy a host process such as PyTorch has already loaded): the
+// single-GPU library has no link-time dependency on it.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+
+namespace asgfem {
+
+namespace {
+// the few NCCL entry points used, with the ABI of nccl.h 2.x (ncclComm_t is an opaque pointer, ncclUniqueId 128 bytes)
+typedef void* nccl_comm_t;
+struct nccl_uid {
+    char internal[128];
+};
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string& err) {
+    if (g_nccl.ok) return true;
+    void* h = nullptr;
+    // a copy already loaded by the host process (PyTorch bundles its own) is found through the global scope first
+    if (dlsym(RTLD_DEFAULT, "ncclCommInitRank")) h = RTLD_DEFAULT;
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        err = std::string("cannot load NCCL: ") + dlerror();
+        return false;
+    }
+    g_nccl.handle = h;
+#define BIND(field, sym)                                                     \
+    do {                                                                     \
+        *(void**)(&g_nccl.field) = dlsym(h, sym);                            \
+        if (!g_nccl.field) {                                                 \
+            err = std::string("NCCL symbol missing: ") + sym;                \
+            return false;                                                    \
+        }                                                                    \
+    } while (0)
+    BIND(GetUniqueId, "ncclGetUniqueId");
+    BIND(CommInitRank, "ncclCommInitRank");
+    BIND(CommDestroy, "ncclCommDestroy");
+    BIND(GroupStart, "ncclGroupStart");
+    BIND(GroupEnd, "ncclGroupEnd");
+    BIND(Send, "ncclSend");
+    BIND(Recv, "ncclRecv");
+    BIND(AllReduce, "ncclAllReduce");
+    BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+    g_nccl.ok = true;
+    return true;
+}
+}  // namespace
+
+struct DistPlan {
+    nccl_comm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    cudaStream_t cs = nullptr;  // communication stream
+    cudaEvent_t packed = nullptr, received = nullptr;
+    // halo plan (local numbering, 0-based on the device): per neighbour a send and a receive row list
+    std::vector<int> nb_rank;
+    std::vector<int64_t> send_ptr, recv_ptr;
+    int64_t* d_send_rows = nullptr;  // 1-based (k_pack_rows convention)
+    int64_t* d_recv_rows = nullptr;
+    double* d_sendbuf = nullptr;
+    double* d_recvbuf = nullptr;
+    int64_t buf_N = 0;               // N the buffers were sized for
+    int64_t interior0 = 0, interior1 = 0;  // owned rows [interior0, interior1) reference no halo column
+    double* d_scalar = nullptr;      // all-reduce scratch (2 doubles)
+    bool halo_set = false;
+};
+
+static DistPlan* dp_of(asgfem_ctx* ctx) { return reinterpret_cast<DistPlan*>(ctx->distplan); }
+
+void dist_free(asgfem_ctx* ctx) {
+    DistPlan* D = dp_of(ctx);
+    if (!D) return;
+    if (D->comm && g_nccl.ok) g_nccl.CommDestroy(D->comm);
+    void* ptrs[] = {D->d_send_rows, D->d_recv_rows, D->d_sendbuf, D->d_recvbuf, D->d_scalar};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (D->packed) cudaEventDestroy(D->packed);
+    if (D->received) cudaEventDestroy(D->received);
+    if (D->cs) cudaStreamDestroy(D->cs);
+    delete D;
+    ctx->distplan = nullptr;
+}
+
+bool dist_active(asgfem_ctx* ctx) {
+    DistPlan* D = dp_of(ctx);
+    return D && D->comm && D->nranks > 1;
+}
+
+#define NCCL_CHECK(ctx, call)                                                                                         \
+    do {                                                                                                              \
+        int _r = (call);                                                                                              \
+        if (_r != 0) return fail((ctx), ASGFEM_ECUDA, std::string(#call) + ": " + g_nccl.GetErrorString(_r));         \
+    } while (0)
+
+int dist_unique_id(void* id128, std::string& err) {
+    if (!load_nccl(err)) return ASGFEM_ESTATE;
+    nccl_uid id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) {
+        err = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r);
+        return ASGFEM_ECUDA;
+    }
+    std::memcpy(id128, &id, 128);
+    return 0;
+}
+
+int dist_init(asgfem_ctx* ctx, int nranks, int rank, const void* id128) {
+    std::string err;
+    if (!load_nccl(err)) return fail(ctx, ASGFEM_ESTATE, err);
+    dist_free(ctx);
+    DistPlan* D = new DistPlan();
+    ctx->distplan = D;
+    D->nranks = nranks;
+    D->rank = rank;
+    nccl_uid id;
+    std::memcpy(&id, id128, 128);
+    NCCL_CHECK(ctx, g_nccl.CommInitRank(&D->comm, nranks, id, rank));
+    ASG_CUDA(ctx, cudaStreamCreateWithFlags(&D->cs, cudaStreamNonBlocking));
+    ASG_CUDA(ctx, cudaEventCreateWithFlags(&D->packed, cudaEventDisableTiming));
+    ASG_CUDA(ctx, cudaEventCreateWithFlags(&D->received, cudaEventDisableTiming));
+    ASG_CUDA(ctx, cudaMalloc((void**)&D->d_scalar, 4 * sizeof(double)));
+    return 0;
+}
+
+int dist_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const int64_t* send_ptr, const int64_t* send_rows,
+                  const int64_t* recv_ptr, const int64_t* recv_rows, int64_t interior0, int64_t interior1) {
+    DistPlan* D = dp_of(ctx);
+    ASG_CHECK(ctx, D && D->comm, ASGFEM_ESTATE, "set_halo: asgfem_comm_init first");
+    ASG_CHECK(ctx, ctx->n > 0 && ctx->n_owned > 0, ASGFEM_ESTATE, "set_halo: pattern and owned rows first");
+    ASG_CHECK(ctx, nneigh >= 0 && (nneigh == 0 || (ranks && send_ptr && recv_ptr)), ASGFEM_EINVAL, "set_halo: bad arguments");
+    ASG_CHECK(ctx, 0 <= interior0 && interior0 <= interior1 && interior1 <= ctx->n_owned, ASGFEM_EINVAL, "set_halo: bad interior range");
+    D->nb_rank.assign(ranks, ranks + nneigh);
+    D->send_ptr.assign(send_ptr, send_ptr + nneigh + 1);
+    D->recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1);
+    for (int k = 0; k < nneigh; ++k)
+        ASG_CHECK(ctx, ranks[k] >= 0 && ranks[k] < D->nranks && ranks[k] != D->rank, ASGFEM_EINVAL, "set_halo: bad neighbour rank");
+    const int64_t ns = D->send_ptr[nneigh], nr = D->recv_ptr[nneigh];
+    for (int64_t k = 0; k < ns; ++k) ASG_CHECK(ctx, send_rows[k] >= 1 && send_rows[k] <= ctx->n_owned, ASGFEM_EINVAL, "set_halo: send row not owned");
+    for (int64_t k = 0; k < nr; ++k)
+        ASG_CHECK(ctx, recv_rows[k] > ctx->n_owned && recv_rows[k] <= ctx->n, ASGFEM_EINVAL, "set_halo: receive row is not a halo row");
+    for (void** p : {(void**)&D->d_send_rows, (void**)&D->d_recv_rows, (void**)&D->d_sendbuf, (void**)&D->d_recvbuf})
+        if (*p) {
+            cudaFree(*p);
+            *p = nullptr;
+        }
+    ASG_CUDA(ctx, cudaMalloc((void**)&D->d_send_rows, sizeof(int64_t) * std::max<int64_t>(ns, 1)));
+    ASG_CUDA(ctx, cudaMalloc((void**)&D->d_recv_rows, sizeof(int64_t) * std::max<int64_t>(nr, 1)));
+    ASG_CUDA(ctx, cudaMemcpyAsync(D->d_send_rows, send_rows, sizeof(int64_t) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    ASG_CUDA(ctx, cudaMemcpyAsync(D->d_recv_rows, recv_rows, sizeof(int64_t) * nr, cudaMemcpyHostToDevice, ctx->stream));
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    D->buf_N = 0;
+    D->interior0 = interior0;
+    D->interior1 = interior1;
+    D->halo_set = true;
+    return 0;
+}
+
+static int ensure_buffers(asgfem_ctx* ctx, DistPlan* D) {
+    if (D->buf_N == ctx->N && D->d_sendbuf) return 0;
+    for (void** p : {(void**)&D->d_sendbuf, (void**)&D->d_recvbuf})
+        if (*p) {
+            cudaFree(*p);
+            *p = nullptr;
+        }
+    const int64_t ns = D->send_ptr.empty() ? 0 : D->send_ptr.back(), nr = D->recv_ptr.empty() ? 0 : D->recv_ptr.back();
+    ASG_CUDA(ctx, cudaMalloc((void**)&D->d_sendbuf, sizeof(double) * std::max<int64_t>(ns * ctx->N, 1)));
+    ASG_CUDA(ctx, cudaMalloc((void**)&D->d_recvbuf, sizeof(double) * std::max<int64_t>(nr * ctx->N, 1)));
+    D->buf_N = ctx->N;
+    return 0;
+}
+
+// Y = A X on the owned rows of this rank.  One launch sequence, no host synchronisation:
+//   stream:       pack send rows | operator on [interior0, interior1) | wait | unpack halo rows | operator on the other owned rows
+//   comm stream:                 | grouped ncclSend / ncclRecv         |
+int dist_apply(asgfem_ctx* ctx, const double* x, double* y) {
+    DistPlan* D = dp_of(ctx);
+    if (!dist_active(ctx)) return apply_launch(ctx, x, y);
+    ASG_CHECK(ctx, D->halo_set, ASGFEM_ESTATE, "apply: asgfem_set_halo first");
+    int rc = ensure_buffers(ctx, D);
+    if (rc) return rc;
+    const int nn = (int)D->nb_rank.size();
+    const int64_t N = ctx->N, ns = D->send_ptr[nn], nr = D->recv_ptr[nn];
+    if ((rc = vec_pack_rows(ctx, x, ns, D->d_send_rows, D->d_sendbuf))) return rc;
+    ASG_CUDA(ctx, cudaEventRecord(D->packed, ctx->stream));
+    ASG_CUDA(ctx, cudaStreamWaitEvent(D->cs, D->packed, 0));
+    NCCL_CHECK(ctx, g_nccl.GroupStart());
+    for (int k = 0; k < nn; ++k) {
+        const int64_t s0 = D->send_ptr[k], s1 = D->send_ptr[k + 1], r0 = D->recv_ptr[k], r1 = D->recv_ptr[k + 1];
+        if (s1 > s0) NCCL_CHECK(ctx, g_nccl.Send(D->d_sendbuf + s0 * N, (size_t)((s1 - s0) * N), NCCL_FLOAT64, D->nb_rank[k], D->comm, D->cs));
+        if (r1 > r0) NCCL_CHECK(ctx, g_nccl.Recv(D->d_recvbuf + r0 * N, (size_t)((r1 - r0) * N), NCCL_FLOAT64, D->nb_rank[k], D->comm, D->cs));
+    }
+    NCCL_CHECK(ctx, g_nccl.GroupEnd());
+    ASG_CUDA(ctx, cudaEventRecord(D->received, D->cs));
+    if (D->interior1 > D->interior0 && (rc = apply_launch(ctx, x, y, D->interior0, D->interior1))) return rc;
+    ASG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, D->received, 0));
+    if ((rc = vec_unpack_rows(ctx, const_cast<double*>(x), nr, D->d_recv_rows, D->d_recvbuf))) return rc;
+    if (D->interior0 > 0 && (rc = apply_launch(ctx, x, y, 0, D->interior0))) return rc;
+    if (D->interior1 < ctx->n_owned && (rc = apply_launch(ctx, x, y, D->interior1, ctx->n_owned))) return rc;
+    return 0;
+}
+
+// sum over the ranks of the inner product on the owned rows (deterministic local part + ncclAllReduce)
+int dist_dot(asgfem_ctx* ctx, const double* a, const double* b, double* out) {
+    DistPlan* D = dp_of(ctx);
+    const int64_t rows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
+    if (!dist_active(ctx)) return vec_dot(ctx, a, b, rows, out);
+    double local = 0;
+    int rc = vec_dot(ctx, a, b, rows, &local);  // leaves the value in d_partial as well; the host copy is what we reduce
+    if (rc) return rc;
+    ASG_CUDA(ctx, cudaMemcpyAsync(D->d_scalar, &local, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.AllReduce(D->d_scalar, D->d_scalar + 1, 1, NCCL_FLOAT64, NCCL_SUM, D->comm, ctx->stream));
+    ASG_CUDA(ctx, cudaMemcpyAsync(out, D->d_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// max over the ranks of a host scalar (device timings)
+int dist_max(asgfem_ctx* ctx, double* v) {
+    DistPlan* D = dp_of(ctx);
+    if (!dist_active(ctx)) return 0;
+    ASG_CUDA(ctx, cudaMemcpyAsync(D->d_scalar + 2, v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.AllReduce(D->d_scalar + 2, D->d_scalar + 3, 1, NCCL_FLOAT64, 2 /* ncclMax */, D->comm, ctx->stream));
+    ASG_CUDA(ctx, cudaMemcpyAsync(v, D->d_scalar + 3, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace asgfem

@@ -108,14 +108,14 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
     PCG_CUDA(cudaMemcpyAsync(p, x, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     k_make_rhs<<<grid, 256, 0, ctx->stream>>>(p, b0, ctx->d_bmask, n, ld, (int64_t)ctx->h_pos[0]);
     // r = b - A x
-    PCG_RC(apply_launch(ctx, x, q));
+    PCG_RC(dist_apply(ctx, x, q));
     PCG_CUDA(cudaMemcpyAsync(r, p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     PCG_RC(vec_axpy(ctx, -1.0, q, r));
     // the reduced system keeps x[bdofs] fixed: residual rows at bdofs are zero by construction
     PCG_RC(precond_apply(ctx, r, z));
     PCG_CUDA(cudaMemcpyAsync(p, z, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     double rz = 0;
-    PCG_RC(vec_dot(ctx, r, z, n, &rz));
+    PCG_RC(dist_dot(ctx, r, z, &rz));
     const double rz0 = rz;
     const double eps = atol + rtol * std::sqrt(std::max(rz0, 0.0));
     double ms_setup = tall.stop();
@@ -124,10 +124,10 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
     tall.start();
     while (k < itmax && std::sqrt(std::max(rz, 0.0)) > eps) {
         tpart.start();
-        PCG_RC(apply_launch(ctx, p, q));
+        PCG_RC(dist_apply(ctx, p, q));
         ms_apply += tpart.stop();
         double pq = 0;
-        PCG_RC(vec_dot(ctx, p, q, n, &pq));
+        PCG_RC(dist_dot(ctx, p, q, &pq));
         if (!(pq > 0.0) || !std::isfinite(pq)) {
             cleanup();
             return fail(ctx, ASGFEM_ENUMERIC, "pcg: p.Ap <= 0 - operator not positive definite on the search direction");
@@ -138,7 +138,7 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
         PCG_RC(precond_apply(ctx, r, z));
         ms_prec += tpart.stop();
         double rz_new = 0;
-        PCG_RC(vec_dot(ctx, r, z, n, &rz_new));
+        PCG_RC(dist_dot(ctx, r, z, &rz_new));
         const double beta = rz_new / rz;
         PCG_RC(vec_xpay(ctx, z, beta, p));  // p = z + beta p
         rz = rz_new;
@@ -150,7 +150,7 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
         // the reference prints ||A x - b|| (solvers_poisson_primal.jl:165-167); b depends on the warm start that x
         // has overwritten, so the norm of the recursively updated residual r_k = b - A x_k is reported instead
         double rr = 0;
-        PCG_RC(vec_dot(ctx, r, r, n, &rr));
+        PCG_RC(dist_dot(ctx, r, r, &rr));
         stats->niter = k;
         stats->solved = std::sqrt(std::max(rz, 0.0)) <= eps ? 1 : 0;
         stats->_pad = 0;

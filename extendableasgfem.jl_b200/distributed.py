@@ -47,18 +47,23 @@ class LocalProblem:
 
     def __init__(self, rank, owner, indptr, indices):
         self.rank = rank
+        owner = np.asarray(owner)
+        indptr = np.asarray(indptr, dtype=np.int64)
+        indices = np.asarray(indices, dtype=np.int64)
         n = len(owner)
-        owned = np.where(owner == rank)[0]
+        row_of = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))  # row of every stored entry
+        mine_row = owner[row_of] == rank
+        foreign_col = owner[indices] != rank
         # interior rows (all columns owned) first, rows that reference a halo column last: the operator on the first
         # n_interior rows does not need the halo exchange and runs while it is in flight
-        touches_halo = np.array([np.any(owner[indices[indptr[i]:indptr[i + 1]]] != rank) for i in owned], dtype=bool) \
-            if len(owned) else np.zeros(0, dtype=bool)
-        self.owned = np.concatenate([owned[~touches_halo], owned[touches_halo]])
+        touches = np.zeros(n, dtype=bool)
+        touches[row_of[mine_row & foreign_col]] = True
+        owned = np.where(owner == rank)[0]
+        th = touches[owned]
+        self.owned = np.concatenate([owned[~th], owned[th]])
         self.n_owned = len(self.owned)
-        self.n_interior = int(np.count_nonzero(~touches_halo))
-        cols = np.unique(np.concatenate([indices[indptr[i]:indptr[i + 1]] for i in self.owned])
-                         if self.n_owned else np.zeros(0, dtype=np.int64))
-        halo = cols[owner[cols] != rank]
+        self.n_interior = int(np.count_nonzero(~th))
+        halo = np.unique(indices[mine_row & foreign_col])
         halo = halo[np.lexsort((halo, owner[halo]))]
         self.halo = halo
         self.local_to_global = np.concatenate([self.owned, halo])
@@ -66,37 +71,33 @@ class LocalProblem:
         g2l = -np.ones(n, dtype=np.int64)
         g2l[self.local_to_global] = np.arange(self.n_local)
         self.global_to_local = g2l
-        # receive lists: local halo positions per neighbour rank
+        # receive lists: local halo positions per neighbour rank (ascending global id)
         self.recv = {int(q): g2l[halo[owner[halo] == q]] for q in np.unique(owner[halo])}
-        # send lists: my owned dofs that rank q references (structurally symmetric pattern: the dofs of mine
-        # adjacent to q's rows are the ones whose rows reference q's dofs - computed from the rows of q's halo)
+        # send lists: my dofs that the rows of rank q reference = the columns of q's rows that I own (no symmetry of the
+        # pattern assumed: this is exactly the halo of q restricted to my dofs, in the same ascending global order)
         self.send = {}
-        for q in self.recv:
-            mine = set()
-            for j in halo[owner[halo] == q]:
-                for i in indices[indptr[j]:indptr[j + 1]]:
-                    if owner[i] == rank:
-                        mine.add(int(i))
-            self.send[q] = g2l[np.array(sorted(mine), dtype=np.int64)]
-        # local CSR: owned rows with local column ids, halo rows empty
-        lp = [0]
-        li = []
-        for i in self.owned:
-            c = g2l[indices[indptr[i]:indptr[i + 1]]]
-            li.append(np.sort(c))
-            lp.append(lp[-1] + len(c))
-        lp.extend([lp[-1]] * len(halo))
-        self.indptr = np.array(lp, dtype=np.int64)
-        self.indices = np.concatenate(li) if li else np.zeros(0, dtype=np.int64)
+        col_mine = owner[indices] == rank
+        for q in np.unique(owner[row_of[col_mine & ~mine_row]]) if n else []:
+            sel = col_mine & (owner[row_of] == q)
+            self.send[int(q)] = g2l[np.unique(indices[sel])]
+        # local CSR: owned rows with local column ids (sorted), halo rows empty
+        cnt = np.diff(indptr)[self.owned]
+        lp = np.zeros(self.n_local + 1, dtype=np.int64)
+        lp[1:self.n_owned + 1] = np.cumsum(cnt)
+        lp[self.n_owned + 1:] = lp[self.n_owned]
+        # entries of the owned rows in the new row order
+        starts = indptr[self.owned]
+        src = np.repeat(starts - lp[:self.n_owned], cnt) + np.arange(lp[self.n_owned], dtype=np.int64)
+        lrow = np.repeat(np.arange(self.n_owned, dtype=np.int64), cnt)
+        lcol = g2l[indices[src]]
+        order = np.lexsort((lcol, lrow))
+        self.indptr = lp
+        self.indices = lcol[order]
+        self._src = src[order]  # position in the global CSR of every local entry
 
     def local_values(self, indptr, indices, vals):
-        """Values of the owned rows in the order of the local CSR (columns re-sorted by local id)."""
-        out = []
-        for i in self.owned:
-            sl = slice(indptr[i], indptr[i + 1])
-            c = self.global_to_local[indices[sl]]
-            out.append(vals[sl][np.argsort(c, kind="stable")])
-        return np.concatenate(out) if out else np.zeros(0)
+        """Values of the owned rows in the order of the local CSR (columns sorted by local id)."""
+        return np.asarray(vals)[self._src]
 
 
 # ---- halo exchange + Krylov loop ---------------------------------------------------------------------

@@ -224,6 +224,28 @@ int asgfem_pack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t
 int asgfem_unpack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t* rows, const void* dbuf);
 int asgfem_vec_dot_owned(asgfem_ctx* ctx, int32_t slot_a, int32_t slot_b, double* out);
 
+
+/* ---- (e) NCCL inside the library -------------------------------------------------------------------
+ * One process per GPU, one context per process.  Rank 0 creates a 128-byte NCCL id (asgfem_comm_unique_id) and the host
+ * layer hands it to the other ranks by any channel it has (MPI.jl bcast, a file, torch.distributed); every rank then
+ * calls asgfem_comm_init.  NCCL is bound at run time (libnccl.so.2), the single-GPU library does not depend on it.
+ * With a communicator and a halo plan installed, asgfem_apply / asgfem_pcg / asgfem_solve_primal_host work on the ROW
+ * SHARD of this rank: asgfem_apply packs the send rows, posts grouped ncclSend/ncclRecv on a communication stream,
+ * applies the operator to the owned rows [interior_row0, interior_row1) (which reference no halo column) while the
+ * exchange is in flight, unpacks the halo rows and applies the remaining owned rows - one launch sequence without host
+ * synchronisation; the Krylov inner products are all-reduced (ncclAllReduce).  The mean preconditioner is the rank-local
+ * one (block-Jacobi over the partition, SURVEY.md section 7: same converged solution, more iterations).
+ * set_halo: neighbour k has rank ranks[k], send rows send_rows[send_ptr[k] .. send_ptr[k+1]) (owned, 1-based local ids)
+ * and receive rows recv_rows[recv_ptr[k] .. recv_ptr[k+1]) (halo rows, 1-based local ids); both sides of an exchange list
+ * the rows in the same (global) order. */
+int asgfem_comm_unique_id(void* id128);
+int asgfem_comm_init(asgfem_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int asgfem_comm_destroy(asgfem_ctx* ctx);
+int asgfem_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const int64_t* send_ptr, const int64_t* send_rows,
+                    const int64_t* recv_ptr, const int64_t* recv_rows, int64_t interior_row0, int64_t interior_row1);
+/* inner product over the owned rows, summed over all ranks (= asgfem_vec_dot_owned without a communicator) */
+int asgfem_vec_dot_global(asgfem_ctx* ctx, int32_t slot_a, int32_t slot_b, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,27 @@ def _worker(rank, world, port, q):
         st = D.pcg(op, dict(x=0, b=1, r=2, z=3, p=4, q=5), atol=1e-14, rtol=1e-13, itmax=500)
         sol = ctx.vec_download(0).reshape(P.N, L.n_local)[:, :L.n_owned]
         err_sol = np.abs(sol - refsol[:, L.owned]).max() / np.abs(refsol).max()
-        q.put((rank, err_apply, st["niter"], bool(st["solved"]), err_sol))
+        # ---- the same through the library's own NCCL path (asgfem_comm_init / asgfem_set_halo): one C call per operator
+        # application and per solve, what the Julia shim would use
+        ids = [A.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+        ctx.set_halo(L.send, L.recv, 0, L.n_interior)
+        ctx.vec_upload(0, xl.reshape(-1))
+        ctx.apply(0, 1)
+        got2 = ctx.vec_download(1).reshape(P.N, L.n_local)[:, :L.n_owned]
+        err_apply2 = np.abs(got2 - ref[:, L.owned]).max() / np.abs(ref).max()
+        same = bool(np.array_equal(got2, got))
+        ctx.vec_zero(0)
+        b0l = np.zeros(L.n_local)
+        b0l[:L.n_owned] = P.b0[L.owned]
+        st2 = ctx.pcg(b0l, 0, 1e-14, 1e-13, 500)
+        sol2 = ctx.vec_download(0).reshape(P.N, L.n_local)[:, :L.n_owned]
+        err_sol2 = np.abs(sol2 - refsol[:, L.owned]).max() / np.abs(refsol).max()
+        gd = ctx.vec_dot_global(0, 0)
+        q.put((rank, err_apply, st["niter"], bool(st["solved"]), err_sol, err_apply2, same, int(st2["niter"]), bool(st2["solved"]),
+               err_sol2, gd))
+        ctx.comm_destroy()
         ctx.close()
     finally:
         dist.destroy_process_group()
@@ -71,7 +91,11 @@ def test_two_gpu_operator_and_pcg():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err_apply, niter, solved, err_sol in res:
+    for rank, err_apply, niter, solved, err_sol, err_apply2, same, niter2, solved2, err_sol2, gd in res:
         assert err_apply < 1e-12, (rank, err_apply)
         assert solved and niter < 300
         assert err_sol < 1e-10, (rank, err_sol)
+        assert err_apply2 < 1e-12 and same, (rank, err_apply2, same)
+        assert solved2 and niter2 == niter, (niter2, niter)
+        assert err_sol2 < 1e-10, (rank, err_sol2)
+    assert res[0][-1] == res[1][-1]  # the all-reduced inner product is the same number on both ranks
