@@ -317,7 +317,24 @@ def run_gpu(args):
         # sharded solve: rank-local mean preconditioner (block-Jacobi over the strips), all-reduced inner products
         try:
             t0 = time.perf_counter()
-            ctx.precond_setup()
+            # exact mean preconditioner: K_0 of the GLOBAL 1024 x (1024 world) mesh, assembled by a throw-away context
+            # (natural numbering = the rank-major order of the strips), factorised by every rank on its host cores
+            gg = A.structured_unitsquare(NX, NX * world)
+            gf = A.FESpace(gg, 1)
+            c0 = A.Context(local_rank)
+            c0.set_multiindices(A.LEGENDRE, np.zeros((1, 1), dtype=np.int64))
+            Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=M_KLE)
+            c0.set_mesh(gg.coords, gg.cellnodes + 1)
+            c0.set_space(1, gf.ndofs, gf.celldofs + 1)
+            c0.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
+            xr_, w_ = A.quadrature_rule(2)
+            c0.assemble_stiffness(0, xr_, w_)
+            gcp, grv = c0.pattern_csc()
+            gnz = c0.get_stiffness(0)
+            c0.close()
+            ctx.precond_setup_global(gf.ndofs, gcp, grv, gnz, gf.bdofs + 1, np.arange(world + 1) * n_owned,
+                                     coords=np.ascontiguousarray(gg.coords))
+            del gcp, grv, gnz
             t_fac = time.perf_counter() - t0
             ctx.vec_alloc(1)
             ctx.vec_zero(0)
@@ -326,7 +343,7 @@ def run_gpu(args):
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
-            st = ctx.pcg(b0, 0, 1e-14, 1e-10, 300)
+            st = ctx.pcg(b0, 0, 1e-14, 1e-14, 300)
             torch.cuda.synchronize()
             t_solve = time.perf_counter() - t0
             t = torch.tensor([t_solve], dtype=torch.float64, device="cuda")
@@ -336,9 +353,11 @@ def run_gpu(args):
                               "factor_s_host": round(t_fac, 2),
                               "ms_per_iteration": round(st["ms_iterations"] / max(st["niter"], 1), 2),
                               "ms_operator_total": round(st["ms_apply"], 1), "ms_preconditioner_total": round(st["ms_precond"], 1),
-                              "rtol": 1e-10,
-                              "note": "sharded PCG inside the library: block-Jacobi mean preconditioner (every rank factorises "
-                                      "its strip of K_0), halo exchange + all-reduce over NCCL; max over ranks"}
+                              "rtol": 1e-14,
+                              "note": "sharded PCG inside the library with the EXACT mean preconditioner: per application the "
+                                      "ranks swap from row shards to mode shards (all-to-all over NCCL), sweep their modes with the "
+                                      "factor of the global K_0 and swap back; halo exchange + all-reduce over NCCL; factor_s_host "
+                                      "= assembly + host Cholesky of the global K_0 on every rank; max over ranks"}
         except Exception as e:  # pragma: no cover
             if rank == 0:
                 out["pcg"] = {"error": str(e)[:200]}

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "asgfem_comm_destroy": (c_i32, [vp]),
     "asgfem_set_halo": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp, c_i64, c_i64]),
     "asgfem_vec_dot_global": (c_i32, [vp, c_i32, c_i32, P(c_f64)]),
+    "asgfem_precond_setup_global": (c_i32, [vp, c_i64, vp, vp, vp, c_i64, vp, vp, vp]),
 }
 
 _lib = None

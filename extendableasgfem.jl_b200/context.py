@@ -164,6 +164,14 @@ class Context:
         self._ck(self.lib.asgfem_vec_dot_owned(self.h, a, b, C.byref(out)))
         return out.value
 
+    def precond_setup_global(self, n_global, colptr, rowval, nzval, bdofs1, row_offsets, coords=None):
+        """Global K_0 (CSC, 1-based, rank-major global numbering) for the exact mean preconditioner of a sharded solve."""
+        cp, rv, nz = _i64(colptr), _i64(rowval), _f64(nzval)
+        bd, ro = _i64(bdofs1), _i64(row_offsets)
+        xy = _f64(coords) if coords is not None else None
+        self._ck(self.lib.asgfem_precond_setup_global(self.h, int(n_global), _ptr(cp), _ptr(rv), _ptr(nz), len(bd), _ptr(bd),
+                                                      _ptr(xy) if xy is not None else None, _ptr(ro)))
+
     def vec_dot_global(self, a, b):
         out = C.c_double()
         self._ck(self.lib.asgfem_vec_dot_global(self.h, a, b, C.byref(out)))

@@ -715,7 +715,7 @@ extern "C" int asgfem_pcg(asgfem_ctx* ctx, const double* b0, int32_t slot_x, dou
     if (set_device(ctx)) return ASGFEM_ECUDA;
     int rc = ensure_ready_for_apply(ctx);
     if (rc) return rc;
-    if (!ctx->precond && (rc = precond_setup(ctx))) return rc;
+    if (!ctx->precond && !dist_has_global_precond(ctx) && (rc = precond_setup(ctx))) return rc;
     return pcg_solve(ctx, b0, ctx->slots[slot_x], atol, rtol, itmax, stats);
 }
 
@@ -878,6 +878,14 @@ extern "C" int asgfem_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* r
     CTX_OR_FAIL(ctx);
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return dist_set_halo(ctx, nneigh, ranks, send_ptr, send_rows, recv_ptr, recv_rows, interior_row0, interior_row1);
+}
+
+extern "C" int asgfem_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* colptr, const int64_t* rowval,
+                                           const double* nzval, int64_t nb, const int64_t* bdofs, const double* coords,
+                                           const int64_t* row_offsets) {
+    CTX_OR_FAIL(ctx);
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    return dist_precond_setup_global(ctx, n_global, colptr, rowval, nzval, nb, bdofs, coords, row_offsets);
 }
 
 extern "C" int asgfem_vec_dot_global(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) {

@@ -198,6 +198,10 @@ int dist_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const i
 int dist_apply(asgfem_ctx* ctx, const double* x, double* y);               // = apply_launch without a communicator
 int dist_dot(asgfem_ctx* ctx, const double* a, const double* b, double* out);  // owned rows, summed over the ranks
 int dist_max(asgfem_ctx* ctx, double* v);
+int dist_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                              int64_t nb, const int64_t* bdofs, const double* coords, const int64_t* row_offsets);
+bool dist_has_global_precond(asgfem_ctx* ctx);
+int dist_precond_apply(asgfem_ctx* ctx, const double* r, double* z);  // = precond_apply without a global factor
 // vecops.cu
 int vec_to_device_layout(asgfem_ctx* ctx, const double* host, double* dvec);
 int apply_host_pipelined(asgfem_ctx* ctx, const double* x, double* Ax, double* dX, double* dY);
@@ -215,6 +219,11 @@ int vec_eval_samples(asgfem_ctx* ctx, const double* u, const double* dR, int64_t
 int precond_setup(asgfem_ctx* ctx);
 void precond_free(asgfem_ctx* ctx);
 int precond_apply(asgfem_ctx* ctx, const double* r, double* z);
+int precond_build(asgfem_ctx* ctx, int64_t nfull, const int64_t* rowptr, const int32_t* col, const double* k0,
+                  const uint8_t* bmask, const double* xy, PrecondPlan** out);
+int precond_apply_plan(asgfem_ctx* ctx, PrecondPlan* P, const double* r, double* z, int64_t nrows, int64_t ld,
+                       const uint8_t* d_bmask);
+void precond_free_plan(PrecondPlan* P);
 // pcg.cu
 int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, double rtol, int64_t itmax,
               asgfem_stats* stats);

@@ -87,6 +87,15 @@ struct DistPlan {
     int64_t interior0 = 0, interior1 = 0;  // owned rows [interior0, interior1) reference no halo column
     double* d_scalar = nullptr;      // all-reduce scratch (2 doubles)
     bool halo_set = false;
+    // global mean preconditioner (exact K_0^-1 for every mode): the ranks swap from row shards to MODE shards, every rank
+    // applies the factor of the global K_0 to its columns, and swap back
+    PrecondPlan* gprec = nullptr;
+    int64_t n_global = 0;
+    std::vector<int64_t> row_off, col_off;  // nranks+1: global row offsets (rank-major order) / device column chunks (x16)
+    uint8_t* d_gbmask = nullptr;
+    double* d_T = nullptr;       // n_global x (columns of this rank)
+    double* d_stage = nullptr;   // n_owned x ld, blocks [n_owned x columns of rank q] one after the other
+    int64_t T_cols = 0, stage_ld = 0;
 };
 
 static DistPlan* dp_of(asgfem_ctx* ctx) { return reinterpret_cast<DistPlan*>(ctx->distplan); }
@@ -95,7 +104,8 @@ void dist_free(asgfem_ctx* ctx) {
     DistPlan* D = dp_of(ctx);
     if (!D) return;
     if (D->comm && g_nccl.ok) g_nccl.CommDestroy(D->comm);
-    void* ptrs[] = {D->d_send_rows, D->d_recv_rows, D->d_sendbuf, D->d_recvbuf, D->d_scalar};
+    precond_free_plan(D->gprec);
+    void* ptrs[] = {D->d_send_rows, D->d_recv_rows, D->d_sendbuf, D->d_recvbuf, D->d_scalar, D->d_gbmask, D->d_T, D->d_stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (D->packed) cudaEventDestroy(D->packed);
@@ -235,6 +245,139 @@ int dist_dot(asgfem_ctx* ctx, const double* a, const double* b, double* out) {
     NCCL_CHECK(ctx, g_nccl.AllReduce(D->d_scalar, D->d_scalar + 1, 1, NCCL_FLOAT64, NCCL_SUM, D->comm, ctx->stream));
     ASG_CUDA(ctx, cudaMemcpyAsync(out, D->d_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- global mean preconditioner ---------------------------------------------------------------------------------------
+namespace {
+struct ColChunks {
+    int n;
+    int64_t off[33];
+};
+// stage block q = rows x (columns of rank q), row-major, blocks concatenated; pack: v -> stage, unpack: stage -> v
+__global__ void k_swap_cols(double* __restrict__ v, double* __restrict__ stage, int64_t nrows, int64_t ld, ColChunks cc, int pack) {
+    const int64_t total = nrows * (ld / 2);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / (ld / 2), c = 2 * (t - i * (ld / 2));
+        int q = 0;
+        while (q + 1 < cc.n && c >= cc.off[q + 1]) ++q;
+        const int64_t w = cc.off[q + 1] - cc.off[q];
+        double2* sp = reinterpret_cast<double2*>(stage + nrows * cc.off[q] + i * w + (c - cc.off[q]));
+        double2* vp = reinterpret_cast<double2*>(v + i * ld + c);
+        if (pack)
+            *sp = *vp;
+        else
+            *vp = *sp;
+    }
+}
+}  // namespace
+
+int dist_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                              int64_t nb, const int64_t* bdofs, const double* coords, const int64_t* row_offsets) {
+    DistPlan* D = dp_of(ctx);
+    ASG_CHECK(ctx, D && D->comm, ASGFEM_ESTATE, "precond_setup_global: asgfem_comm_init first");
+    ASG_CHECK(ctx, ctx->ld > 0 && ctx->n_owned > 0, ASGFEM_ESTATE, "precond_setup_global: multi-indices and owned rows first");
+    ASG_CHECK(ctx, n_global > 0 && colptr && rowval && nzval && row_offsets, ASGFEM_EINVAL, "precond_setup_global: bad arguments");
+    ASG_CHECK(ctx, D->nranks <= 32, ASGFEM_EINVAL, "precond_setup_global: at most 32 ranks");
+    D->row_off.assign(row_offsets, row_offsets + D->nranks + 1);
+    ASG_CHECK(ctx, D->row_off[0] == 0 && D->row_off[D->nranks] == n_global &&
+                       D->row_off[D->rank + 1] - D->row_off[D->rank] == ctx->n_owned,
+              ASGFEM_EINVAL, "precond_setup_global: row offsets do not match the owned rows of this rank");
+    // CSC (1-based) -> CSR (0-based); K_0 is symmetric, the transposition keeps the routine general
+    const int64_t nnz = colptr[n_global] - 1;
+    std::vector<int64_t> rp((size_t)n_global + 1, 0);
+    for (int64_t p = 0; p < nnz; ++p) {
+        ASG_CHECK(ctx, rowval[p] >= 1 && rowval[p] <= n_global, ASGFEM_EINVAL, "precond_setup_global: row index out of range");
+        rp[(size_t)rowval[p]]++;
+    }
+    for (int64_t i = 0; i < n_global; ++i) rp[(size_t)i + 1] += rp[(size_t)i];
+    std::vector<int32_t> ci((size_t)nnz);
+    std::vector<double> cv((size_t)nnz);
+    {
+        std::vector<int64_t> fill(rp.begin(), rp.end() - 1);
+        for (int64_t c = 0; c < n_global; ++c)
+            for (int64_t p = colptr[c] - 1; p < colptr[c + 1] - 1; ++p) {
+                const int64_t at = fill[(size_t)(rowval[p] - 1)]++;
+                ci[(size_t)at] = (int32_t)c;
+                cv[(size_t)at] = nzval[p];
+            }
+    }
+    std::vector<uint8_t> bm((size_t)n_global, 0);
+    for (int64_t k = 0; k < nb; ++k) {
+        ASG_CHECK(ctx, bdofs[k] >= 1 && bdofs[k] <= n_global, ASGFEM_EINVAL, "precond_setup_global: boundary dof out of range");
+        bm[(size_t)(bdofs[k] - 1)] = 1;
+    }
+    precond_free_plan(D->gprec);
+    D->gprec = nullptr;
+    int rc = precond_build(ctx, n_global, rp.data(), ci.data(), cv.data(), bm.data(), coords, &D->gprec);
+    if (rc) return rc;
+    D->n_global = n_global;
+    if ((rc = dev_upload(ctx, &D->d_gbmask, bm))) return rc;
+    // column chunks: tiles of 16 device columns dealt out evenly
+    const int64_t tiles = ctx->ld / 16;
+    D->col_off.assign((size_t)D->nranks + 1, 0);
+    for (int q = 0; q <= D->nranks; ++q) D->col_off[(size_t)q] = 16 * (tiles * q / D->nranks);
+    for (void** p : {(void**)&D->d_T, (void**)&D->d_stage})
+        if (*p) {
+            cudaFree(*p);
+            *p = nullptr;
+        }
+    D->T_cols = D->col_off[(size_t)D->rank + 1] - D->col_off[(size_t)D->rank];
+    D->stage_ld = ctx->ld;
+    ASG_CUDA(ctx, cudaMalloc((void**)&D->d_T, sizeof(double) * (size_t)std::max<int64_t>(n_global * D->T_cols, 1)));
+    ASG_CUDA(ctx, cudaMalloc((void**)&D->d_stage, sizeof(double) * (size_t)ctx->n_owned * (size_t)ctx->ld));
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+bool dist_has_global_precond(asgfem_ctx* ctx) {
+    DistPlan* D = dp_of(ctx);
+    return dist_active(ctx) && D->gprec;
+}
+
+// z = (I (x) K_0^-1) r with the GLOBAL K_0: row shards -> mode shards (all-to-all), sweeps, and back
+int dist_precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
+    DistPlan* D = dp_of(ctx);
+    if (!dist_has_global_precond(ctx)) return precond_apply(ctx, r, z);
+    ASG_CHECK(ctx, D->stage_ld == ctx->ld, ASGFEM_ESTATE, "precond_apply: multi-index set changed after precond_setup_global");
+    const int64_t no = ctx->n_owned, ld = ctx->ld, wp = D->T_cols;
+    ColChunks cc;
+    cc.n = D->nranks;
+    for (int q = 0; q <= D->nranks; ++q) cc.off[q] = D->col_off[(size_t)q];
+    const int grid = (int)std::min<int64_t>(148 * 16, (no * (ld / 2) + 255) / 256);
+    k_swap_cols<<<grid, 256, 0, ctx->stream>>>(const_cast<double*>(r), D->d_stage, no, ld, cc, 1);
+    ASG_CUDA(ctx, cudaGetLastError());
+    auto exchange = [&](bool forward) -> int {
+        NCCL_CHECK(ctx, g_nccl.GroupStart());
+        for (int q = 0; q < D->nranks; ++q) {
+            const int64_t wq = D->col_off[(size_t)q + 1] - D->col_off[(size_t)q], nq = D->row_off[(size_t)q + 1] - D->row_off[(size_t)q];
+            double* mine = D->d_stage + no * D->col_off[(size_t)q];  // my rows, columns of rank q
+            double* theirs = D->d_T + D->row_off[(size_t)q] * wp;    // rows of rank q, my columns
+            if (q == D->rank) {
+                if (wp > 0)
+                    ASG_CUDA(ctx, cudaMemcpyAsync(forward ? theirs : mine, forward ? mine : theirs, sizeof(double) * (size_t)(no * wp),
+                                                  cudaMemcpyDeviceToDevice, ctx->stream));
+                continue;
+            }
+            if (forward) {
+                if (no * wq > 0) NCCL_CHECK(ctx, g_nccl.Send(mine, (size_t)(no * wq), NCCL_FLOAT64, q, D->comm, ctx->stream));
+                if (nq * wp > 0) NCCL_CHECK(ctx, g_nccl.Recv(theirs, (size_t)(nq * wp), NCCL_FLOAT64, q, D->comm, ctx->stream));
+            } else {
+                if (nq * wp > 0) NCCL_CHECK(ctx, g_nccl.Send(theirs, (size_t)(nq * wp), NCCL_FLOAT64, q, D->comm, ctx->stream));
+                if (no * wq > 0) NCCL_CHECK(ctx, g_nccl.Recv(mine, (size_t)(no * wq), NCCL_FLOAT64, q, D->comm, ctx->stream));
+            }
+        }
+        NCCL_CHECK(ctx, g_nccl.GroupEnd());
+        return 0;
+    };
+    int rc = exchange(true);
+    if (rc) return rc;
+    if (wp > 0 && (rc = precond_apply_plan(ctx, D->gprec, D->d_T, D->d_T, D->n_global, wp, D->d_gbmask))) return rc;
+    if ((rc = exchange(false))) return rc;
+    k_swap_cols<<<grid, 256, 0, ctx->stream>>>(z, D->d_stage, no, ld, cc, 0);
+    ASG_CUDA(ctx, cudaGetLastError());
+    // rows beyond the owned ones (halo) carry no part of z
+    if (ctx->n > no) ASG_CUDA(ctx, cudaMemsetAsync(z + no * ld, 0, sizeof(double) * (size_t)((ctx->n - no) * ld), ctx->stream));
     return 0;
 }
 

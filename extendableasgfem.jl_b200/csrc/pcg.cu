@@ -112,7 +112,7 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
     PCG_CUDA(cudaMemcpyAsync(r, p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     PCG_RC(vec_axpy(ctx, -1.0, q, r));
     // the reduced system keeps x[bdofs] fixed: residual rows at bdofs are zero by construction
-    PCG_RC(precond_apply(ctx, r, z));
+    PCG_RC(dist_precond_apply(ctx, r, z));
     PCG_CUDA(cudaMemcpyAsync(p, z, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     double rz = 0;
     PCG_RC(dist_dot(ctx, r, z, &rz));
@@ -135,7 +135,7 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
         const double alpha = rz / pq;
         k_update_xr<<<grid, 256, 0, ctx->stream>>>(alpha, p, q, x, r, total);
         tpart.start();
-        PCG_RC(precond_apply(ctx, r, z));
+        PCG_RC(dist_precond_apply(ctx, r, z));
         ms_prec += tpart.stop();
         double rz_new = 0;
         PCG_RC(dist_dot(ctx, r, z, &rz_new));

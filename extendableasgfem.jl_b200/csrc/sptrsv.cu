@@ -63,13 +63,16 @@ struct PrecondPlan {
     int64_t lnz = 0;
 };
 
-void precond_free(asgfem_ctx* ctx) {
-    PrecondPlan* P = ctx->precond;
+void precond_free_plan(PrecondPlan* P) {
     if (!P) return;
     void* ptrs[] = {P->small.blk, P->small.rec, P->d_perm, P->d_work};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     delete P;
+}
+
+void precond_free(asgfem_ctx* ctx) {
+    precond_free_plan(ctx->precond);
     ctx->precond = nullptr;
 }
 
@@ -576,12 +579,25 @@ int precond_setup(asgfem_ctx* ctx) {
             }
         }
     }
-    int rc = cholesky_reduced(ctx->n, ctx->h_rowptr.data(), ctx->h_col.data(), k0.data(), ctx->h_bmask.data(),
-                              xy.empty() ? nullptr : xy.data(), 256, F, err);
+    PrecondPlan* P = nullptr;
+    int rc = precond_build(ctx, ctx->n, ctx->h_rowptr.data(), ctx->h_col.data(), k0.data(), ctx->h_bmask.data(),
+                           xy.empty() ? nullptr : xy.data(), &P);
+    if (rc) return rc;
+    ctx->precond = P;
+    return 0;
+}
+
+// Factorises the Dirichlet-reduced matrix (rows / columns with bmask != 0 eliminated) on the host and uploads the sweep tasks.
+// Used for the matrix of this context (precond_setup) and for the GLOBAL mean matrix of a row-sharded run (dist.cu).
+int precond_build(asgfem_ctx* ctx, int64_t nfull, const int64_t* rowptr, const int32_t* col, const double* k0,
+                  const uint8_t* bmask, const double* xy, PrecondPlan** out) {
+    *out = nullptr;
+    CholFactor F;
+    std::string err;
+    int rc = cholesky_reduced(nfull, rowptr, col, k0, bmask, xy, 256, F, err);
     if (rc) return fail(ctx, rc, "precond_setup: " + err);
     ASG_CHECK(ctx, (int64_t)F.Li.size() < (1ll << 31), ASGFEM_EINVAL, "precond_setup: factor with >= 2^31 nonzeros not supported");
     PrecondPlan* P = new PrecondPlan();
-    ctx->precond = P;
     P->nred = F.n;
     P->lnz = (int64_t)F.Li.size();
     const int64_t n = F.n;
@@ -601,18 +617,25 @@ int precond_setup(asgfem_ctx* ctx) {
             }
     }
     rc = build_tasks(ctx, F, cptr, cidx, cval, P->small, P->launches);
-    if (rc) return rc;
-    rc = dev_upload(ctx, &P->d_perm, F.perm);
-    if (rc) return rc;
+    if (!rc) rc = dev_upload(ctx, &P->d_perm, F.perm);
+    if (rc) {
+        precond_free_plan(P);
+        return rc;
+    }
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = P;
     return 0;
 }
 
 int precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
-    PrecondPlan* P = ctx->precond;
-    ASG_CHECK(ctx, P, ASGFEM_ESTATE, "precond_apply: setup missing");
-    const int64_t ld = ctx->ld;
-    ASG_CHECK(ctx, ld > 0, ASGFEM_ESTATE, "precond_apply: multi-indices not set");
+    ASG_CHECK(ctx, ctx->precond, ASGFEM_ESTATE, "precond_apply: setup missing");
+    return precond_apply_plan(ctx, ctx->precond, r, z, ctx->n, ctx->ld, ctx->d_bmask);
+}
+
+// z = K^-1 r for all columns of row-major nrows x ld blocks (ld a multiple of 16); rows with d_bmask != 0 give 0
+int precond_apply_plan(asgfem_ctx* ctx, PrecondPlan* P, const double* r, double* z, int64_t nrows, int64_t ld,
+                       const uint8_t* d_bmask) {
+    ASG_CHECK(ctx, ld > 0 && ld % MT == 0, ASGFEM_ESTATE, "precond_apply: column count must be a positive multiple of 16");
     if (P->work_ld != ld) {  // the factor survives a change of the multi-index set, the work vector does not
         if (P->d_work) cudaFree(P->d_work);
         P->d_work = nullptr;
@@ -630,7 +653,7 @@ int precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
             launch_small<true>(P->launches[k], tiles, ctx->stream, P->d_work, ld, P->small);
     }
     // z may alias r: boundary rows are zeroed first, interior rows are overwritten from the work vector
-    k_zero_masked_rows<<<(unsigned)std::min<int64_t>(ctx->n, 148 * 8), 128, 0, ctx->stream>>>(z, ctx->d_bmask, ctx->n, ld);
+    k_zero_masked_rows<<<(unsigned)std::min<int64_t>(nrows, 148 * 8), 128, 0, ctx->stream>>>(z, d_bmask, nrows, ld);
     if (P->nred > 0) k_scatter_perm<<<blocks, 256, 0, ctx->stream>>>(P->d_work, z, P->d_perm, P->nred, ld);
     ASG_CUDA(ctx, cudaGetLastError());
     return 0;

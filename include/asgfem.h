@@ -243,6 +243,17 @@ int asgfem_comm_init(asgfem_ctx* ctx, int32_t nranks, int32_t rank, const void* 
 int asgfem_comm_destroy(asgfem_ctx* ctx);
 int asgfem_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const int64_t* send_ptr, const int64_t* send_rows,
                     const int64_t* recv_ptr, const int64_t* recv_rows, int64_t interior_row0, int64_t interior_row1);
+/* EXACT mean preconditioner for the sharded solve: MyPreconditionerPrimal (solvers_poisson_primal.jl:30-78) applies
+ * K_0^-1 of the GLOBAL mesh to every mode block, which no rank can do on its row shard.  The modes are independent, so
+ * the library swaps from row shards to MODE shards for the preconditioner: every rank receives all rows of its share of
+ * the device columns (grouped ncclSend/ncclRecv, all-to-all), sweeps them with the factor of the global K_0 and sends the
+ * rows back - the iteration counts of the single-GPU solve are kept at any number of ranks.
+ * The host layer hands the global K_0 (CSC, 1-based, GLOBAL numbering = the owned rows of rank 0, then rank 1, ... in
+ * their local order) and the global Dirichlet dofs to every rank; row_offsets[nranks+1] are the first global rows of the
+ * ranks; coords (2 x n_global, may be NULL) steer the nested dissection.  Every rank factorises on its host cores. */
+int asgfem_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* colptr, const int64_t* rowval,
+                                const double* nzval, int64_t nb, const int64_t* bdofs, const double* coords,
+                                const int64_t* row_offsets);
 /* inner product over the owned rows, summed over all ranks (= asgfem_vec_dot_owned without a communicator) */
 int asgfem_vec_dot_global(asgfem_ctx* ctx, int32_t slot_a, int32_t slot_b, double* out);
 

@@ -23,6 +23,16 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
+        _worker_body(rank, world, q, dist, A, D, oproblem, osolver)
+    except Exception as e:  # the parent must not wait for the timeout
+        import traceback
+        q.put(("error", rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _worker_body(rank, world, q, dist, A, D, oproblem, osolver):
+    if True:
         P = oproblem.poisson_simple(nrefs=3, order=2)
         A0 = sp.csr_matrix(P.A0)
         owner = D.partition_rows(P.n, world)  # index blocks (dof coordinates of P2 face dofs are not needed)
@@ -71,12 +81,44 @@ def _worker(rank, world, port, q):
         sol2 = ctx.vec_download(0).reshape(P.N, L.n_local)[:, :L.n_owned]
         err_sol2 = np.abs(sol2 - refsol[:, L.owned]).max() / np.abs(refsol).max()
         gd = ctx.vec_dot_global(0, 0)
+        # ---- exact (global) mean preconditioner through the mode-shard transposition: the iteration count of the
+        # single-GPU solve, whatever the number of ranks
+        Ls = [D.LocalProblem(r_, owner, A0.indptr, A0.indices) for r_ in range(world)]
+        perm = np.concatenate([l.owned for l in Ls])       # rank-major global numbering
+        inv = np.empty(P.n, dtype=np.int64)
+        inv[perm] = np.arange(P.n)
+        A0g = sp.csc_matrix(sp.csr_matrix(P.A0)[perm][:, perm])
+        A0g.sort_indices()
+        offs = np.concatenate([[0], np.cumsum([l.n_owned for l in Ls])])
+        ctx.precond_setup_global(P.n, A0g.indptr + 1, A0g.indices + 1, A0g.data, inv[P.bdofs] + 1, offs)
+        ctx.vec_zero(0)
+        st3 = ctx.pcg(b0l, 0, 1e-14, 1e-13, 500)
+        sol3 = ctx.vec_download(0).reshape(P.N, L.n_local)[:, :L.n_owned]
+        err_sol3 = np.abs(sol3 - refsol[:, L.owned]).max() / np.abs(refsol).max()
+        # reference iteration count: the same solve on one GPU (rank 0 only)
+        nit1 = -1
+        if rank == 0:
+            c1 = A.Context(rank)
+            c1.set_multiindices(P.family, np.array(P.multi_indices, dtype=np.int64))
+            A0c = sp.csc_matrix(P.A0)
+            A0c.sort_indices()
+            c1.set_pattern_csc(P.n, A0c.indptr.astype(np.int64) + 1, A0c.indices.astype(np.int64) + 1)
+            c1.set_num_stiffness(P.M)
+            c1.set_stiffness(0, A0c.data)
+            for m_, Am_ in enumerate(P.Am, start=1):
+                Am_ = sp.csc_matrix(Am_)
+                Am_.sort_indices()
+                c1.set_stiffness(m_, Am_.data)
+            c1.set_bdofs(P.bdofs + 1)
+            c1.vec_alloc(1)
+            c1.vec_zero(0)
+            nit1 = int(c1.pcg(P.b0, 0, 1e-14, 1e-13, 500)["niter"])
+            c1.close()
         q.put((rank, err_apply, st["niter"], bool(st["solved"]), err_sol, err_apply2, same, int(st2["niter"]), bool(st2["solved"]),
-               err_sol2, gd))
+               err_sol2, int(st3["niter"]), bool(st3["solved"]), err_sol3, nit1, gd))
+        dist.barrier()
         ctx.comm_destroy()
         ctx.close()
-    finally:
-        dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -87,15 +129,28 @@ def test_two_gpu_operator_and_pcg():
     procs = [c.Process(target=_worker, args=(r, world, 29650 + os.getpid() % 300, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = []
+    for _ in range(world):
+        try:
+            r = q.get(timeout=240)
+        except Exception:
+            r = ("error", -1, "timeout waiting for a rank")
+        if r[0] == "error":
+            for p in procs:  # the other rank may be stuck in a collective
+                p.terminate()
+            raise AssertionError(r)
+        res.append(r)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err_apply, niter, solved, err_sol, err_apply2, same, niter2, solved2, err_sol2, gd in res:
+    for rank, err_apply, niter, solved, err_sol, err_apply2, same, niter2, solved2, err_sol2, niter3, solved3, err_sol3, nit1, gd in res:
         assert err_apply < 1e-12, (rank, err_apply)
         assert solved and niter < 300
         assert err_sol < 1e-10, (rank, err_sol)
         assert err_apply2 < 1e-12 and same, (rank, err_apply2, same)
         assert solved2 and niter2 == niter, (niter2, niter)
         assert err_sol2 < 1e-10, (rank, err_sol2)
+        assert solved3 and err_sol3 < 1e-10 and niter3 < niter, (niter3, niter, err_sol3)
+        if nit1 >= 0:
+            assert abs(niter3 - nit1) <= 1, (niter3, nit1)  # exact mean preconditioner: the single-GPU iteration count
     assert res[0][-1] == res[1][-1]  # the all-reduced inner product is the same number on both ranks
