@@ -578,7 +578,7 @@ static int ensure_ready_for_apply(asgfem_ctx* ctx) {
 
 extern "C" int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant) {
     CTX_OR_FAIL(ctx);
-    ASG_CHECK(ctx, variant == 0 || variant == 1 || variant == 7 || variant == 8, ASGFEM_EINVAL, "apply variant must be 0, 1, 7 or 8");
+    ASG_CHECK(ctx, variant == 0 || variant == 1 || variant == 7 || variant == 9, ASGFEM_EINVAL, "apply variant must be 0 (automatic), 1, 7 or 9");
     ctx->apply_variant = variant;
     return 0;
 }

@@ -1,19 +1,19 @@
 // Fused SGFE operator  Y = sum_m (G_m (x) K_m) X  with Dirichlet rows zeroed
 // (LinearAlgebra.mul!(Ax, S::MySystemPrimal, x), src/modelproblems/solvers_poisson_primal.jl:86-124).
 //
-// Two hand-written kernels for sm_100a:
+// Three hand-written kernels for sm_100a:
 //
-//  variant 8  k_apply_mma      (apply_mma.cu) the default: block products on the fp64 MMA path, mailbox exchange.
+//  variant 7  k_apply_ts2      (apply_ts2.cu) packed mode-stationary DFMA kernel: lanes own modes, X rows of the dof row in
+//             registers; the fastest kernel where its plan fits (N <= 2048 modes, M <= 63, short rows).
+//  variant 9  k_apply_blk      (apply_blk.cu) block products on the fp64 MMA path (DMMA m8n8k4) with a list exchange:
+//             any N (passes over the mode blocks), rows of up to 24 entries (P2), any M <= 255.
 //  variant 1  k_apply_gather   thread = (dof row i, device column c); walks the neighbour list of the column's mode in the
 //             reference's accumulation order (nu ascending, direction ascending) and reads X and K_m through L1/L2.
-//             Simple and exact in ordering: the in-library cross-check of the default kernel, and the fallback for
-//             shapes its plan declines (rows with more than 24 entries, more than 4096 modes per 16 warps, ...).
+//             Simple and exact in ordering: the in-library cross-check of the other kernels and the last fallback.
 //
-// Both kernels never touch uncoupled (m, nu) pairs of the reference loop; the MMA kernel evaluates 8 x 8 blocks of pairs.
-// The kernels work in DEVICE COLUMN space: column c of every vector holds mode ctx->h_inv[c] (padding columns: none);
-// the coupling lists uploaded by asgfem_set_multiindices are relabelled accordingly.
-// The round-1 kernels (row-block tiled, row-resident dst-/direction-major, mode-stationary DFMA variants 6/7) are retired:
-// their measurements are kept in DESIGN.md section 4 and profiles/r01_*.
+// No kernel touches uncoupled (m, nu) pairs of the reference loop.  All kernels work in DEVICE COLUMN space: column c of
+// every vector holds mode ctx->h_inv[c] (padding columns: none, kept at zero); the coupling lists uploaded by
+// asgfem_set_multiindices are relabelled accordingly.  Retired kernels and their measurements: profiles/README.md.
 #include <algorithm>
 
 #include "common.h"
@@ -49,7 +49,7 @@ void apply_free_plan(asgfem_ctx* ctx) {
 }
 
 int apply_build_plan(asgfem_ctx* ctx) {
-    int rc = apply_mma_build(ctx);
+    int rc = apply_blk_build(ctx);
     if (rc) return rc;
     rc = apply_ts2_build(ctx);
     if (rc) return rc;
@@ -65,12 +65,12 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_
     }
     r1 = std::min(r1, nrows_all);
     int variant = ctx->apply_variant;
-    // automatic choice by measurement (config 4, B200): packed mode-stationary DFMA kernel 51 ms, MMA kernel 72-82 ms
-    if (variant == 0) variant = apply_ts2_preferred(ctx) ? 7 : apply_mma_usable(ctx) ? 8 : 1;
+    // automatic choice by measurement (config 4, B200): packed mode-stationary DFMA kernel 51 ms, block kernel 55 ms
+    if (variant == 0) variant = apply_ts2_preferred(ctx) ? 7 : apply_blk_usable(ctx) ? 9 : 1;
     if (r1 <= r0) return 0;
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (variant == 8) {
-        int rc = apply_mma_launch(ctx, x, y, r0, r1);
+    if (variant == 9) {
+        int rc = apply_blk_launch(ctx, x, y, r0, r1);
         if (rc) return rc;
     } else if (variant == 7) {
         int rc = apply_ts2_launch(ctx, x, y, r0, r1);

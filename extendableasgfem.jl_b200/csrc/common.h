@@ -179,10 +179,12 @@ int apply_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0 = 0, in
 // apply_mma.cu
 int apply_mma_layout(asgfem_ctx* ctx);   // mode-side plan + device column order (set_multiindices)
 bool apply_mma_layout_ok(asgfem_ctx* ctx);
-int apply_mma_build(asgfem_ctx* ctx);    // kernel tables (first apply after the pattern is known)
-bool apply_mma_usable(asgfem_ctx* ctx);
 void apply_mma_free(asgfem_ctx* ctx);
-int apply_mma_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
+// apply_blk.cu (kernel tables live inside the MmaPlan)
+int apply_blk_build(asgfem_ctx* ctx);
+bool apply_blk_usable(asgfem_ctx* ctx);
+void apply_blk_free(asgfem_ctx* ctx);
+int apply_blk_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, int64_t r1);
 // apply_ts2.cu
 int apply_ts2_build(asgfem_ctx* ctx);
 void apply_ts2_free(asgfem_ctx* ctx);

@@ -87,7 +87,7 @@ def test_vector_layout_roundtrip_and_random_fill(c1):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [1, 7, 8])
+@pytest.mark.parametrize("variant", [1, 7, 9])
 def test_apply_matches_oracle(c1, mid, variant):
     for P in (c1, mid):
         ctx = make_ctx(P)
@@ -117,13 +117,13 @@ def test_apply_matches_oracle_on_bench_sets(nx, order, N, M):
     ctx = make_ctx(P)
     ran = []
     from asgfem_b200 import _lib
-    for variant in (0, 1, 7, 8):
+    for variant in (0, 1, 7, 9):
         ctx.set_apply_variant(variant)
         ctx.vec_upload(0, x)
         try:
             ctx.apply(0, 1)
         except _lib.AsgfemError as e:  # a kernel may decline a shape; it must say so
-            assert variant in (7, 8) and "not available" in str(e)
+            assert variant in (7, 9) and "not available" in str(e)
             continue
         ran.append(variant)
         got = ctx.vec_download(1)
@@ -133,7 +133,7 @@ def test_apply_matches_oracle_on_bench_sets(nx, order, N, M):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 7, 8])
+@pytest.mark.parametrize("variant", [0, 1, 7, 9])
 def test_apply_host_pipelined_row_blocks(c1, mid, variant, monkeypatch):
     """The mul! seam overlaps upload / operator / download block by block; small blocks force the multi-block
     schedule, including rows whose columns live in much later blocks (P2 edge dofs of config 1)."""
@@ -167,7 +167,7 @@ def test_apply_random_sets_lshape(family):
         S = osolver.SystemPrimal(P.A0, P.Am, P.G, P.bdofs, P.N)
         x = rng.standard_normal(P.n * P.N)
         ref = S.mul(x)
-        for variant in (1, 7, 8):
+        for variant in (1, 7, 9):
             ctx = make_ctx(P)
             ctx.set_apply_variant(variant)
             assert relerr(ctx.apply_host(x), ref) < TOL_APPLY
@@ -187,7 +187,7 @@ def test_apply_linearity_at_scale():
     ctx.vec_alloc(5)
     ctx.vec_fill_random(0, 1)
     ctx.vec_fill_random(1, 2)
-    ctx.set_apply_variant(8)
+    ctx.set_apply_variant(9)
     ctx.apply(0, 2)
     ctx.apply(1, 3)
     ctx.vec_axpy(0.5, 1, 0)      # x0 += 0.5 x1
@@ -203,7 +203,7 @@ def test_apply_linearity_at_scale():
     ctx.close()
 
 
-@pytest.mark.parametrize("ts_variant", [7, 8])
+@pytest.mark.parametrize("ts_variant", [7, 9])
 @pytest.mark.parametrize("nx,M,N", [(129, 20, 2000), (65, 12, 700), (97, 6, 100), (33, 20, 2048), (33, 40, 1500), (33, 3, 35)])
 def test_apply_mode_stationary_matches_gather_at_bench_shape(nx, M, N, ts_variant):
     """The benchmark's mode set (2000 graded-lex modes in 20 dimensions) and other shapes (wide: M > 31, tiny, one and two
@@ -227,6 +227,31 @@ def test_apply_mode_stationary_matches_gather_at_bench_shape(nx, M, N, ts_varian
     assert np.array_equal(b, c)
     assert relerr(b, a) < TOL_APPLY
     assert np.max(np.abs(b - a)) <= 1e-12 * np.max(np.abs(a))
+    ctx.close()
+
+
+@pytest.mark.parametrize("order,nx,M,N", [(2, 17, 20, 5000), (2, 33, 8, 300), (1, 17, 70, 600)])
+def test_apply_block_kernel_long_rows_and_many_modes(order, nx, M, N):
+    """Shapes only the block kernel (variant 9) covers: P2 rows (up to 24 entries -> 6 k-steps), the mode count of config 5
+    (N = 5000 -> several passes per dof row, lists in global memory), more than 63 directions.  Reference: the gather
+    kernel (variant 1)."""
+    g = A.structured_unitsquare(nx)
+    fes = A.FESpace(g, order)
+    modes = A.graded_lex_multiindices(M, N)
+    TB = A.TensorizedBasis(A.LegendrePolynomials, modes)
+    sol = A.SGFEVector(fes, TB)
+    A.setup_device_problem(sol, A.StochasticCoefficientCosinus(tau=0.9, decay=2, mean=1, maxm=M))
+    ctx = TB.ctx
+    ctx.vec_alloc(4)
+    ctx.vec_fill_random(0, 11)
+    ctx.set_apply_variant(1)
+    ctx.apply(0, 1)
+    ctx.set_apply_variant(9)
+    ctx.apply(0, 2)
+    ctx.apply(0, 3)
+    a, b, c = ctx.vec_download(1), ctx.vec_download(2), ctx.vec_download(3)
+    assert np.array_equal(b, c)
+    assert relerr(b, a) < TOL_APPLY
     ctx.close()
 
 
@@ -371,7 +396,7 @@ def test_edge_cases_and_error_codes():
     ctx = make_ctx(P1)
     x = np.random.default_rng(0).standard_normal(P1.n)
     S = osolver.SystemPrimal(P1.A0, P1.Am, P1.G, P1.bdofs, 1)
-    for variant in (1, 7, 8):
+    for variant in (1, 7, 9):
         ctx.set_apply_variant(variant)
         assert relerr(ctx.apply_host(x), S.mul(x)) < TOL_APPLY
     sol = np.zeros(P1.n)
@@ -454,7 +479,7 @@ def test_operator_properties_p2_hermite_at_scale():
     ctx.vec_upload(0, x)
     ctx.vec_upload(1, y)
     ref = None
-    for variant in (1, 7, 8):
+    for variant in (1, 7, 9):
         ctx.set_apply_variant(variant)
         try:
             ctx.apply(0, 2)
@@ -517,7 +542,7 @@ def test_logprimal_seam_matches_oracle(order):
     x = np.random.default_rng(4).standard_normal(P.n * P.N)
     y = S.mul(x)
     ctx = TB.ctx
-    for variant in (1, 7, 8):
+    for variant in (1, 7, 9):
         ctx.set_apply_variant(variant)
         assert relerr(ctx.apply_host(x), y) < TOL_APPLY
     # the preconditioner is A^-1 per mode, not (A + N0)^-1
