@@ -163,6 +163,132 @@ def build_local_problem(A, rank, world):
     return ctx, fes, n_owned, halo
 
 
+def build_strip_problem(A, rank, world, order, ncx, ncy_per_rank, n_modes, device):
+    """Row shard of a structured P1 / P2 problem for configs[4]: a mesh of ncx x (ncy_per_rank * world) squares, rank r owns
+    the dofs with y-index in [r, r + 1) * ncy_per_rank (half-integer rows of edge dofs: the half row above an owned node
+    row).  Local numbering: owned dofs sorted by (y, x) - the rows along the lower cut first, along the upper cut last,
+    so that the rows without halo columns are one contiguous range -, then the lower halo, then the upper halo.
+    Returns (ctx, n_owned, n_local, send, recv, interior)."""
+    nx = ncx + 1
+    ny_tot = ncy_per_rank * world + 1
+    y_lo, y_hi = rank * ncy_per_rank, (rank + 1) * ncy_per_rank  # owned node rows [y_lo, y_hi); the last rank also owns the top row
+    if rank == world - 1:
+        y_hi = ny_tot
+    ext_lo, ext_hi = max(y_lo - 1, 0), min(y_hi + 1, ny_tot)
+    hx, hy = 1.0 / ncx, 1.0 / (ny_tot - 1)
+    g = A.structured_unitsquare(nx, ext_hi - ext_lo, 0.0, 1.0, ext_lo * hy, (ext_hi - 1) * hy)
+    fes = A.FESpace(g, order)
+    # integer dof positions in half-mesh-width units
+    ix = np.rint(g.coords[:, 0] / hx).astype(np.int64)
+    iy = np.rint(g.coords[:, 1] / hy).astype(np.int64)
+    px, py = 2 * ix, 2 * iy
+    if order == 2:
+        fa, fb = g.facenodes[:, 0], g.facenodes[:, 1]
+        px = np.concatenate([px, ix[fa] + ix[fb]])
+        py = np.concatenate([py, iy[fa] + iy[fb]])
+    owned = (py >= 2 * y_lo) & (py < 2 * y_hi)
+    lower = py < 2 * y_lo
+    upper = py >= 2 * y_hi
+    key = py * (4 * nx) + px
+    order_of = lambda mask: np.where(mask)[0][np.argsort(key[mask], kind="stable")]  # noqa: E731
+    o_own, o_lo, o_up = order_of(owned), order_of(lower), order_of(upper)
+    perm = np.concatenate([o_own, o_lo, o_up])  # new -> old
+    new_of_old = np.empty(fes.ndofs, dtype=np.int64)
+    new_of_old[perm] = np.arange(fes.ndofs)
+    n_owned, n_local = len(o_own), fes.ndofs
+    celldofs = new_of_old[fes.celldofs]
+    pxn, pyn = px[perm], py[perm]
+    on_bnd = (pxn == 0) | (pxn == 2 * ncx) | (pyn == 0) | (pyn == 2 * (ny_tot - 1))
+    bdofs = np.where(on_bnd)[0]
+    ctx = A.Context(device)
+    ctx.set_multiindices(A.LEGENDRE, np.array(A.graded_lex_multiindices(M_KLE, n_modes), dtype=np.int64))
+    Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=M_KLE)
+    ctx.set_mesh(g.coords, g.cellnodes + 1)
+    ctx.set_space(order, fes.ndofs, celldofs + 1)
+    ctx.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
+    xref, w = A.quadrature_rule(2 * order)
+    ctx.assemble_stiffness(M_KLE, xref, w)
+    send, recv = {}, {}
+    if world > 1:
+        ctx.set_bdofs(np.union1d(bdofs, np.arange(n_owned, n_local)) + 1)
+        ctx.set_owned_rows(n_owned)
+        # my lower halo = the dofs of the lower neighbour with y in [y_lo - 1, y_lo); it needs my dofs with y = y_lo as its
+        # upper halo.  Both sides list the rows in (y, x) order.
+        if y_lo > 0:
+            recv[rank - 1] = n_owned + np.arange(len(o_lo))
+            send[rank - 1] = np.where(pyn[:n_owned] == 2 * y_lo)[0]
+        if y_hi < ny_tot:
+            recv[rank + 1] = n_owned + len(o_lo) + np.arange(len(o_up))
+            send[rank + 1] = np.where(pyn[:n_owned] >= 2 * (y_hi - 1))[0]
+    else:
+        ctx.set_bdofs(bdofs + 1)
+    i0 = int(np.sum(pyn[:n_owned] == 2 * y_lo)) if y_lo > 0 else 0
+    i1 = int(np.sum(pyn[:n_owned] < 2 * (y_hi - 1))) if y_hi < ny_tot else n_owned
+    return ctx, n_owned, n_local, send, recv, (i0, i1)
+
+
+def run_c5_leg(A, torch, dist, rank, world, local_rank, steps, warmup, variant):
+    """configs[4]: 1024 x 1024 squares, P2 (4,198,401 dofs) x 5000 multi-indices, M = 20, row-partitioned over the ranks
+    (STRONG scaling: the mesh is fixed).  Operator applications with NCCL halo exchange; the symmetry defect
+    <A u, v> - <u, A v> checks the sharded operator.  Three vectors per rank (42 GB each at 4 GPUs)."""
+    ncx = int(os.environ.get("ASGFEM_BENCH_C5_NX", 1024))
+    n_modes = int(os.environ.get("ASGFEM_BENCH_C5_N", 5000))
+    order = int(os.environ.get("ASGFEM_BENCH_C5_ORDER", 2))
+    assert ncx % world == 0
+    t0 = time.perf_counter()
+    ctx, n_owned, n_local, send, recv, interior = build_strip_problem(A, rank, world, order, ncx, ncx // world, n_modes, local_rank)
+    ctx.set_apply_variant(variant)
+    nnz = len(ctx.pattern_csc()[1])
+    if world > 1:
+        ids = [A.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+        ctx.set_halo(send, recv, *interior)
+    ctx.vec_alloc(3)
+    t_setup = time.perf_counter() - t0
+    ctx.vec_fill_random(0, SEED + 300 + rank)
+    ctx.vec_fill_random(2, SEED + 400 + rank)
+    ctx.apply(0, 1)  # u = A x1 (vanishes on the Dirichlet rows)
+    ctx.apply(2, 0)  # v = A x2
+    ctx.apply(1, 2)  # A u
+    d1 = ctx.vec_dot_global(2, 0) if world > 1 else ctx.vec_dot(2, 0)
+    ctx.apply(0, 2)  # A v
+    d2 = ctx.vec_dot_global(1, 2) if world > 1 else ctx.vec_dot(1, 2)
+    sym = abs(d1 - d2) / max(abs(d1), 1e-300)
+    for _ in range(warmup):
+        ctx.apply(0, 1)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kms = []
+    for _ in range(steps):
+        ctx.apply(0, 1)
+        kms.append(ctx.last_apply_ms())
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    step_ms = (time.perf_counter() - t0) * 1e3 / steps
+    tot = torch.tensor([float(n_owned), float(nnz), 0.0], dtype=torch.float64, device="cuda")
+    mx = torch.tensor([step_ms, t_setup], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(tot)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    n_glob, nnz_glob = int(tot[0].item()), int(tot[1].item())
+    step_ms = float(mx[0].item())
+    ctx.close()
+    peak, _ = measured_peaks()
+    bytes_alg = algorithmic_bytes(n_glob, n_modes, nnz_glob, M_KLE)
+    return {"workload": f"configs[4]: {ncx}x{ncx} squares, P{order} ({n_glob:,} dofs) x {n_modes} graded-lex Legendre "
+                        f"multi-indices, M={M_KLE}, row-partitioned over {world} GPUs (strong scaling), NCCL halo exchange inside the library",
+            "n_gpus": world, "n_dofs": n_glob, "n_multiindices": n_modes, "nnz_pattern_sum_over_ranks": nnz_glob,
+            "ms_per_step": round(step_ms, 3), "value": round(n_glob * n_modes / (step_ms * 1e-3) / 1e9, 3), "unit": "GDoF/s",
+            "kernel_ms_rank0": round(float(np.mean(kms)), 3), "steps": steps, "warmup": warmup,
+            "sharded_operator_symmetry_defect": sym, "setup_s_max": round(float(mx[1].item()), 1),
+            "hbm_roofline_frac_aggregate": round(bytes_alg / (step_ms * 1e-3) / 1e9 / (peak * world), 4),
+            "kernel_variant": variant or "auto"}
+
+
 def run_gpu(args):
     import torch
 
@@ -361,6 +487,17 @@ def run_gpu(args):
         except Exception as e:  # pragma: no cover
             if rank == 0:
                 out["pcg"] = {"error": str(e)[:200]}
+    # ---- configs[4] (4.2M P2 dofs x 5000 modes) row-partitioned over the ranks: needs >= 4 GPUs for three vectors ---------
+    if world >= int(os.environ.get("ASGFEM_BENCH_C5_MINWORLD", 4)) and not args.no_c5:
+        try:
+            ctx.close()  # frees the vectors of the weak-scaling problem
+            ctx = None
+            c5 = run_c5_leg(A, torch, dist, rank, world, local_rank, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), args.variant)
+            if rank == 0:
+                out["c5"] = c5
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                out["c5"] = {"error": str(e)[:300]}
     if rank == 0 and world == 1 and not args.no_pcg:
         try:
             t0 = time.perf_counter()
@@ -480,7 +617,8 @@ def run_gpu(args):
                 out["pcg"]["cpu_solve"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(out))
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if dist:
         dist.destroy_process_group()
 
@@ -664,8 +802,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] leg (runs at >= 4 GPUs)")
     ap.add_argument("--variant", type=int, default=0,
-                    help="operator kernel: 0 auto, 1 reference-order gather, 7 packed mode-stationary DFMA, 8 block MMA")
+                    help="operator kernel: 0 auto, 1 reference-order gather, 7 packed mode-stationary DFMA, 9 block MMA with list exchange")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcg", action="store_true")
