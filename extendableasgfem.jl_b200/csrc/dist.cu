@@ -214,23 +214,21 @@ int dist_apply(asgfem_ctx* ctx, const double* x, double* y) {
     if (rc) return rc;
     const int nn = (int)D->nb_rank.size();
     const int64_t N = ctx->N, ns = D->send_ptr[nn], nr = D->recv_ptr[nn];
+    // Exchange first, then ONE operator launch over all owned rows.  The halo rows are 2 x 16 MB per neighbour (about
+    // 0.1 ms over NVLink); overlapping them with the interior rows (round 1 / first version of this function: NCCL on a
+    // second stream, three operator launches) cost more than it hid: the persistent operator CTAs and the NCCL CTAs compete
+    // for the SMs, a rank whose NCCL kernel starts late stalls its neighbours' kernels, and every extra launch pays the
+    // 222 KB table prologue - 73.8 ms per step at 4 GPUs against 51.5 ms for the launch alone.
     if ((rc = vec_pack_rows(ctx, x, ns, D->d_send_rows, D->d_sendbuf))) return rc;
-    ASG_CUDA(ctx, cudaEventRecord(D->packed, ctx->stream));
-    ASG_CUDA(ctx, cudaStreamWaitEvent(D->cs, D->packed, 0));
     NCCL_CHECK(ctx, g_nccl.GroupStart());
     for (int k = 0; k < nn; ++k) {
         const int64_t s0 = D->send_ptr[k], s1 = D->send_ptr[k + 1], r0 = D->recv_ptr[k], r1 = D->recv_ptr[k + 1];
-        if (s1 > s0) NCCL_CHECK(ctx, g_nccl.Send(D->d_sendbuf + s0 * N, (size_t)((s1 - s0) * N), NCCL_FLOAT64, D->nb_rank[k], D->comm, D->cs));
-        if (r1 > r0) NCCL_CHECK(ctx, g_nccl.Recv(D->d_recvbuf + r0 * N, (size_t)((r1 - r0) * N), NCCL_FLOAT64, D->nb_rank[k], D->comm, D->cs));
+        if (s1 > s0) NCCL_CHECK(ctx, g_nccl.Send(D->d_sendbuf + s0 * N, (size_t)((s1 - s0) * N), NCCL_FLOAT64, D->nb_rank[k], D->comm, ctx->stream));
+        if (r1 > r0) NCCL_CHECK(ctx, g_nccl.Recv(D->d_recvbuf + r0 * N, (size_t)((r1 - r0) * N), NCCL_FLOAT64, D->nb_rank[k], D->comm, ctx->stream));
     }
     NCCL_CHECK(ctx, g_nccl.GroupEnd());
-    ASG_CUDA(ctx, cudaEventRecord(D->received, D->cs));
-    if (D->interior1 > D->interior0 && (rc = apply_launch(ctx, x, y, D->interior0, D->interior1))) return rc;
-    ASG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, D->received, 0));
     if ((rc = vec_unpack_rows(ctx, const_cast<double*>(x), nr, D->d_recv_rows, D->d_recvbuf))) return rc;
-    if (D->interior0 > 0 && (rc = apply_launch(ctx, x, y, 0, D->interior0))) return rc;
-    if (D->interior1 < ctx->n_owned && (rc = apply_launch(ctx, x, y, D->interior1, ctx->n_owned))) return rc;
-    return 0;
+    return apply_launch(ctx, x, y, 0, ctx->n_owned);
 }
 
 // sum over the ranks of the inner product on the owned rows (deterministic local part + ncclAllReduce)

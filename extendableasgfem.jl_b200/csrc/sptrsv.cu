@@ -371,19 +371,22 @@ __global__ void __launch_bounds__(WMAX <= 24 ? SWEEP_THREADS : SWEEP_THREADS / 2
 k_small_step(double* __restrict__ W, int64_t ld, SmallDev S, int t0, int t1) {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
     __shared__ __align__(8) unsigned long long sweep_bars[2 * (SWEEP_THREADS / 32)];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // the tasks of a launch are independent: gridDim.y CTAs share them (mode shards of a multi-GPU solve have few mode
+    // tiles; without the split only ld / 16 SMs would work)
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) + blockIdx.y * (blockDim.x >> 5), nwarps = (blockDim.x >> 5) * gridDim.y;
+    const int lwarp = threadIdx.x >> 5;
     if (t0 + warp >= t1) return;
     const int half = lane >> 4;
     const int64_t mode0 = (int64_t)blockIdx.x * MT, mode = mode0 + (lane & (MT - 1));
     const int bufB = small_buf_bytes(WMAX);
     if (lane == 0) {
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * warp);
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * lwarp);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    SmallPipe<BWD> pipe{S, sweep_smem + (size_t)warp * 2 * bufB, (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * warp),
+    SmallPipe<BWD> pipe{S, sweep_smem + (size_t)lwarp * 2 * bufB, (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * lwarp),
                         bufB,  t1, nwarps, lane};
     pipe.start(t0 + warp);
     for (int t = t0 + warp; t < t1; t += nwarps) {
@@ -400,22 +403,25 @@ k_small_step(double* __restrict__ W, int64_t ld, SmallDev S, int t0, int t1) {
 }
 
 template <int WMAX, bool BWD>
-void launch_small_k(int t0, int t1, int tiles, cudaStream_t st, double* W, int64_t ld, const SmallDev& S) {
+void launch_small_k(int t0, int t1, int tiles, int split, cudaStream_t st, double* W, int64_t ld, const SmallDev& S) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_small_step<WMAX, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
         configured = true;
     }
-    k_small_step<WMAX, BWD><<<tiles, WMAX <= 24 ? SWEEP_THREADS : SWEEP_THREADS / 2, SWEEP_SMEM, st>>>(W, ld, S, t0, t1);
+    constexpr int threads = WMAX <= 24 ? SWEEP_THREADS : SWEEP_THREADS / 2;
+    const int ntask = t1 - t0, per = threads / 32;
+    const int gy = std::max(1, std::min(split, (ntask + per - 1) / per));  // no CTAs without a task
+    k_small_step<WMAX, BWD><<<dim3((unsigned)tiles, (unsigned)gy), threads, SWEEP_SMEM, st>>>(W, ld, S, t0, t1);
 }
 
 template <bool BWD>
-void launch_small(const std::array<int, 3>& L, int tiles, cudaStream_t st, double* W, int64_t ld, const SmallDev& S) {
+void launch_small(const std::array<int, 3>& L, int tiles, int split, cudaStream_t st, double* W, int64_t ld, const SmallDev& S) {
     switch (L[2]) {
-        case 8: launch_small_k<8, BWD>(L[0], L[1], tiles, st, W, ld, S); break;
-        case 16: launch_small_k<16, BWD>(L[0], L[1], tiles, st, W, ld, S); break;
-        case 24: launch_small_k<24, BWD>(L[0], L[1], tiles, st, W, ld, S); break;
-        default: launch_small_k<32, BWD>(L[0], L[1], tiles, st, W, ld, S); break;
+        case 8: launch_small_k<8, BWD>(L[0], L[1], tiles, split, st, W, ld, S); break;
+        case 16: launch_small_k<16, BWD>(L[0], L[1], tiles, split, st, W, ld, S); break;
+        case 24: launch_small_k<24, BWD>(L[0], L[1], tiles, split, st, W, ld, S); break;
+        default: launch_small_k<32, BWD>(L[0], L[1], tiles, split, st, W, ld, S); break;
     }
 }
 
@@ -647,10 +653,12 @@ int precond_apply_plan(asgfem_ctx* ctx, PrecondPlan* P, const double* r, double*
     if (P->nred > 0) {
         k_gather_perm<<<blocks, 256, 0, ctx->stream>>>(r, P->d_work, P->d_perm, P->nred, ld);
         const int tiles = (int)(ld / MT);  // all device columns (the column order is private, padding columns hold zeros)
+        int split = std::max(1, 148 / tiles);  // CTAs per mode tile: fill the SMs when there are few tiles
+        if (const char* e = getenv("ASGFEM_SWEEP_SPLIT")) split = std::max(1, atoi(e));
         for (size_t k = 0; k < P->launches.size(); ++k)
-            launch_small<false>(P->launches[k], tiles, ctx->stream, P->d_work, ld, P->small);
+            launch_small<false>(P->launches[k], tiles, split, ctx->stream, P->d_work, ld, P->small);
         for (size_t k = P->launches.size(); k-- > 0;)
-            launch_small<true>(P->launches[k], tiles, ctx->stream, P->d_work, ld, P->small);
+            launch_small<true>(P->launches[k], tiles, split, ctx->stream, P->d_work, ld, P->small);
     }
     // z may alias r: boundary rows are zeroed first, interior rows are overwritten from the work vector
     k_zero_masked_rows<<<(unsigned)std::min<int64_t>(nrows, 148 * 8), 128, 0, ctx->stream>>>(z, d_bmask, nrows, ld);
