@@ -15,10 +15,12 @@
 //   forward   z_T = inv(L_TT) w_T,  W[A(T)] -= P z_T        (one fp64 RED per target row and mode: sibling subtrees
 //                                                            update the same ancestor rows concurrently)
 //   backward  y_T = inv(L_TT)^T (z_T - P^T y_A(T))           (pull: no atomics)
-// A warp takes a task; its two half-warps hold the 16 modes of the tile (lane = mode), the <= 32 values of the
-// sub-block per mode live in registers, and the factor data - read exactly once per CTA, no reuse - is streamed
-// through a per-warp two-stage pipeline of bulk copies (cp.async.bulk + mbarrier) into shared memory, from where it is
-// read with half-warp-uniform 16-byte loads: no column indices, no shuffles in the inner loops.
+// A warp takes a task and 16 modes (two MMA column tiles of 8).  All products are DMMA m8n8k4: the factor data (read exactly
+// once per CTA, no reuse; streamed through a per-warp two-stage pipeline of bulk copies, cp.async.bulk + mbarrier, into
+// shared memory) gives the A fragments - 8 rows x 4 columns, row stride = 4 mod 8 doubles so that a half-warp touches 16
+// different banks, the backward sweep reads the same records transposed -, the 32 x 16 values of the sub-block are B
+// fragments / accumulators in registers (fragment orders converted with shuffles).  Round 1 used one DFMA per lane and
+// 16-byte operand load (lane = mode): 127 ms per application at config 4, issue / latency bound.
 // Sub-blocks with many panel rows (the separators near the root) are split into a solve-only task and push-only tasks
 // of <= 64 rows, so that the few large separators at the top of the tree keep all warps of the CTA busy.
 // Launches are ordered by (tree depth descending, separator chunk, sub-block, phase): everything inside one launch is
@@ -111,20 +113,19 @@ __global__ void k_zero_masked_rows(double* __restrict__ z, const uint8_t* __rest
     }
 }
 
-// offset of row r in the pair-packed inverse triangle: rows 2i and 2i+1 both hold 2i+2 entries
-__host__ __device__ __forceinline__ int inv_row_off(int r) {
-    const int i = r >> 1;
-    return 2 * i * (i + 1) + (r & 1) * (2 * i + 2);
-}
-// record geometry for a sub-block of width w staged through buffers of `buf` bytes
+// Record geometry for a sub-block of width w staged through buffers of `buf` bytes.  Rows of the inverse and of the panel
+// have the stride wp doubles with wp % 16 in {4, 12}: the MMA fragment loads (8 rows x 4 columns, or 4 rows x 8 columns
+// for the transposed use of the backward sweep) then touch 16 different 8-byte banks per half-warp.
 struct SmallGeom {
-    int wp, invB, R, arB, chunkB;  // even(w), bytes of the inverse, rows per chunk, bytes of a chunk's row list, full chunk
+    int wp, wr, invB, R, arB, chunkB;  // row stride, rows of the inverse (w rounded up to 8), bytes of the inverse, panel rows
+                                       // per chunk (multiple of 8), bytes of a chunk's row list, bytes of a full chunk
 };
 __host__ __device__ __forceinline__ SmallGeom small_geom(int w, int buf, int kind) {
     SmallGeom g;
-    g.wp = (w + 1) & ~1;
-    g.invB = kind == TASK_PUSH_ONLY ? 0 : inv_row_off(g.wp) * 8;
-    g.R = ((buf - 16) / (g.wp * 8 + 4)) & ~1;
+    g.wr = (w + 7) & ~7;
+    g.wp = g.wr + 4;  // 12, 20, 28, 36: a fragment never reads past the end of a row
+    g.invB = kind == TASK_PUSH_ONLY ? 0 : g.wr * g.wp * 8;
+    g.R = ((buf - 16) / (g.wp * 8 + 4)) & ~7;
     g.arB = (4 * g.R + 15) & ~15;
     g.chunkB = g.arB + g.R * g.wp * 8;
     return g;
@@ -194,7 +195,7 @@ struct SmallPipe {
             bytes = pg.invB;
         } else {
             src += pg.invB + (int64_t)pc * pg.chunkB;
-            const int r = min(pg.R, pb.nA - pc * pg.R);
+            const int r = (min(pg.R, pb.nA - pc * pg.R) + 7) & ~7;  // the record pads the last chunk with zero rows
             bytes = pg.arB + r * pg.wp * 8;
         }
         if (lane == 0) {
@@ -227,140 +228,177 @@ struct SmallPipe {
     }
 };
 
-__device__ __forceinline__ double2 lds_d2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void sw_dmma(double2& c, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void red_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
-// forward task: z_T = inv(L_TT) w_T (unless push-only: W already holds z_T), then W[A(T)] -= P z_T
-template <int WMAX>
-__device__ __forceinline__ void small_fwd(const SmallBlk b, SmallPipe<false>& pipe, double* __restrict__ W, int64_t ld, int64_t mode,
-                                          int half) {
-    const int w = b.w;
-    double* wt = W + (int64_t)b.j0 * ld + mode;
-    double v[WMAX];
+// C fragments (rows 8 i + g, modes 8 j + 2 t, 2 t + 1) -> B fragments (rows 4 s + t, mode 8 j + g) of the same 32 x 16 block:
+// the value of B lane (g, t) sits in C lane (g' = 4 (s & 1) + t, t' = g >> 1), component g & 1 of m-tile s >> 1
+template <int NQ>
+__device__ __forceinline__ void c_to_b(const double2 (&c)[(NQ + 1) / 2][2], double (&bq)[NQ][2], int g, int t) {
 #pragma unroll
-    for (int c = 0; c < WMAX; ++c) v[c] = c < w ? __ldcg(wt + (int64_t)c * ld) : 0.0;
-    if (b.kind != TASK_PUSH_ONLY) {
-        const double* inv = reinterpret_cast<const double*>(pipe.acquire());
-        // rows from the bottom up: row r needs v[c <= r] only, so z overwrites v in place (one register array)
+    for (int s = 0; s < NQ; ++s) {
+        const int src = 4 * (4 * (s & 1) + t) + (g >> 1);
 #pragma unroll
-        for (int i = WMAX / 2 - 1; i >= 0; --i) {
-            if (2 * i < w) {  // warp-uniform
-                const double* row = inv + 2 * i * (i + 1) + half * (2 * i + 2);  // half h computes row 2i + h
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                for (int q = 0; q <= i; ++q) {
-                    const double2 l = lds_d2(row + 2 * q);
-                    a0 = fma(l.x, v[2 * q], a0);
-                    a1 = fma(l.y, v[2 * q + 1], a1);
-                }
-                const double mine = a0 + a1;
-                const double other = __shfl_xor_sync(0xffffffffu, mine, 16);
-                v[2 * i] = half ? other : mine;
-                v[2 * i + 1] = half ? mine : other;
-                if (2 * i + half < w) wt[(int64_t)(2 * i + half) * ld] = mine;
-            }
+        for (int j = 0; j < 2; ++j) {
+            const double x = __shfl_sync(0xffffffffu, c[s >> 1][j].x, src), y = __shfl_sync(0xffffffffu, c[s >> 1][j].y, src);
+            bq[s][j] = (g & 1) ? y : x;
         }
     }
-    double(&z)[WMAX] = v;
-    const SmallGeom g = small_geom(w, pipe.bufB, b.kind);
-    for (int a0r = 0; a0r < b.nA; a0r += g.R) {
-        const unsigned char* ch = pipe.acquire();
-        const int32_t* ar = reinterpret_cast<const int32_t*>(ch);
-        const double* P = reinterpret_cast<const double*>(ch + g.arB);
-        const int nr = min(g.R, b.nA - a0r);
-        for (int p = 0; p < nr; p += 2) {
-            const bool ok = p + half < nr;
-            const int a = ok ? p + half : nr - 1;
-            const int64_t r = ar[a];
-            const double* prow = P + a * g.wp;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+}
+
+// The sweeps work on 16 modes per warp (two MMA column tiles of 8); lane = (g, t) = (lane / 4, lane % 4).
+// forward task: z_T = inv(L_TT) w_T (unless push-only: W already holds z_T), then W[A(T)] -= P z_T.  All products are
+// DMMA m8n8k4: A fragments (inverse / panel, 8 rows x 4 columns) from the staged record, B fragments (4 rows x 8 modes)
+// in registers, accumulators in fragment order; the updates of the target rows are fp64 REDs (other tasks share them).
+template <int WMAX>
+__device__ __forceinline__ void small_fwd(const SmallBlk b, SmallPipe<false>& pipe, double* __restrict__ W, int64_t ld, int64_t mode0,
+                                          int lane) {
+    constexpr int NQ = WMAX / 4, NM = WMAX / 8;
+    const int g = lane >> 2, t = lane & 3;
+    const int w = b.w;
+    const SmallGeom geo = small_geom(w, pipe.bufB, b.kind);
+    double* wt = W + (int64_t)b.j0 * ld + mode0;
+    double zb[NQ][2];  // B fragments of w_T, later of z_T
 #pragma unroll
-            for (int q = 0; q < WMAX / 2; q += 2) {
-                if (2 * q < w) {
-                    const double2 l = lds_d2(prow + 2 * q);
-                    s0 = fma(l.x, z[2 * q], s0);
-                    s1 = fma(l.y, z[2 * q + 1], s1);
+    for (int s = 0; s < NQ; ++s)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) zb[s][j] = 4 * s + t < w ? __ldcg(wt + (int64_t)(4 * s + t) * ld + 8 * j + g) : 0.0;
+    if (b.kind != TASK_PUSH_ONLY) {
+        const double* inv = reinterpret_cast<const double*>(pipe.acquire()) + g * geo.wp + t;
+        double2 zc[NM][2];
+#pragma unroll
+        for (int i = 0; i < NM; ++i) {
+            zc[i][0] = zc[i][1] = make_double2(0.0, 0.0);
+            if (8 * i < w) {  // warp-uniform
+#pragma unroll
+                for (int s = 0; s <= 2 * i + 1; ++s) {
+                    const double a = inv[8 * i * geo.wp + 4 * s];
+                    sw_dmma(zc[i][0], a, zb[s][0]);
+                    sw_dmma(zc[i][1], a, zb[s][1]);
                 }
-                if (2 * q + 2 < w) {
-                    const double2 l = lds_d2(prow + 2 * q + 2);
-                    s2 = fma(l.x, z[2 * q + 2], s2);
-                    s3 = fma(l.y, z[2 * q + 3], s3);
+                if (8 * i + g < w) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) *reinterpret_cast<double2*>(wt + (int64_t)(8 * i + g) * ld + 8 * j + 2 * t) = zc[i][j];
                 }
             }
-            if (ok) atomicAdd(W + r * ld + mode, -((s0 + s1) + (s2 + s3)));  // other tasks share these target rows
+        }
+        c_to_b<NQ>(zc, zb, g, t);
+    }
+    for (int a0r = 0; a0r < b.nA; a0r += geo.R) {
+        const unsigned char* ch = pipe.acquire();
+        const int32_t* ar = reinterpret_cast<const int32_t*>(ch);
+        const double* P = reinterpret_cast<const double*>(ch + geo.arB) + g * geo.wp + t;
+        const int nr = min(geo.R, b.nA - a0r);
+        for (int p = 0; p < nr; p += 8) {
+            const int64_t r = p + g < nr ? ar[p + g] : -1;
+            double2 c0 = make_double2(0.0, 0.0), c1 = c0;
+            const double* pr = P + p * geo.wp;
+#pragma unroll
+            for (int s = 0; s < NQ; ++s) {
+                if (4 * s < w) {
+                    const double a = pr[4 * s];
+                    sw_dmma(c0, a, zb[s][0]);
+                    sw_dmma(c1, a, zb[s][1]);
+                }
+            }
+            if (r >= 0) {
+                double* dst = W + r * ld + mode0 + 2 * t;
+                red_add_f64(dst, -c0.x);
+                red_add_f64(dst + 1, -c0.y);
+                red_add_f64(dst + 8, -c1.x);
+                red_add_f64(dst + 9, -c1.y);
+            }
         }
     }
 }
 
 // backward task: y_T = inv(L_TT)^T (z_T - P^T y_A(T)); a pull-only task (part of the panel rows of a split sub-block)
-// subtracts its share of P^T y_A from z_T in memory and leaves the solve to the solve-only task of the next launch
+// subtracts its share of P^T y_A from z_T in memory and leaves the solve to the solve-only task of the next launch.
+// The transposed products read the same records: A fragment element (column 8 i + g, row 4 s + t) of P^T or inv^T.
 template <int WMAX>
-__device__ __forceinline__ void small_bwd(const SmallBlk b, SmallPipe<true>& pipe, double* __restrict__ W, int64_t ld, int64_t mode,
-                                          int half) {
+__device__ __forceinline__ void small_bwd(const SmallBlk b, SmallPipe<true>& pipe, double* __restrict__ W, int64_t ld, int64_t mode0,
+                                          int lane) {
+    constexpr int NQ = WMAX / 4, NM = WMAX / 8;
+    const int g = lane >> 2, t = lane & 3;
     const int w = b.w;
-    double* wt = W + (int64_t)b.j0 * ld + mode;
-    double acc[WMAX];
+    const SmallGeom geo = small_geom(w, pipe.bufB, b.kind);
+    double* wt = W + (int64_t)b.j0 * ld + mode0;
+    double2 acc[NM][2];
 #pragma unroll
-    for (int c = 0; c < WMAX; ++c) acc[c] = 0.0;
-    const SmallGeom g = small_geom(w, pipe.bufB, b.kind);
-    for (int a0r = 0; a0r < b.nA; a0r += g.R) {
+    for (int i = 0; i < NM; ++i) acc[i][0] = acc[i][1] = make_double2(0.0, 0.0);
+    for (int a0r = 0; a0r < b.nA; a0r += geo.R) {
         const unsigned char* ch = pipe.acquire();
         const int32_t* ar = reinterpret_cast<const int32_t*>(ch);
-        const double* P = reinterpret_cast<const double*>(ch + g.arB);
-        const int nr = min(g.R, b.nA - a0r);
-        // y values two pairs ahead of their use: the gathers from W are the only global loads of this loop
-        auto load_y = [&](int p) {
-            const int a = p + half;
-            return a < nr ? __ldcg(W + (int64_t)ar[a] * ld + mode) : 0.0;
+        const double* P = reinterpret_cast<const double*>(ch + geo.arB) + t * geo.wp + g;
+        const int nr = min(geo.R, b.nA - a0r);
+        // y values (B fragments: row 4 s + t of the chunk, mode 8 j + g) one step ahead of their use
+        auto load_y = [&](int p, double (&y)[2]) {
+            const bool ok = p + t < nr;
+            const double* src = W + (int64_t)(ok ? ar[p + t] : 0) * ld + mode0 + g;
+            y[0] = ok ? __ldcg(src) : 0.0;
+            y[1] = ok ? __ldcg(src + 8) : 0.0;
         };
-        double y0 = load_y(0), y1 = load_y(2);
-        for (int p = 0; p < nr; p += 2) {
-            const double y = y0;
-            y0 = y1;
-            y1 = load_y(p + 4);
-            const int a = min(p + half, nr - 1);
-            const double* prow = P + a * g.wp;
+        double y0[2], y1[2];
+        load_y(0, y0);
+        for (int p = 0; p < nr; p += 4) {
+            load_y(p + 4, y1);
+            const double* pr = P + p * geo.wp;
 #pragma unroll
-            for (int q = 0; q < WMAX / 2; ++q) {
-                if (2 * q < w) {
-                    const double2 l = lds_d2(prow + 2 * q);
-                    acc[2 * q] = fma(l.x, y, acc[2 * q]);
-                    acc[2 * q + 1] = fma(l.y, y, acc[2 * q + 1]);
+            for (int i = 0; i < NM; ++i) {
+                if (8 * i < w) {
+                    const double a = pr[8 * i];
+                    sw_dmma(acc[i][0], a, y0[0]);
+                    sw_dmma(acc[i][1], a, y0[1]);
                 }
             }
+            y0[0] = y1[0], y0[1] = y1[1];
         }
     }
     if (b.kind == TASK_PUSH_ONLY) {
 #pragma unroll
-        for (int i = 0; i < WMAX / 2; ++i) {
-            if (2 * i < w) {
-                const double s0 = acc[2 * i] + __shfl_xor_sync(0xffffffffu, acc[2 * i], 16);
-                const double s1 = acc[2 * i + 1] + __shfl_xor_sync(0xffffffffu, acc[2 * i + 1], 16);
-                if (2 * i + half < w) atomicAdd(wt + (int64_t)(2 * i + half) * ld, -(half ? s1 : s0));
+        for (int i = 0; i < NM; ++i) {
+            if (8 * i + g < w) {
+                double* dst = wt + (int64_t)(8 * i + g) * ld + 2 * t;
+                red_add_f64(dst, -acc[i][0].x);
+                red_add_f64(dst + 1, -acc[i][0].y);
+                red_add_f64(dst + 8, -acc[i][1].x);
+                red_add_f64(dst + 9, -acc[i][1].y);
             }
         }
         return;
     }
-    double(&t)[WMAX] = acc;  // t = z_T - P^T y_A, in place
+    // t = z_T - P^T y_A in fragment order, then as B fragments
 #pragma unroll
-    for (int c = 0; c < WMAX; ++c) {
-        const double own = c < w ? __ldcg(wt + (int64_t)c * ld) : 0.0;
-        t[c] = own - (acc[c] + __shfl_xor_sync(0xffffffffu, acc[c], 16));
+    for (int i = 0; i < NM; ++i) {
+        const bool ok = 8 * i + g < w;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double2 z = ok ? __ldcg(reinterpret_cast<const double2*>(wt + (int64_t)(8 * i + g) * ld + 8 * j + 2 * t)) : make_double2(0.0, 0.0);
+            acc[i][j].x = z.x - acc[i][j].x;
+            acc[i][j].y = z.y - acc[i][j].y;
+        }
     }
-    const double* inv = reinterpret_cast<const double*>(pipe.acquire());
+    double tb[NQ][2];
+    c_to_b<NQ>(acc, tb, g, t);
+    const double* inv = reinterpret_cast<const double*>(pipe.acquire()) + t * geo.wp + g;
 #pragma unroll
-    for (int i = 0; i < WMAX / 2; ++i) {
-        if (2 * i < w) {
-            // y_r = sum_{c >= r} inv[c][r] t[c], r = 2i + half; inv[2i][2i+1] is a stored zero
-            const double* col = inv + 2 * i + half;
-            double a0 = 0.0, a1 = 0.0;
+    for (int i = 0; i < NM; ++i) {
+        if (8 * i < w) {
+            double2 c0 = make_double2(0.0, 0.0), c1 = c0;
 #pragma unroll
-            for (int j = i; j < WMAX / 2; ++j) {
-                if (2 * j < w) {
-                    a0 = fma(col[2 * j * (j + 1)], t[2 * j], a0);
-                    a1 = fma(col[2 * j * (j + 1) + 2 * j + 2], t[2 * j + 1], a1);
+            for (int s = 2 * i; s < NQ; ++s) {
+                if (4 * s < w) {
+                    const double a = inv[4 * s * geo.wp + 8 * i];  // inv[column 4 s + t][row 8 i + g]
+                    sw_dmma(c0, a, tb[s][0]);
+                    sw_dmma(c1, a, tb[s][1]);
                 }
             }
-            if (2 * i + half < w) wt[(int64_t)(2 * i + half) * ld] = a0 + a1;
+            if (8 * i + g < w) {
+                *reinterpret_cast<double2*>(wt + (int64_t)(8 * i + g) * ld + 2 * t) = c0;
+                *reinterpret_cast<double2*>(wt + (int64_t)(8 * i + g) * ld + 8 + 2 * t) = c1;
+            }
         }
     }
 }
@@ -376,8 +414,7 @@ k_small_step(double* __restrict__ W, int64_t ld, SmallDev S, int t0, int t1) {
     const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) + blockIdx.y * (blockDim.x >> 5), nwarps = (blockDim.x >> 5) * gridDim.y;
     const int lwarp = threadIdx.x >> 5;
     if (t0 + warp >= t1) return;
-    const int half = lane >> 4;
-    const int64_t mode0 = (int64_t)blockIdx.x * MT, mode = mode0 + (lane & (MT - 1));
+    const int64_t mode0 = (int64_t)blockIdx.x * MT;
     const int bufB = small_buf_bytes(WMAX);
     if (lane == 0) {
         const unsigned bar = (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * lwarp);
@@ -396,9 +433,9 @@ k_small_step(double* __restrict__ W, int64_t ld, SmallDev S, int t0, int t1) {
             if (lane < nb.w) prefetch_l2(W + (int64_t)(nb.j0 + lane) * ld + mode0);
         }
         if constexpr (BWD)
-            small_bwd<WMAX>(b, pipe, W, ld, mode, half);
+            small_bwd<WMAX>(b, pipe, W, ld, mode0, lane);
         else
-            small_fwd<WMAX>(b, pipe, W, ld, mode, half);
+            small_fwd<WMAX>(b, pipe, W, ld, mode0, lane);
     }
 }
 
@@ -492,13 +529,13 @@ int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>
                 T.key = base_key + phase;
                 T.wclass = wcl;
                 size_t bytes = (size_t)g.invB;
-                for (int c = 0; c < nch; ++c) bytes += (size_t)g.arB + (size_t)std::min(g.R, cnt - c * g.R) * g.wp * 8;
+                for (int c = 0; c < nch; ++c) bytes += (size_t)g.arB + (size_t)((std::min(g.R, cnt - c * g.R) + 7) & ~7) * g.wp * 8;
                 rec.resize(rec.size() + bytes, 0);
                 unsigned char* base = rec.data() + T.blk.rec_off;
                 if (g.invB) {
                     double* inv = reinterpret_cast<double*>(base);
                     for (int32_t r = 0; r < w; ++r)
-                        for (int32_t c = 0; c <= r; ++c) inv[(size_t)inv_row_off(r) + c] = X[(size_t)r * w + c];
+                        for (int32_t c = 0; c <= r; ++c) inv[(size_t)r * g.wp + c] = X[(size_t)r * w + c];
                 }
                 for (int a = a_lo; a < a_hi; ++a) {
                     unsigned char* ch = base + g.invB + (size_t)((a - a_lo) / g.R) * g.chunkB;
