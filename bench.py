@@ -447,19 +447,21 @@ def run_gpu(args):
             # (natural numbering = the rank-major order of the strips), factorised by every rank on its host cores
             gg = A.structured_unitsquare(NX, NX * world)
             gf = A.FESpace(gg, 1)
-            c0 = A.Context(local_rank)
-            c0.set_multiindices(A.LEGENDRE, np.zeros((1, 1), dtype=np.int64))
-            Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=M_KLE)
-            c0.set_mesh(gg.coords, gg.cellnodes + 1)
-            c0.set_space(1, gf.ndofs, gf.celldofs + 1)
-            c0.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
-            xr_, w_ = A.quadrature_rule(2)
-            c0.assemble_stiffness(0, xr_, w_)
-            gcp, grv = c0.pattern_csc()
-            gnz = c0.get_stiffness(0)
-            c0.close()
+            gcp = grv = gnz = None
+            if rank == 0:  # rank 0 factorises and broadcasts the sweep tasks (asgfem_precond_setup_global is collective)
+                c0 = A.Context(local_rank)
+                c0.set_multiindices(A.LEGENDRE, np.zeros((1, 1), dtype=np.int64))
+                Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=M_KLE)
+                c0.set_mesh(gg.coords, gg.cellnodes + 1)
+                c0.set_space(1, gf.ndofs, gf.celldofs + 1)
+                c0.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
+                xr_, w_ = A.quadrature_rule(2)
+                c0.assemble_stiffness(0, xr_, w_)
+                gcp, grv = c0.pattern_csc()
+                gnz = c0.get_stiffness(0)
+                c0.close()
             ctx.precond_setup_global(gf.ndofs, gcp, grv, gnz, gf.bdofs + 1, np.arange(world + 1) * n_owned,
-                                     coords=np.ascontiguousarray(gg.coords))
+                                     coords=np.ascontiguousarray(gg.coords) if rank == 0 else None)
             del gcp, grv, gnz
             t_fac = time.perf_counter() - t0
             ctx.vec_alloc(1)
@@ -483,7 +485,7 @@ def run_gpu(args):
                               "note": "sharded PCG inside the library with the EXACT mean preconditioner: per application the "
                                       "ranks swap from row shards to mode shards (all-to-all over NCCL), sweep their modes with the "
                                       "factor of the global K_0 and swap back; halo exchange + all-reduce over NCCL; factor_s_host "
-                                      "= assembly + host Cholesky of the global K_0 on every rank; max over ranks"}
+                                      "= assembly + host Cholesky of the global K_0 on rank 0 + NCCL broadcast of the sweep tasks; max over ranks"}
         except Exception as e:  # pragma: no cover
             if rank == 0:
                 out["pcg"] = {"error": str(e)[:200]}

@@ -165,12 +165,16 @@ class Context:
         return out.value
 
     def precond_setup_global(self, n_global, colptr, rowval, nzval, bdofs1, row_offsets, coords=None):
-        """Global K_0 (CSC, 1-based, rank-major global numbering) for the exact mean preconditioner of a sharded solve."""
-        cp, rv, nz = _i64(colptr), _i64(rowval), _f64(nzval)
+        """Global K_0 (CSC, 1-based, rank-major global numbering) for the exact mean preconditioner of a sharded solve.
+        Collective: rank 0 factorises and broadcasts the sweep tasks, so the matrix (and coords) may be None elsewhere."""
+        cp = _i64(colptr) if colptr is not None else None
+        rv = _i64(rowval) if rowval is not None else None
+        nz = _f64(nzval) if nzval is not None else None
         bd, ro = _i64(bdofs1), _i64(row_offsets)
         xy = _f64(coords) if coords is not None else None
-        self._ck(self.lib.asgfem_precond_setup_global(self.h, int(n_global), _ptr(cp), _ptr(rv), _ptr(nz), len(bd), _ptr(bd),
-                                                      _ptr(xy) if xy is not None else None, _ptr(ro)))
+        opt = lambda a: _ptr(a) if a is not None else None  # noqa: E731
+        self._ck(self.lib.asgfem_precond_setup_global(self.h, int(n_global), opt(cp), opt(rv), opt(nz), len(bd), _ptr(bd),
+                                                      opt(xy), _ptr(ro)))
 
     def vec_dot_global(self, a, b):
         out = C.c_double()

@@ -226,6 +226,10 @@ int precond_build(asgfem_ctx* ctx, int64_t nfull, const int64_t* rowptr, const i
 int precond_apply_plan(asgfem_ctx* ctx, PrecondPlan* P, const double* r, double* z, int64_t nrows, int64_t ld,
                        const uint8_t* d_bmask);
 void precond_free_plan(PrecondPlan* P);
+void precond_plan_sizes(const PrecondPlan* P, int64_t sizes[5]);
+int precond_plan_alloc(asgfem_ctx* ctx, const int64_t sizes[5], PrecondPlan** out);
+void precond_plan_buffers(PrecondPlan* P, void* ptrs[3], size_t bytes[3]);
+int* precond_plan_launches(PrecondPlan* P);
 // pcg.cu
 int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, double rtol, int64_t itmax,
               asgfem_stats* stats);

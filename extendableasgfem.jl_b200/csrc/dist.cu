@@ -31,6 +31,7 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
@@ -64,6 +65,7 @@ bool load_nccl(std::string& err) {
     BIND(Send, "ncclSend");
     BIND(Recv, "ncclRecv");
     BIND(AllReduce, "ncclAllReduce");
+    BIND(Broadcast, "ncclBroadcast");
     BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
     g_nccl.ok = true;
@@ -275,31 +277,13 @@ int dist_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* 
     DistPlan* D = dp_of(ctx);
     ASG_CHECK(ctx, D && D->comm, ASGFEM_ESTATE, "precond_setup_global: asgfem_comm_init first");
     ASG_CHECK(ctx, ctx->ld > 0 && ctx->n_owned > 0, ASGFEM_ESTATE, "precond_setup_global: multi-indices and owned rows first");
-    ASG_CHECK(ctx, n_global > 0 && colptr && rowval && nzval && row_offsets, ASGFEM_EINVAL, "precond_setup_global: bad arguments");
+    ASG_CHECK(ctx, n_global > 0 && row_offsets && (D->rank != 0 || (colptr && rowval && nzval)), ASGFEM_EINVAL,
+              "precond_setup_global: bad arguments (the matrix is needed on rank 0 only)");
     ASG_CHECK(ctx, D->nranks <= 32, ASGFEM_EINVAL, "precond_setup_global: at most 32 ranks");
     D->row_off.assign(row_offsets, row_offsets + D->nranks + 1);
     ASG_CHECK(ctx, D->row_off[0] == 0 && D->row_off[D->nranks] == n_global &&
                        D->row_off[D->rank + 1] - D->row_off[D->rank] == ctx->n_owned,
               ASGFEM_EINVAL, "precond_setup_global: row offsets do not match the owned rows of this rank");
-    // CSC (1-based) -> CSR (0-based); K_0 is symmetric, the transposition keeps the routine general
-    const int64_t nnz = colptr[n_global] - 1;
-    std::vector<int64_t> rp((size_t)n_global + 1, 0);
-    for (int64_t p = 0; p < nnz; ++p) {
-        ASG_CHECK(ctx, rowval[p] >= 1 && rowval[p] <= n_global, ASGFEM_EINVAL, "precond_setup_global: row index out of range");
-        rp[(size_t)rowval[p]]++;
-    }
-    for (int64_t i = 0; i < n_global; ++i) rp[(size_t)i + 1] += rp[(size_t)i];
-    std::vector<int32_t> ci((size_t)nnz);
-    std::vector<double> cv((size_t)nnz);
-    {
-        std::vector<int64_t> fill(rp.begin(), rp.end() - 1);
-        for (int64_t c = 0; c < n_global; ++c)
-            for (int64_t p = colptr[c] - 1; p < colptr[c + 1] - 1; ++p) {
-                const int64_t at = fill[(size_t)(rowval[p] - 1)]++;
-                ci[(size_t)at] = (int32_t)c;
-                cv[(size_t)at] = nzval[p];
-            }
-    }
     std::vector<uint8_t> bm((size_t)n_global, 0);
     for (int64_t k = 0; k < nb; ++k) {
         ASG_CHECK(ctx, bdofs[k] >= 1 && bdofs[k] <= n_global, ASGFEM_EINVAL, "precond_setup_global: boundary dof out of range");
@@ -307,8 +291,68 @@ int dist_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* 
     }
     precond_free_plan(D->gprec);
     D->gprec = nullptr;
-    int rc = precond_build(ctx, n_global, rp.data(), ci.data(), cv.data(), bm.data(), coords, &D->gprec);
-    if (rc) return rc;
+    // Rank 0 factorises (all host cores to itself; with every rank factorising the same matrix the host Cholesky of the 4 M
+    // dof mean matrix took 47 s at 4 GPUs) and hands the sweep tasks to the others over NCCL.
+    int rc = 0;
+    int64_t hdr[6] = {0, 0, 0, 0, 0, 0};  // sizes + status of the root
+    if (D->rank == 0) {
+        // CSC (1-based) -> CSR (0-based); K_0 is symmetric, the transposition keeps the routine general
+        const int64_t nnz = colptr[n_global] - 1;
+        std::vector<int64_t> rp((size_t)n_global + 1, 0);
+        bool ok = true;
+        for (int64_t p = 0; p < nnz; ++p) {
+            if (rowval[p] < 1 || rowval[p] > n_global) {
+                ok = false;
+                break;
+            }
+            rp[(size_t)rowval[p]]++;
+        }
+        if (!ok) {
+            rc = fail(ctx, ASGFEM_EINVAL, "precond_setup_global: row index out of range");
+        } else {
+            for (int64_t i = 0; i < n_global; ++i) rp[(size_t)i + 1] += rp[(size_t)i];
+            std::vector<int32_t> ci((size_t)nnz);
+            std::vector<double> cv((size_t)nnz);
+            std::vector<int64_t> fill(rp.begin(), rp.end() - 1);
+            for (int64_t c = 0; c < n_global; ++c)
+                for (int64_t p = colptr[c] - 1; p < colptr[c + 1] - 1; ++p) {
+                    const int64_t at = fill[(size_t)(rowval[p] - 1)]++;
+                    ci[(size_t)at] = (int32_t)c;
+                    cv[(size_t)at] = nzval[p];
+                }
+            rc = precond_build(ctx, n_global, rp.data(), ci.data(), cv.data(), bm.data(), coords, &D->gprec);
+        }
+        if (!rc) precond_plan_sizes(D->gprec, hdr);
+        hdr[5] = rc;
+    }
+    {
+        // header and launch list through a small device buffer
+        int64_t* d_hdr = nullptr;
+        ASG_CUDA(ctx, cudaMalloc((void**)&d_hdr, sizeof(hdr)));
+        ASG_CUDA(ctx, cudaMemcpyAsync(d_hdr, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_CHECK(ctx, g_nccl.Broadcast(d_hdr, d_hdr, sizeof(hdr), 0 /* ncclInt8 */, 0, D->comm, ctx->stream));
+        ASG_CUDA(ctx, cudaMemcpyAsync(hdr, d_hdr, sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream));
+        ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_hdr);
+        if (hdr[5] != 0) return D->rank == 0 ? rc : fail(ctx, (int)hdr[5], "precond_setup_global: the factorisation on rank 0 failed");
+        if (D->rank != 0 && (rc = precond_plan_alloc(ctx, hdr, &D->gprec))) return rc;
+        void* ptrs[3];
+        size_t bytes[3];
+        precond_plan_buffers(D->gprec, ptrs, bytes);
+        for (int k = 0; k < 3; ++k)
+            if (bytes[k] > 0) NCCL_CHECK(ctx, g_nccl.Broadcast(ptrs[k], ptrs[k], bytes[k], 0 /* ncclInt8 */, 0, D->comm, ctx->stream));
+        const size_t lbytes = sizeof(int) * 3 * (size_t)hdr[4];
+        if (lbytes > 0) {
+            int* d_l = nullptr;
+            ASG_CUDA(ctx, cudaMalloc((void**)&d_l, lbytes));
+            if (D->rank == 0) ASG_CUDA(ctx, cudaMemcpyAsync(d_l, precond_plan_launches(D->gprec), lbytes, cudaMemcpyHostToDevice, ctx->stream));
+            NCCL_CHECK(ctx, g_nccl.Broadcast(d_l, d_l, lbytes, 0 /* ncclInt8 */, 0, D->comm, ctx->stream));
+            if (D->rank != 0) ASG_CUDA(ctx, cudaMemcpyAsync(precond_plan_launches(D->gprec), d_l, lbytes, cudaMemcpyDeviceToHost, ctx->stream));
+            ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(d_l);
+        }
+        ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     D->n_global = n_global;
     if ((rc = dev_upload(ctx, &D->d_gbmask, bm))) return rc;
     // column chunks: tiles of 16 device columns dealt out evenly

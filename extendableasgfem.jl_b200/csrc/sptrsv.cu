@@ -63,6 +63,7 @@ struct PrecondPlan {
     double* d_work = nullptr;  // nred x work_ld, (re)allocated by precond_apply when the column count of the vectors changes
     int64_t work_ld = 0;
     int64_t lnz = 0;
+    int64_t rec_bytes = 0;  // size of small.rec
 };
 
 void precond_free_plan(PrecondPlan* P) {
@@ -466,7 +467,7 @@ void launch_small(const std::array<int, 3>& L, int tiles, int split, cudaStream_
 // inverse triangle and the dense panel) in launch order.  Lp/Li/Lx: rows of L; cptr/cidx/cval: columns of L with
 // ascending rows.
 int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx,
-                const std::vector<double>& cval, SmallDev& D, std::vector<std::array<int, 3>>& launches) {
+                const std::vector<double>& cval, SmallDev& D, std::vector<std::array<int, 3>>& launches, int64_t* rec_bytes) {
     const int64_t n = F.n;
     struct Task {
         SmallBlk blk;
@@ -583,6 +584,7 @@ int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>
     int rc = 0;
     rc |= dev_upload(ctx, &D.blk, blk);
     rc |= dev_upload(ctx, &D.rec, rec);
+    *rec_bytes = (int64_t)rec.size();
     if (rc) return rc;
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
     return 0;
@@ -659,7 +661,7 @@ int precond_build(asgfem_ctx* ctx, int64_t nfull, const int64_t* rowptr, const i
                 cval[at] = F.Lx[p];
             }
     }
-    rc = build_tasks(ctx, F, cptr, cidx, cval, P->small, P->launches);
+    rc = build_tasks(ctx, F, cptr, cidx, cval, P->small, P->launches, &P->rec_bytes);
     if (!rc) rc = dev_upload(ctx, &P->d_perm, F.perm);
     if (rc) {
         precond_free_plan(P);
@@ -669,6 +671,29 @@ int precond_build(asgfem_ctx* ctx, int64_t nfull, const int64_t* rowptr, const i
     *out = P;
     return 0;
 }
+
+// ---- hand-over of a built plan to other ranks (dist.cu: rank 0 factorises the global mean matrix, the others receive the
+//      sweep tasks over NCCL).  sizes = {nred, lnz, task count, record bytes, launch count}; buffers = {perm (int32 x nred),
+//      task descriptors (32 bytes each), records}; the launch list (3 ints per launch) travels as host data.
+void precond_plan_sizes(const PrecondPlan* P, int64_t sizes[5]) {
+    sizes[0] = P->nred, sizes[1] = P->lnz, sizes[2] = P->small.nblocks, sizes[3] = P->rec_bytes, sizes[4] = (int64_t)P->launches.size();
+}
+int precond_plan_alloc(asgfem_ctx* ctx, const int64_t sizes[5], PrecondPlan** out) {
+    PrecondPlan* P = new PrecondPlan();
+    P->nred = sizes[0], P->lnz = sizes[1], P->small.nblocks = (int)sizes[2], P->rec_bytes = sizes[3];
+    P->launches.assign((size_t)sizes[4], {0, 0, 0});
+    *out = P;
+    ASG_CUDA(ctx, cudaMalloc((void**)&P->d_perm, sizeof(int32_t) * (size_t)std::max<int64_t>(sizes[0], 1)));
+    ASG_CUDA(ctx, cudaMalloc((void**)&P->small.blk, sizeof(SmallBlk) * (size_t)std::max<int64_t>(sizes[2], 1)));
+    ASG_CUDA(ctx, cudaMalloc((void**)&P->small.rec, (size_t)std::max<int64_t>(sizes[3], 16)));
+    return 0;
+}
+void precond_plan_buffers(PrecondPlan* P, void* ptrs[3], size_t bytes[3]) {
+    ptrs[0] = P->d_perm, bytes[0] = sizeof(int32_t) * (size_t)P->nred;
+    ptrs[1] = P->small.blk, bytes[1] = sizeof(SmallBlk) * (size_t)P->small.nblocks;
+    ptrs[2] = P->small.rec, bytes[2] = (size_t)P->rec_bytes;
+}
+int* precond_plan_launches(PrecondPlan* P) { return P->launches.empty() ? nullptr : P->launches[0].data(); }
 
 int precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
     ASG_CHECK(ctx, ctx->precond, ASGFEM_ESTATE, "precond_apply: setup missing");

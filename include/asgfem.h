@@ -250,7 +250,8 @@ int asgfem_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const
  * rows back - the iteration counts of the single-GPU solve are kept at any number of ranks.
  * The host layer hands the global K_0 (CSC, 1-based, GLOBAL numbering = the owned rows of rank 0, then rank 1, ... in
  * their local order) and the global Dirichlet dofs to every rank; row_offsets[nranks+1] are the first global rows of the
- * ranks; coords (2 x n_global, may be NULL) steer the nested dissection.  Every rank factorises on its host cores. */
+ * ranks; coords (2 x n_global, may be NULL) steer the nested dissection.  COLLECTIVE: rank 0 factorises on its host cores and
+ * broadcasts the sweep tasks over NCCL, so colptr / rowval / nzval / coords are read on rank 0 only (may be NULL elsewhere). */
 int asgfem_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* colptr, const int64_t* rowval,
                                 const double* nzval, int64_t nb, const int64_t* bdofs, const double* coords,
                                 const int64_t* row_offsets);
