@@ -62,7 +62,10 @@ int32_t bfs(const Graph& g, int32_t start, const std::vector<int32_t>& tag, int3
 void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double* xy, std::vector<BlockRec>& blocks,
                        int32_t max_block) {
     const int32_t n = g.n;
-    const int32_t LEAF = 24;
+    // dissection stops at subdomains of <= LEAF unknowns (dense leaf blocks of the triangular sweeps); measured at config 4
+    // (sptrsv.cu, DMMA sweeps): see DESIGN.md section 5
+    int32_t LEAF = 24;
+    if (const char* e = std::getenv("ASGFEM_CHOL_LEAF")) LEAF = std::max(4, atoi(e));
     perm.assign((size_t)n, -1);
     std::vector<int32_t> tag((size_t)n, 0), dist((size_t)n, -1), bfsout, lv, tmp;
     struct Task {

@@ -36,6 +36,7 @@ constexpr int MT = 16;           // modes per CTA (half a warp wide)
 constexpr int SMALL_W = 32;      // columns of a sub-block
 constexpr int SPLIT_ROWS = 64;   // panel rows of a push-only task; panels up to this size stay fused with their solve
 constexpr int SWEEP_THREADS = 512;
+constexpr int TOP_DEPTH = 5;     // dissection levels 0..5 (<= 63 separators): launches merged into one kernel per sweep
 constexpr int SWEEP_SMEM = 224 * 1024;  // two staging buffers per warp
 
 enum : int32_t { TASK_FUSED = 0, TASK_SOLVE_ONLY = 1, TASK_PUSH_ONLY = 2 };
@@ -64,11 +65,12 @@ struct PrecondPlan {
     int64_t work_ld = 0;
     int64_t lnz = 0;
     int64_t rec_bytes = 0;  // size of small.rec
+    int* d_launches = nullptr;  // device copy of the launch list (merged launches), made by the first application
 };
 
 void precond_free_plan(PrecondPlan* P) {
     if (!P) return;
-    void* ptrs[] = {P->small.blk, P->small.rec, P->d_perm, P->d_work};
+    void* ptrs[] = {P->small.blk, P->small.rec, P->d_perm, P->d_work, P->d_launches};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     delete P;
@@ -209,9 +211,9 @@ struct SmallPipe {
         }
         advance();
     }
-    __device__ __forceinline__ void start(int t0w) {
+    __device__ __forceinline__ void start(int t0w) {  // first piece of the warp's first task -> the buffer the next acquire uses
         set_task(t0w);
-        issue(0);
+        issue(k & 1u);
     }
     // waits for the next piece in sequence and returns its buffer; the piece after it is put in flight first
     __device__ __forceinline__ const unsigned char* acquire() {
@@ -440,6 +442,60 @@ k_small_step(double* __restrict__ W, int64_t ld, SmallDev S, int t0, int t1) {
     }
 }
 
+// Several consecutive launches of the list in ONE kernel: the mode tiles are independent, so the only synchronisation a
+// launch boundary provides - all tasks of launch l are done before a task of launch l + 1 starts - is needed inside a CTA
+// only, and a block barrier gives it.  The top of the dissection tree is a long chain of small dependent launches (370 per
+// sweep at config 4, 30 us each with a few warps busy); merged they cost a barrier each.
+template <int WMAX, bool BWD>
+__global__ void __launch_bounds__(WMAX <= 24 ? SWEEP_THREADS : SWEEP_THREADS / 2, 1)
+k_small_multi(double* __restrict__ W, int64_t ld, SmallDev S, const int* __restrict__ L, int l0, int l1) {
+    extern __shared__ __align__(128) unsigned char sweep_smem[];
+    __shared__ __align__(8) unsigned long long sweep_bars[2 * (SWEEP_THREADS / 32)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t mode0 = (int64_t)blockIdx.x * MT;
+    const int bufB = small_buf_bytes(WMAX);
+    if (lane == 0) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * warp);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    SmallPipe<BWD> pipe{S, sweep_smem + (size_t)warp * 2 * bufB, (unsigned)__cvta_generic_to_shared(sweep_bars + 2 * warp),
+                        bufB,  0, nwarps, lane};
+    for (int li = BWD ? l1 - 1 : l0; BWD ? li >= l0 : li < l1; li += BWD ? -1 : 1) {
+        const int t0 = L[3 * li], t1 = L[3 * li + 1];
+        if (t0 + warp < t1) {
+            pipe.t1 = t1;
+            pipe.start(t0 + warp);
+            for (int t = t0 + warp; t < t1; t += nwarps) {
+                const SmallBlk b = load_blk(S, t);
+                if (t + nwarps < t1) {
+                    const SmallBlk nb = load_blk(S, t + nwarps);
+                    if (lane < nb.w) prefetch_l2(W + (int64_t)(nb.j0 + lane) * ld + mode0);
+                }
+                if constexpr (BWD)
+                    small_bwd<WMAX>(b, pipe, W, ld, mode0, lane);
+                else
+                    small_fwd<WMAX>(b, pipe, W, ld, mode0, lane);
+            }
+        }
+        __threadfence();  // stores and reductions of this launch before the loads of the next one (other warps of the CTA)
+        __syncthreads();
+    }
+}
+
+template <int WMAX, bool BWD>
+void launch_small_multi(int l0, int l1, int tiles, cudaStream_t st, double* W, int64_t ld, const SmallDev& S, const int* dL) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_small_multi<WMAX, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
+        configured = true;
+    }
+    constexpr int threads = WMAX <= 24 ? SWEEP_THREADS : SWEEP_THREADS / 2;
+    k_small_multi<WMAX, BWD><<<tiles, threads, SWEEP_SMEM, st>>>(W, ld, S, dL, l0, l1);
+}
+
 template <int WMAX, bool BWD>
 void launch_small_k(int t0, int t1, int tiles, int split, cudaStream_t st, double* W, int64_t ld, const SmallDev& S) {
     static bool configured = false;
@@ -485,7 +541,9 @@ int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>
         const int nsub = (B.len + SMALL_W - 1) / SMALL_W;
         for (int sub = 0; sub < nsub; ++sub) {
             const int32_t j0 = B.start + sub * SMALL_W, w = std::min(SMALL_W, B.start + B.len - j0);
-            const int wcl = wclass_of(w), buf = small_buf_bytes(wcl);
+            // the top of the tree (few, long separators: a chain of small dependent launches) uses the 32-column kernel for
+            // all widths, so that its launches can be merged into one kernel; below, a sub-block keeps its width class
+            const int wcl = B.depth <= TOP_DEPTH ? 32 : wclass_of(w), buf = small_buf_bytes(wcl);
             // target rows: everything below the sub-block that its columns touch (mark: -1 unseen, -2 seen)
             list.clear();
             for (int32_t c = j0; c < j0 + w; ++c)
@@ -717,10 +775,32 @@ int precond_apply_plan(asgfem_ctx* ctx, PrecondPlan* P, const double* r, double*
         const int tiles = (int)(ld / MT);  // all device columns (the column order is private, padding columns hold zeros)
         int split = std::max(1, 148 / tiles);  // CTAs per mode tile: fill the SMs when there are few tiles
         if (const char* e = getenv("ASGFEM_SWEEP_SPLIT")) split = std::max(1, atoi(e));
-        for (size_t k = 0; k < P->launches.size(); ++k)
-            launch_small<false>(P->launches[k], tiles, split, ctx->stream, P->d_work, ld, P->small);
-        for (size_t k = P->launches.size(); k-- > 0;)
-            launch_small<true>(P->launches[k], tiles, split, ctx->stream, P->d_work, ld, P->small);
+        // runs of consecutive 32-column launches go into one kernel each (needs all tasks of a mode tile in one CTA)
+        const bool merge = split == 1 && !getenv("ASGFEM_SWEEP_NOMERGE");
+        if (merge && !P->d_launches && !P->launches.empty()) {
+            ASG_CUDA(ctx, cudaMalloc((void**)&P->d_launches, sizeof(int) * 3 * P->launches.size()));
+            ASG_CUDA(ctx, cudaMemcpyAsync(P->d_launches, P->launches[0].data(), sizeof(int) * 3 * P->launches.size(), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        std::vector<std::array<int, 2>> runs;  // [first launch, one past the last), in forward order
+        for (size_t k = 0; k < P->launches.size();) {
+            size_t e = k + 1;
+            if (merge && P->launches[k][2] == 32)
+                while (e < P->launches.size() && P->launches[e][2] == 32) ++e;
+            runs.push_back({(int)k, (int)e});
+            k = e;
+        }
+        for (size_t q = 0; q < runs.size(); ++q) {
+            if (runs[q][1] - runs[q][0] > 1)
+                launch_small_multi<32, false>(runs[q][0], runs[q][1], tiles, ctx->stream, P->d_work, ld, P->small, P->d_launches);
+            else
+                launch_small<false>(P->launches[(size_t)runs[q][0]], tiles, split, ctx->stream, P->d_work, ld, P->small);
+        }
+        for (size_t q = runs.size(); q-- > 0;) {
+            if (runs[q][1] - runs[q][0] > 1)
+                launch_small_multi<32, true>(runs[q][0], runs[q][1], tiles, ctx->stream, P->d_work, ld, P->small, P->d_launches);
+            else
+                launch_small<true>(P->launches[(size_t)runs[q][0]], tiles, split, ctx->stream, P->d_work, ld, P->small);
+        }
     }
     // z may alias r: boundary rows are zeroed first, interior rows are overwritten from the work vector
     k_zero_masked_rows<<<(unsigned)std::min<int64_t>(nrows, 148 * 8), 128, 0, ctx->stream>>>(z, d_bmask, nrows, ld);

@@ -15,5 +15,12 @@ ctx = TB.ctx
 ctx.precond_setup()
 ctx.vec_alloc(2)
 ctx.vec_fill_random(0, 1)
-for _ in range(int(os.environ.get("REPS", 2))):
+import time, torch
+reps = int(os.environ.get("REPS", 2))
+ctx.precond_apply(0, 1)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(reps):
     ctx.precond_apply(0, 1)
+torch.cuda.synchronize()
+print("precond_apply ms:", (time.perf_counter() - t0) / reps * 1e3, "leaf", os.environ.get("ASGFEM_CHOL_LEAF", "24"), flush=True)

@@ -1,4 +1,4 @@
-NX=1024 REPS=2 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_small_step|k_gather_perm|k_scatter_perm|k_zero" --csv --log-file gpurun_out/r2_trsv_launches.csv python tools/prof_trsv.py > gpurun_out/r2_pc_ncu.log 2>&1
+NX=1024 REPS=2 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_small_step|k_small_multi|k_gather_perm|k_scatter_perm|k_zero" --csv --log-file gpurun_out/r2_trsv_launches.csv python tools/prof_trsv.py > gpurun_out/r2_pc_ncu.log 2>&1
 tail -2 gpurun_out/r2_pc_ncu.log
 python - <<'PY'
 import csv,collections
