@@ -440,7 +440,11 @@ int apply_ts2_build(asgfem_ctx* ctx) {
                                     (uint32_t)m * kbytes2 | (uint32_t)(units[(size_t)u].disp + l) << 15;
                                 ++q;
                             }
-                    for (; q < 4; ++q) lane[(((size_t)w * TS2_SLOTS + s) * 4 + q) * 32 + l] = dummy_lane;
+                    // padding units repeat the lane's first unit (same K row, same T entry: the same value is stored again by
+                    // the same thread); a lane without any unit - or any lane when long rows accumulate T in chunks -
+                    // computes on K_0 and stores to its own dummy entry
+                    const uint32_t fill = q > 0 && P->nchunk_max == 1 ? lane[(((size_t)w * TS2_SLOTS + s) * 4 + 0) * 32 + l] : (uint32_t)(D + 16 + l) << 15;
+                    for (; q < 4; ++q) lane[(((size_t)w * TS2_SLOTS + s) * 4 + q) * 32 + l] = fill;
                 }
             }
         }

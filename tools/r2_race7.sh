@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests/test_gpu_hotpath.py -x -q -m gpu -k "apply" 2>&1 | tail -3
+bash tools/r2_san.sh
