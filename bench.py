@@ -164,67 +164,15 @@ def build_local_problem(A, rank, world):
 
 
 def build_strip_problem(A, rank, world, order, ncx, ncy_per_rank, n_modes, device):
-    """Row shard of a structured P1 / P2 problem for configs[4]: a mesh of ncx x (ncy_per_rank * world) squares, rank r owns
-    the dofs with y-index in [r, r + 1) * ncy_per_rank (half-integer rows of edge dofs: the half row above an owned node
-    row).  Local numbering: owned dofs sorted by (y, x) - the rows along the lower cut first, along the upper cut last,
-    so that the rows without halo columns are one contiguous range -, then the lower halo, then the upper halo.
-    Returns (ctx, n_owned, n_local, send, recv, interior)."""
-    nx = ncx + 1
-    ny_tot = ncy_per_rank * world + 1
-    y_lo, y_hi = rank * ncy_per_rank, (rank + 1) * ncy_per_rank  # owned node rows [y_lo, y_hi); the last rank also owns the top row
-    if rank == world - 1:
-        y_hi = ny_tot
-    ext_lo, ext_hi = max(y_lo - 1, 0), min(y_hi + 1, ny_tot)
-    hx, hy = 1.0 / ncx, 1.0 / (ny_tot - 1)
-    g = A.structured_unitsquare(nx, ext_hi - ext_lo, 0.0, 1.0, ext_lo * hy, (ext_hi - 1) * hy)
-    fes = A.FESpace(g, order)
-    # integer dof positions in half-mesh-width units
-    ix = np.rint(g.coords[:, 0] / hx).astype(np.int64)
-    iy = np.rint(g.coords[:, 1] / hy).astype(np.int64)
-    px, py = 2 * ix, 2 * iy
-    if order == 2:
-        fa, fb = g.facenodes[:, 0], g.facenodes[:, 1]
-        px = np.concatenate([px, ix[fa] + ix[fb]])
-        py = np.concatenate([py, iy[fa] + iy[fb]])
-    owned = (py >= 2 * y_lo) & (py < 2 * y_hi)
-    lower = py < 2 * y_lo
-    upper = py >= 2 * y_hi
-    key = py * (4 * nx) + px
-    order_of = lambda mask: np.where(mask)[0][np.argsort(key[mask], kind="stable")]  # noqa: E731
-    o_own, o_lo, o_up = order_of(owned), order_of(lower), order_of(upper)
-    perm = np.concatenate([o_own, o_lo, o_up])  # new -> old
-    new_of_old = np.empty(fes.ndofs, dtype=np.int64)
-    new_of_old[perm] = np.arange(fes.ndofs)
-    n_owned, n_local = len(o_own), fes.ndofs
-    celldofs = new_of_old[fes.celldofs]
-    pxn, pyn = px[perm], py[perm]
-    on_bnd = (pxn == 0) | (pxn == 2 * ncx) | (pyn == 0) | (pyn == 2 * (ny_tot - 1))
-    bdofs = np.where(on_bnd)[0]
+    """Row shard of a structured P1 / P2 problem for configs[4] (asgfem_b200.distributed.strip_shard) with the stiffness
+    matrices assembled on the device.  Returns (ctx, n_owned, n_local, send, recv, interior)."""
+    from asgfem_b200 import distributed as D
+    S = D.strip_shard(rank, world, order, ncx, ncy_per_rank)
     ctx = A.Context(device)
     ctx.set_multiindices(A.LEGENDRE, np.array(A.graded_lex_multiindices(M_KLE, n_modes), dtype=np.int64))
-    Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=M_KLE)
-    ctx.set_mesh(g.coords, g.cellnodes + 1)
-    ctx.set_space(order, fes.ndofs, celldofs + 1)
-    ctx.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
-    xref, w = A.quadrature_rule(2 * order)
-    ctx.assemble_stiffness(M_KLE, xref, w)
-    send, recv = {}, {}
-    if world > 1:
-        ctx.set_bdofs(np.union1d(bdofs, np.arange(n_owned, n_local)) + 1)
-        ctx.set_owned_rows(n_owned)
-        # my lower halo = the dofs of the lower neighbour with y in [y_lo - 1, y_lo); it needs my dofs with y = y_lo as its
-        # upper halo.  Both sides list the rows in (y, x) order.
-        if y_lo > 0:
-            recv[rank - 1] = n_owned + np.arange(len(o_lo))
-            send[rank - 1] = np.where(pyn[:n_owned] == 2 * y_lo)[0]
-        if y_hi < ny_tot:
-            recv[rank + 1] = n_owned + len(o_lo) + np.arange(len(o_up))
-            send[rank + 1] = np.where(pyn[:n_owned] >= 2 * (y_hi - 1))[0]
-    else:
-        ctx.set_bdofs(bdofs + 1)
-    i0 = int(np.sum(pyn[:n_owned] == 2 * y_lo)) if y_lo > 0 else 0
-    i1 = int(np.sum(pyn[:n_owned] < 2 * (y_hi - 1))) if y_hi < ny_tot else n_owned
-    return ctx, n_owned, n_local, send, recv, (i0, i1)
+    D.setup_strip_context(ctx, S, A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=M_KLE), M_KLE,
+                          A.quadrature_rule(2 * order))
+    return ctx, S.n_owned, S.n_local, S.send, S.recv, S.interior
 
 
 def run_c5_leg(A, torch, dist, rank, world, local_rank, steps, warmup, variant):

@@ -326,6 +326,17 @@ class Context:
     def set_owned_rows(self, n_owned):
         self._ck(self.lib.asgfem_set_owned_rows(self.h, n_owned))
 
+    def set_owned_cells(self, owned):
+        """Row-sharded estimator: flags (one per cell of the rank's mesh) of the cells this rank owns; None = all."""
+        if owned is None:
+            self._ck(self.lib.asgfem_set_owned_cells(self.h, 0, None))
+            return
+        f = np.ascontiguousarray(np.asarray(owned, dtype=np.uint8))
+        self._ck(self.lib.asgfem_set_owned_cells(self.h, len(f), f.ctypes.data))
+
+    def halo_exchange(self, slot):
+        self._ck(self.lib.asgfem_halo_exchange(self.h, slot))
+
     def vec_device_ptr(self, slot):
         p, ld = C.c_void_p(), C.c_int64()
         self._ck(self.lib.asgfem_vec_device_ptr(self.h, slot, C.byref(p), C.byref(ld)))

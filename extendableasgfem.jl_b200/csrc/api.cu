@@ -905,6 +905,27 @@ extern "C" int asgfem_set_owned_rows(asgfem_ctx* ctx, int64_t n_owned) {
     return 0;
 }
 
+extern "C" int asgfem_halo_exchange(asgfem_ctx* ctx, int32_t slot) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    int rc = dist_halo_exchange(ctx, ctx->slots[slot]);
+    if (rc) return rc;
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int asgfem_set_owned_cells(asgfem_ctx* ctx, int64_t ncells, const uint8_t* owned) {
+    CTX_OR_FAIL(ctx);
+    if (!owned) {
+        ctx->h_cell_owned.clear();
+        return 0;
+    }
+    ASG_CHECK(ctx, ctx->ncells > 0 && ncells == ctx->ncells, ASGFEM_EINVAL, "set_owned_cells: one flag per cell of the mesh (asgfem_set_mesh first)");
+    ctx->h_cell_owned.assign(owned, owned + ncells);
+    return 0;
+}
+
 extern "C" int asgfem_vec_device_ptr(asgfem_ctx* ctx, int32_t slot, void** dptr, int64_t* ld) {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;

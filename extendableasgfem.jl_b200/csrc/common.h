@@ -118,6 +118,7 @@ struct asgfem_ctx {
     int32_t order = 0, ndofs4cell = 0;
     int64_t ndofs_space = 0;
     std::vector<int32_t> h_celldofs;  // 0-based
+    std::vector<uint8_t> h_cell_owned;  // row-sharded estimator: 1 = this rank owns the cell (empty: all cells)
     int32_t* d_celldofs = nullptr;
     int64_t maxm = 0;
     double mean = 0;
@@ -197,9 +198,11 @@ void dist_free(asgfem_ctx* ctx);
 bool dist_active(asgfem_ctx* ctx);
 int dist_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const int64_t* send_ptr, const int64_t* send_rows,
                   const int64_t* recv_ptr, const int64_t* recv_rows, int64_t interior0, int64_t interior1);
+int dist_halo_exchange(asgfem_ctx* ctx, double* x);                        // no-op without a communicator
 int dist_apply(asgfem_ctx* ctx, const double* x, double* y);               // = apply_launch without a communicator
 int dist_dot(asgfem_ctx* ctx, const double* a, const double* b, double* out);  // owned rows, summed over the ranks
 int dist_max(asgfem_ctx* ctx, double* v);
+int dist_allreduce_sum(asgfem_ctx* ctx, double* dbuf, size_t n);  // in place on the device, stream-ordered; no-op without a communicator
 int dist_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                               int64_t nb, const int64_t* bdofs, const double* coords, const int64_t* row_offsets);
 bool dist_has_global_precond(asgfem_ctx* ctx);

@@ -208,19 +208,15 @@ static int ensure_buffers(asgfem_ctx* ctx, DistPlan* D) {
 // Y = A X on the owned rows of this rank.  One launch sequence, no host synchronisation:
 //   stream:       pack send rows | operator on [interior0, interior1) | wait | unpack halo rows | operator on the other owned rows
 //   comm stream:                 | grouped ncclSend / ncclRecv         |
-int dist_apply(asgfem_ctx* ctx, const double* x, double* y) {
+// halo rows of x <- owned rows of the neighbours (pack, ncclSend / ncclRecv, unpack on the context's stream)
+int dist_halo_exchange(asgfem_ctx* ctx, double* x) {
     DistPlan* D = dp_of(ctx);
-    if (!dist_active(ctx)) return apply_launch(ctx, x, y);
-    ASG_CHECK(ctx, D->halo_set, ASGFEM_ESTATE, "apply: asgfem_set_halo first");
+    if (!dist_active(ctx)) return 0;
+    ASG_CHECK(ctx, D->halo_set, ASGFEM_ESTATE, "halo exchange: asgfem_set_halo first");
     int rc = ensure_buffers(ctx, D);
     if (rc) return rc;
     const int nn = (int)D->nb_rank.size();
     const int64_t N = ctx->N, ns = D->send_ptr[nn], nr = D->recv_ptr[nn];
-    // Exchange first, then ONE operator launch over all owned rows.  The halo rows are 2 x 16 MB per neighbour (about
-    // 0.1 ms over NVLink); overlapping them with the interior rows (round 1 / first version of this function: NCCL on a
-    // second stream, three operator launches) cost more than it hid: the persistent operator CTAs and the NCCL CTAs compete
-    // for the SMs, a rank whose NCCL kernel starts late stalls its neighbours' kernels, and every extra launch pays the
-    // 222 KB table prologue - 73.8 ms per step at 4 GPUs against 51.5 ms for the launch alone.
     if ((rc = vec_pack_rows(ctx, x, ns, D->d_send_rows, D->d_sendbuf))) return rc;
     NCCL_CHECK(ctx, g_nccl.GroupStart());
     for (int k = 0; k < nn; ++k) {
@@ -229,7 +225,18 @@ int dist_apply(asgfem_ctx* ctx, const double* x, double* y) {
         if (r1 > r0) NCCL_CHECK(ctx, g_nccl.Recv(D->d_recvbuf + r0 * N, (size_t)((r1 - r0) * N), NCCL_FLOAT64, D->nb_rank[k], D->comm, ctx->stream));
     }
     NCCL_CHECK(ctx, g_nccl.GroupEnd());
-    if ((rc = vec_unpack_rows(ctx, const_cast<double*>(x), nr, D->d_recv_rows, D->d_recvbuf))) return rc;
+    return vec_unpack_rows(ctx, x, nr, D->d_recv_rows, D->d_recvbuf);
+}
+
+// Exchange first, then ONE operator launch over all owned rows.  The halo rows are 2 x 16 MB per neighbour (about 0.1 ms
+// over NVLink); overlapping them with the interior rows (round 1 / first version of this function: NCCL on a second
+// stream, three operator launches) cost more than it hid: the persistent operator CTAs and the NCCL CTAs compete for the
+// SMs, a rank whose NCCL kernel starts late stalls its neighbours' kernels, and every extra launch pays the 222 KB table
+// prologue - 73.8 ms per step at 4 GPUs against 51.5 ms for the launch alone.
+int dist_apply(asgfem_ctx* ctx, const double* x, double* y) {
+    if (!dist_active(ctx)) return apply_launch(ctx, x, y);
+    int rc = dist_halo_exchange(ctx, const_cast<double*>(x));
+    if (rc) return rc;
     return apply_launch(ctx, x, y, 0, ctx->n_owned);
 }
 
@@ -420,6 +427,14 @@ int dist_precond_apply(asgfem_ctx* ctx, const double* r, double* z) {
     ASG_CUDA(ctx, cudaGetLastError());
     // rows beyond the owned ones (halo) carry no part of z
     if (ctx->n > no) ASG_CUDA(ctx, cudaMemsetAsync(z + no * ld, 0, sizeof(double) * (size_t)((ctx->n - no) * ld), ctx->stream));
+    return 0;
+}
+
+// sum over the ranks of a device array (estimator totals), in place, on the context's stream
+int dist_allreduce_sum(asgfem_ctx* ctx, double* dbuf, size_t n) {
+    DistPlan* D = dp_of(ctx);
+    if (!dist_active(ctx) || n == 0) return 0;
+    NCCL_CHECK(ctx, g_nccl.AllReduce(dbuf, dbuf, n, NCCL_FLOAT64, NCCL_SUM, D->comm, ctx->stream));
     return 0;
 }
 

@@ -222,13 +222,18 @@ __global__ void __launch_bounds__(256) k_est_jumps(EstArgs a) {
 }
 
 // partial column sums over row chunks: part[chunk][j] = sum_{r in chunk} A[r][j]   (fixed order)
+// wrow (may be null): weight of a row - the share of a cell / face this rank owns in a row-sharded run
 __global__ void k_colsum_partial(const double* __restrict__ A, int64_t nrows, int64_t ld, int ncols, int chunk,
-                                 double* __restrict__ part) {
+                                 double* __restrict__ part, const double* __restrict__ wrow) {
     int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
     int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(r0 + chunk, nrows);
     double s = 0.0;
-    for (int64_t r = r0; r < r1; ++r) s += A[r * ld + j];
+    if (wrow) {
+        for (int64_t r = r0; r < r1; ++r) s += wrow[r] * A[r * ld + j];
+    } else {
+        for (int64_t r = r0; r < r1; ++r) s += A[r * ld + j];
+    }
     part[(int64_t)blockIdx.x * ncols + j] = s;
 }
 
@@ -424,15 +429,32 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
     ASG_CUDA(ctx, cudaMalloc(&d_part.p, sizeof(double) * (size_t)std::max(ncc, nfc) * N_ext));
     ASG_CUDA(ctx, cudaMalloc(&d_sums.p, sizeof(double) * 2 * N_ext));
     dim3 gb(ncc, (unsigned)((N_ext + 127) / 128));
-    k_colsum_partial<<<gb, 128, 0, ctx->stream>>>(a.E, ncells, ldE, (int)N_ext, chunk, (double*)d_part.p);
+    // row-sharded run (asgfem_set_owned_cells): a cell counts where it is owned, an interior face with the share of its two
+    // cells that this rank owns (1, 1/2 or 0: the neighbour adds the other half); the sums are all-reduced below
+    DevBuf d_wc, d_wf;
+    const double *wcell = nullptr, *wface = nullptr;
+    if (!ctx->h_cell_owned.empty()) {
+        ASG_CHECK(ctx, (int64_t)ctx->h_cell_owned.size() == ncells, ASGFEM_ESTATE, "estimate: owned-cell flags do not match the mesh");
+        std::vector<double> wc((size_t)ncells), wfv((size_t)nfaces);
+        for (int64_t c = 0; c < ncells; ++c) wc[(size_t)c] = ctx->h_cell_owned[(size_t)c] ? 1.0 : 0.0;
+        for (int64_t f = 0; f < nfaces; ++f) {
+            const int32_t c0 = face_cells[(size_t)(2 * f)], c1 = face_cells[(size_t)(2 * f + 1)];
+            wfv[(size_t)f] = 0.5 * ((c0 >= 0 ? wc[(size_t)c0] : 0.0) + (c1 >= 0 ? wc[(size_t)c1] : 0.0));
+        }
+        if ((rc = upload(d_wc, wc.data(), sizeof(double) * ncells))) return rc;
+        if ((rc = upload(d_wf, wfv.data(), sizeof(double) * nfaces))) return rc;
+        wcell = (const double*)d_wc.p, wface = (const double*)d_wf.p;
+    }
+    k_colsum_partial<<<gb, 128, 0, ctx->stream>>>(a.E, ncells, ldE, (int)N_ext, chunk, (double*)d_part.p, wcell);
     k_colsum_final<<<(unsigned)((N_ext + 127) / 128), 128, 0, ctx->stream>>>((double*)d_part.p, ncc, (int)N_ext, (double*)d_sums.p);
     dim3 gf(nfc, (unsigned)((N_ext + 127) / 128));
-    k_colsum_partial<<<gf, 128, 0, ctx->stream>>>(a.JF, nfaces, ldE, (int)N_ext, chunk, (double*)d_part.p);
+    k_colsum_partial<<<gf, 128, 0, ctx->stream>>>(a.JF, nfaces, ldE, (int)N_ext, chunk, (double*)d_part.p, wface);
     k_colsum_final<<<(unsigned)((N_ext + 127) / 128), 128, 0, ctx->stream>>>((double*)d_part.p, nfc, (int)N_ext,
                                                                             (double*)d_sums.p + N_ext);
     k_add_face_jumps<<<gridc, 256, 0, ctx->stream>>>(a.E, a.JF, a.cell_faces, ncells, ldE, (int)N_ext);
     ASG_CUDA(ctx, cudaGetLastError());
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if ((rc = dist_allreduce_sum(ctx, (double*)d_sums.p, (size_t)(2 * N_ext)))) return rc;  // no-op without a communicator
     std::vector<double> sums((size_t)(2 * N_ext));
     ASG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums.p, sizeof(double) * 2 * N_ext, cudaMemcpyDeviceToHost, ctx->stream));
 

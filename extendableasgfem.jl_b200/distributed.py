@@ -261,3 +261,87 @@ def setup_context(ctx, local: LocalProblem, mats, bdofs0, family, multi_indices)
     ctx.set_bdofs(excluded + 1)
     ctx.set_owned_rows(local.n_owned)
     return ctx
+
+
+# ---- strips of a structured mesh: dof ownership by coordinates (benchmark configs[4], sharded estimator) -----------------
+class StripShard:
+    """Row shard of a structured P1 / P2 mesh of ncx x (ncy_per_rank * world) squares cut into horizontal strips.
+
+    Rank r owns the dofs with y-index in [r, r + 1) * ncy_per_rank (for P2 edge dofs: the half row above an owned node
+    row; the last rank also owns the top row).  Its mesh = the cells that touch an owned dof plus `upper_halo_rows - 1`
+    more cell rows above (the estimator needs the cell across every face of an owned cell: upper_halo_rows = 2).  Local
+    numbering: owned dofs sorted by (y, x) - the rows along the lower cut first, along the upper cut last, so that the
+    rows without halo columns are one contiguous range `interior` -, then the lower halo, then the upper halo.
+    send / recv: dict neighbour rank -> local dof ids (0-based), both sides in (y, x) order.  cell_owned: the cells whose
+    lower node row is owned (every cell of the global mesh is owned by exactly one rank)."""
+
+
+def strip_shard(rank, world, order, ncx, ncy_per_rank, upper_halo_rows=1):
+    from . import grids as _g
+    S = StripShard()
+    nx = ncx + 1
+    ny_tot = ncy_per_rank * world + 1
+    y_lo, y_hi = rank * ncy_per_rank, (rank + 1) * ncy_per_rank
+    if rank == world - 1:
+        y_hi = ny_tot
+    ext_lo, ext_hi = max(y_lo - 1, 0), min(y_hi + upper_halo_rows, ny_tot)
+    hx, hy = 1.0 / ncx, 1.0 / (ny_tot - 1)
+    g = _g.structured_unitsquare(nx, ext_hi - ext_lo, 0.0, 1.0, ext_lo * hy, (ext_hi - 1) * hy)
+    fes = _g.FESpace(g, order)
+    ix = np.rint(g.coords[:, 0] / hx).astype(np.int64)
+    iy = np.rint(g.coords[:, 1] / hy).astype(np.int64)
+    px, py = 2 * ix, 2 * iy  # dof positions in half mesh widths
+    if order == 2:
+        fa, fb = g.facenodes[:, 0], g.facenodes[:, 1]
+        px = np.concatenate([px, ix[fa] + ix[fb]])
+        py = np.concatenate([py, iy[fa] + iy[fb]])
+    owned = (py >= 2 * y_lo) & (py < 2 * y_hi)
+    lower, upper = py < 2 * y_lo, py >= 2 * y_hi
+    key = py * (4 * nx) + px
+
+    def order_of(mask):
+        idx = np.where(mask)[0]
+        return idx[np.argsort(key[mask], kind="stable")]
+
+    o_own, o_lo, o_up = order_of(owned), order_of(lower), order_of(upper)
+    perm = np.concatenate([o_own, o_lo, o_up])  # new -> old
+    new_of_old = np.empty(fes.ndofs, dtype=np.int64)
+    new_of_old[perm] = np.arange(fes.ndofs)
+    S.grid, S.fes, S.order = g, fes, order
+    S.n_owned, S.n_local = len(o_own), fes.ndofs
+    S.celldofs = new_of_old[fes.celldofs]
+    S.perm, S.new_of_old = perm, new_of_old
+    pxn, pyn = px[perm], py[perm]
+    S.px, S.py = pxn, pyn
+    S.bdofs = np.where((pxn == 0) | (pxn == 2 * ncx) | (pyn == 0) | (pyn == 2 * (ny_tot - 1)))[0]
+    S.send, S.recv = {}, {}
+    if y_lo > 0:  # lower neighbour: its upper halo = my dofs with y in [y_lo, y_lo + upper_halo_rows - 1]
+        S.recv[rank - 1] = S.n_owned + np.arange(len(o_lo))
+        S.send[rank - 1] = np.where(pyn[:S.n_owned] <= 2 * (y_lo + upper_halo_rows - 1))[0]
+    if y_hi < ny_tot:  # upper neighbour: its lower halo = my dofs with y in [y_hi - 1, y_hi)
+        S.recv[rank + 1] = S.n_owned + len(o_lo) + np.arange(len(o_up))
+        S.send[rank + 1] = np.where(pyn[:S.n_owned] >= 2 * (y_hi - 1))[0]
+    i0 = int(np.sum(pyn[:S.n_owned] == 2 * y_lo)) if y_lo > 0 else 0
+    i1 = int(np.sum(pyn[:S.n_owned] < 2 * (y_hi - 1))) if y_hi < ny_tot else S.n_owned
+    S.interior = (i0, i1)
+    cy = iy[g.cellnodes].min(axis=1)  # lower node row of a cell
+    S.cell_owned = ((cy >= y_lo) & (cy < y_hi)).astype(np.uint8)
+    S.global_dof_key = key[perm]  # (y, x) key: identical for the same dof on every rank
+    S.rank, S.world = rank, world
+    return S
+
+
+def setup_strip_context(ctx, S, coefficient, M, quadrature):
+    """Mesh, renumbered space, coefficient tables and device assembly of K_0..K_M for a strip shard; halo rows are flagged
+    like Dirichlet rows (they are not part of this rank's system)."""
+    g = S.grid
+    ctx.set_mesh(g.coords, g.cellnodes + 1)
+    ctx.set_space(S.order, S.n_local, S.celldofs + 1)
+    ctx.set_coefficient_cosinus(coefficient.mean_value, coefficient.decay_factors, coefficient.b1, coefficient.b2)
+    xref, w = quadrature
+    ctx.assemble_stiffness(M, xref, w)
+    if S.world > 1:
+        ctx.set_bdofs(np.union1d(S.bdofs, np.arange(S.n_owned, S.n_local)) + 1)
+        ctx.set_owned_rows(S.n_owned)
+    else:
+        ctx.set_bdofs(S.bdofs + 1)

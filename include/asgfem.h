@@ -213,6 +213,15 @@ int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ex
  * Vectors have n_local rows; only owned rows are written by apply.  The host layer (torch.distributed /
  * NCCL) exchanges halo rows between the pack/unpack calls and all-reduces the partial dots. */
 int asgfem_set_owned_rows(asgfem_ctx* ctx, int64_t n_owned);
+/* Row-sharded estimator (cells and faces sharded with the rows, totals all-reduced).  The mesh of a
+ * rank = its owned cells plus the layer of neighbouring cells whose dofs are its halo rows; owned[c] != 0 marks the cells it
+ * owns (NULL: all cells again).  asgfem_estimate_poisson_primal then sums eta4modes over the owned cells, counts an interior
+ * face with the share of its two cells that the rank owns (the neighbour adds the rest) and all-reduces the sums over the
+ * communicator of asgfem_comm_init; eta4cell is meaningful in the rows of the owned cells.  The solution vector must hold
+ * current halo rows (asgfem_halo_exchange). */
+int asgfem_set_owned_cells(asgfem_ctx* ctx, int64_t ncells, const uint8_t* owned);
+/* fills the halo rows of a vector slot from the neighbours' owned rows (the exchange asgfem_apply performs internally) */
+int asgfem_halo_exchange(asgfem_ctx* ctx, int32_t slot);
 /* Operator on the local rows [row0, row1) only (0-based, half open, clipped to the owned rows); the other rows of slot sy
  * are left untouched.  Lets the host layer apply the rows that reference no halo column while the halo exchange is in
  * flight, and the rows along the partition boundary afterwards.  asgfem_last_apply_ms reports this launch. */

@@ -254,6 +254,20 @@ function estimate(::Type{PoissonProblemPrimal}, sol::SGFEVector, C::StochasticCo
 end
 
 """
+Row-sharded runs (one Julia task / process per GPU, NCCL inside the library): `comm_init!` with the 128-byte id of
+`asgfem_comm_unique_id` (created on rank 0, distributed by the host layer), `set_halo!` with the 1-based local row lists,
+then `mul!` / `solve_primal!` work on the rank's row shard.  For the estimator the rank's mesh holds its owned cells plus
+the neighbouring cell layer; `set_owned_cells!` marks the owned ones and `halo_exchange!` fills the halo rows of the
+solution before `estimate` (the mode totals are all-reduced inside the library).
+"""
+comm_init!(ctx::Context, nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ctx, ccall((:asgfem_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.h, nranks, rank, id))
+set_owned_cells!(ctx::Context, owned::Vector{UInt8}) =
+    check(ctx, ccall((:asgfem_set_owned_cells, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{UInt8}), ctx.h, length(owned), owned))
+halo_exchange!(ctx::Context, slot::Integer = 0) =
+    check(ctx, ccall((:asgfem_halo_exchange, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.h, slot))
+
+"""
     ASGFEMCuda.activate!()
 
 Overrides the reference methods so that `solve!(PoissonProblemPrimal, ...)` (src/modelproblems/poisson_primal.jl:75)

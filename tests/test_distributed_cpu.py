@@ -161,3 +161,30 @@ def test_partition_is_balanced_and_complete():
         assert counts.sum() == P.n and counts.max() - counts.min() <= parts
     owner = D.partition_rows(10, 3)
     assert list(owner) == [0, 0, 0, 1, 1, 1, 2, 2, 2, 2]
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("upper", [1, 2])
+def test_strip_shards_partition_dofs_and_cells(order, upper):
+    """Strips of a structured mesh (bench configs[4], sharded estimator): every dof and every cell has exactly one owner,
+    and the send list of a rank names the same dofs in the same order as the receive list of its neighbour."""
+    from asgfem_b200 import distributed as D
+    world, ncx, ncy = 4, 16, 4
+    shards = [D.strip_shard(r, world, order, ncx, ncy, upper) for r in range(world)]
+    n_glob = (ncx + 1) * (ncy * world + 1) if order == 1 else (2 * ncx + 1) * (2 * ncy * world + 1)
+    assert sum(S.n_owned for S in shards) == n_glob
+    assert sum(int(S.cell_owned.sum()) for S in shards) == 2 * ncx * ncy * world
+    keys = np.concatenate([S.global_dof_key[:S.n_owned] for S in shards])
+    assert len(np.unique(keys)) == n_glob
+    for r in range(world - 1):
+        lo, up = shards[r], shards[r + 1]
+        assert np.array_equal(lo.global_dof_key[lo.send[r + 1]], up.global_dof_key[up.recv[r]])
+        assert np.array_equal(up.global_dof_key[up.send[r]], lo.global_dof_key[lo.recv[r + 1]])
+    for S in shards:
+        i0, i1 = S.interior
+        assert 0 <= i0 <= i1 <= S.n_owned
+        # rows [i0, i1) touch no halo dof: no cell contains both such a dof and a halo dof
+        touches = np.zeros(S.n_local, dtype=bool)
+        halo_cell = (S.celldofs >= S.n_owned).any(axis=1)
+        touches[np.unique(S.celldofs[halo_cell])] = True
+        assert not touches[i0:i1].any()

@@ -154,3 +154,111 @@ def test_two_gpu_operator_and_pcg():
         if nit1 >= 0:
             assert abs(niter3 - nit1) <= 1, (niter3, nit1)  # exact mean preconditioner: the single-GPU iteration count
     assert res[0][-1] == res[1][-1]  # the all-reduced inner product is the same number on both ranks
+
+
+# ---- row-sharded estimator (cells / faces sharded with the rows, totals all-reduced) -------------
+def _est_worker(rank, world, port, q, order):
+    import torch.distributed as dist
+
+    import asgfem_b200 as A
+    from asgfem_b200 import distributed as D, multiindices as MI, grids as G
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ncx, ncy = 12, 6
+        modes = A.graded_lex_multiindices(3, 10)
+        Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=8)
+        mi_ext = np.array(MI.add_boundary_modes(modes, tail_extension=(5, 2)), dtype=np.int64)
+        quadorder = 2 * (order - 1) + 1
+        xref, w = G.quadrature_rule(quadorder)
+        sf, wf = G.quadrature_rule_1d(quadorder)
+
+        def field(S):  # the same smooth "solution" on every rank: a function of the global dof position and the mode
+            k = np.arange(len(modes))[:, None]
+            return np.sin(0.37 * S.px[None, :] + 0.11 * k) * np.cos(0.23 * S.py[None, :] - 0.05 * k) / (1.0 + k)
+
+        def cell_keys(S):
+            c = S.grid.cellnodes
+            xy = S.grid.coords[c].sum(axis=1)  # 3 x centroid
+            return np.rint(xy[:, 0] * 1e6).astype(np.int64) * 10_000_000 + np.rint(xy[:, 1] * 1e6).astype(np.int64)
+
+        def run(S, ctx, sharded):
+            ctx.set_multiindices(A.LEGENDRE, np.array(modes, dtype=np.int64))
+            D.setup_strip_context(ctx, S, Cf, 3, G.quadrature_rule(2 * order))
+            ctx.vec_alloc(1)
+            u = field(S)
+            if sharded:
+                u[:, S.n_owned:] = 0.0  # the exchange must fill the halo rows
+            ctx.vec_upload(0, u.reshape(-1))
+            if sharded:
+                ids = [A.Context.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                ctx.comm_init(world, rank, ids[0])
+                ctx.set_halo(S.send, S.recv, *S.interior)
+                ctx.halo_exchange(0)
+                ctx.set_owned_cells(S.cell_owned)
+            c = S.grid.cellnodes
+            x1, x2, x3 = S.grid.coords[c[:, 0]], S.grid.coords[c[:, 1]], S.grid.coords[c[:, 2]]
+            xq = x1[:, None, :] + xref[None, :, 0:1] * (x2 - x1)[:, None, :] + xref[None, :, 1:2] * (x3 - x1)[:, None, :]
+            fq = 1.0 + xq[:, :, 0] * xq[:, :, 1]
+            return ctx.estimate_poisson_primal(0, mi_ext, xref, w, sf, wf, S.grid.ncells, fq)
+
+        S = D.strip_shard(rank, world, order, ncx, ncy, upper_halo_rows=2)
+        ctx = A.Context(rank)
+        em, ec = run(S, ctx, True)
+        own = S.cell_owned.astype(bool)
+        out = (rank, em.copy(), cell_keys(S)[own], np.array(ec)[own].copy(), None, None, None)
+        if rank == 0:  # reference: the whole mesh on one GPU
+            S1 = D.strip_shard(0, 1, order, ncx, ncy * world)
+            c1 = A.Context(rank)
+            em1, ec1 = run(S1, c1, False)
+            out = out[:4] + (em1.copy(), cell_keys(S1), np.array(ec1).copy())
+            c1.close()
+        q.put(out)
+        dist.barrier()
+        ctx.comm_destroy()
+        ctx.close()
+    except Exception:
+        import traceback
+        q.put(("error", rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("order", [1, 2])
+def test_two_gpu_estimator_matches_single_gpu(order):
+    world = 2
+    c = mp.get_context("spawn")
+    q = c.Queue()
+    procs = [c.Process(target=_est_worker, args=(r, world, 29350 + os.getpid() % 300 + order, q, order)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        try:
+            r = q.get(timeout=240)
+        except Exception:
+            r = ("error", -1, "timeout waiting for a rank")
+        if r[0] == "error":
+            for p in procs:
+                p.terminate()
+            raise AssertionError(r)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    em_ref, keys_ref, ec_ref = res[0][4], res[0][5], res[0][6]
+    pos = {int(k): i for i, k in enumerate(keys_ref)}
+    seen = 0
+    for r in range(world):
+        _, em, keys, ec = res[r][:4]
+        # the all-reduced mode totals are the single-GPU ones on every rank (tolerance of the estimator: 1e-10)
+        assert np.max(np.abs(em - em_ref)) <= 1e-10 * np.max(np.abs(em_ref)), (r, em, em_ref)
+        rows = np.array([pos[int(k)] for k in keys])
+        assert np.max(np.abs(ec - ec_ref[rows])) <= 1e-10 * np.max(np.abs(ec_ref))
+        seen += len(rows)
+    assert seen == len(keys_ref)  # every cell of the mesh is owned by exactly one rank
