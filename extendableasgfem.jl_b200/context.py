@@ -270,6 +270,21 @@ class Context:
         self._ck(self.lib.asgfem_pcg(self.h, _ptr(b0), slot_x, atol, rtol, itmax, C.byref(st)))
         return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
 
+    def set_samples(self, samples):
+        """samples: (Msamples, nsamples) - the columns of the device vectors become the samples (asgfem_set_samples)."""
+        S = np.asfortranarray(np.asarray(samples, dtype=np.float64))
+        Ms, ns = S.shape
+        self._ck(self.lib.asgfem_set_samples(self.h, ns, Ms, S.ctypes.data))
+        self.nsamples = ns
+
+    def solve_samples_host(self, b, atol=1e-14, rtol=1e-14, itmax=0):
+        """Deterministic solutions of all samples: returns (u, stats), u of shape (n, nsamples)."""
+        b = _f64(b)
+        out = np.zeros((self.nsamples, len(b)))  # C-order (nsamples, n) == n x nsamples column-major
+        st = _lib.Stats()
+        self._ck(self.lib.asgfem_solve_samples_host(self.h, _ptr(out), _ptr(b), atol, rtol, itmax, C.byref(st)))
+        return out.T, {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
+
     def solve_primal_host(self, sol, b0, atol=1e-14, rtol=1e-14, itmax=0):
         assert sol.dtype == np.float64 and sol.flags.c_contiguous
         b0 = _f64(b0)

@@ -74,6 +74,55 @@ extern "C" int asgfem_destroy(asgfem_ctx* ctx) {
     return 0;
 }
 
+// ---- samples as columns (deterministic reference solutions of the MC error, src/sampling_error.jl:84-128) -----------
+// For the affine coefficient a(x, xi) = a_0(x) + sum_m xi_m a_m(x) the deterministic problem of sample s has the matrix
+// K(xi_s) = K_0 + sum_m xi_{s,m} K_m on the pattern shared by all K_m.  With the samples as the columns of the vectors,
+// all nsamples systems are ONE block system with a diagonal coupling (G_m = diag(xi_{.,m})): the operator kernel, the
+// multi-RHS mean preconditioner K_0^-1 and the PCG of the SGFE solve apply unchanged (the reference solves the samples
+// one by one on host threads with ExtendableFEM.solve).
+extern "C" int asgfem_set_samples(asgfem_ctx* ctx, int64_t nsamples, int64_t Msamples, const double* samples) {
+    CTX_OR_FAIL(ctx);
+    ASG_CHECK(ctx, nsamples >= 1 && nsamples < 65536 && Msamples >= 0 && (samples || Msamples == 0), ASGFEM_EINVAL, "set_samples: bad arguments");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    free_vec_storage(ctx);
+    apply_free_plan(ctx);
+    apply_mma_free(ctx);
+    ctx->sample_mode = true;
+    ctx->mis = asgfem::MultiIndexSet();
+    ctx->coup = asgfem::Coupling();
+    ctx->N = nsamples;
+    ctx->ld = (nsamples + 31) / 32 * 32;
+    ctx->h_pos.resize((size_t)nsamples);
+    ctx->h_inv.assign((size_t)ctx->ld, -1);
+    for (int64_t k = 0; k < nsamples; ++k) ctx->h_pos[(size_t)k] = ctx->h_inv[(size_t)k] = (int32_t)k;
+    Coupling& CC = ctx->coup_col;
+    CC.ptr.assign((size_t)ctx->ld + 1, 0);
+    CC.m.clear();
+    CC.nu.clear();
+    CC.g.clear();
+    for (int64_t c = 0; c < ctx->ld; ++c) {
+        if (c < nsamples)
+            for (int64_t m = 0; m < Msamples; ++m) {  // directions beyond the uploaded matrices are rejected at the first apply
+                CC.m.push_back((int32_t)(m + 1));
+                CC.nu.push_back((int32_t)c);
+                CC.g.push_back(samples[m + Msamples * c]);
+            }
+        CC.ptr[(size_t)c + 1] = (int32_t)CC.m.size();
+    }
+    ctx->coup = CC;
+    ctx->coup.ptr.resize((size_t)nsamples + 1);
+    int rc = 0;
+    rc |= dev_upload(ctx, &ctx->d_cptr, CC.ptr);
+    rc |= dev_upload(ctx, &ctx->d_cm, CC.m);
+    rc |= dev_upload(ctx, &ctx->d_cnu, CC.nu);
+    rc |= dev_upload(ctx, &ctx->d_cg, CC.g);
+    rc |= dev_upload(ctx, &ctx->d_pos, ctx->h_pos);
+    rc |= dev_upload(ctx, &ctx->d_inv, ctx->h_inv);
+    if (rc) return rc;
+    ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // ---- multi-indices ----------------------------------------------------------------------------
 extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t N, int64_t M, const int64_t* mi) {
     CTX_OR_FAIL(ctx);
@@ -83,6 +132,7 @@ extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t 
     for (int64_t k = 0; k < N * M; ++k) ASG_CHECK(ctx, mi[k] >= 0, ASGFEM_EINVAL, "negative multi-index entry");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     free_vec_storage(ctx);  // vectors are sized by the column count, and the column order changes with the set
+    ctx->sample_mode = false;
     ctx->family = family;
     ctx->mis.N = N;
     ctx->mis.M = M;
@@ -732,6 +782,24 @@ extern "C" int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const doub
     if ((rc = pcg_solve(ctx, b0, ctx->slots[0], atol, rtol, itmax, stats))) return rc;
     return vec_to_host_layout(ctx, ctx->slots[0], sol);
 }
+
+// out (n x nsamples, column s = solution of sample s): K(xi_s) u_s = b with u_s = 0 on the Dirichlet dofs
+extern "C" int asgfem_solve_samples_host(asgfem_ctx* ctx, double* out, const double* b, double atol, double rtol, int64_t itmax,
+                                         asgfem_stats* stats) {
+    CTX_OR_FAIL(ctx);
+    ASG_CHECK(ctx, ctx->sample_mode, ASGFEM_ESTATE, "solve_samples: asgfem_set_samples first");
+    ASG_CHECK(ctx, out && b, ASGFEM_EINVAL, "null host pointer");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    int rc = ensure_ready_for_apply(ctx);
+    if (rc) return rc;
+    for (int32_t m : ctx->coup_col.m) ASG_CHECK(ctx, m <= ctx->M, ASGFEM_EINVAL, "solve_samples: more sample dimensions than stiffness matrices K_m");
+    if ((rc = ensure_work_slots(ctx, 1))) return rc;
+    ASG_CUDA(ctx, cudaMemsetAsync(ctx->slots[0], 0, sizeof(double) * (size_t)ctx->n * (size_t)ctx->ld, ctx->stream));
+    if (!ctx->precond && (rc = precond_setup(ctx))) return rc;
+    if ((rc = pcg_solve(ctx, b, ctx->slots[0], atol, rtol, itmax, stats))) return rc;
+    return vec_to_host_layout(ctx, ctx->slots[0], out);
+}
+
 
 // ---- log-transformed primal problem ----------------------------------------------------------------
 extern "C" int asgfem_set_precond_matrix_csc(asgfem_ctx* ctx, const int64_t* colptr, const int64_t* rowval,

@@ -103,7 +103,7 @@ int apply_ts2_build(asgfem_ctx* ctx) {
     const int64_t N = ctx->ld, nrows = ctx->n_owned >= 0 ? ctx->n_owned : ctx->n;
     const int M = ctx->M, Mp = M + 1;
     const Coupling& C = ctx->coup_col;
-    if (N <= 0 || M < 0 || M > 63) return 0;
+    if (N <= 0 || M < 0 || M > 63 || ctx->sample_mode) return 0;  // per-sample weights do not fit the 64-entry weight table
     int maxlen = 1;
     for (int64_t i = 0; i < nrows; ++i) maxlen = std::max<int>(maxlen, (int)(ctx->h_rowptr[i + 1] - ctx->h_rowptr[i]));
     P->NS = maxlen <= 7 ? 7 : 8;

@@ -130,6 +130,7 @@ struct asgfem_ctx {
 
     // kernels
     int apply_variant = 0;
+    bool sample_mode = false;  // columns = samples of the random vector (asgfem_set_samples): diagonal coupling, rhs in every column
     double last_apply_ms = 0;
     double last_estimate_ms = 0;
     bool apply_ready = false;  // kernel tables of the operator built for the current pattern / multi-index set

@@ -19,7 +19,7 @@ __global__ void k_make_rhs(double* __restrict__ b, const double* __restrict__ b0
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t i = t / ld, mu = t - i * ld;
         double v = b[t];
-        if (mu == col0) v += b0[i];  // device column of mode 1 (the mean mode)
+        if (mu == col0 || (col0 < 0 && mu < -col0 - 1)) v += b0[i];  // column of the mean mode, or the first -col0 - 1 columns
         b[t] = bmask[i] ? 0.0 : v;
     }
 }
@@ -106,7 +106,7 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
     tall.start();
     // b = deepcopy(sol); b[1] += b0; b[m][bdofs] = 0   -> stored in p for now
     PCG_CUDA(cudaMemcpyAsync(p, x, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_make_rhs<<<grid, 256, 0, ctx->stream>>>(p, b0, ctx->d_bmask, n, ld, (int64_t)ctx->h_pos[0]);
+    k_make_rhs<<<grid, 256, 0, ctx->stream>>>(p, b0, ctx->d_bmask, n, ld, ctx->sample_mode ? -(ctx->N + 1) : (int64_t)ctx->h_pos[0]);
     // r = b - A x
     PCG_RC(dist_apply(ctx, x, q));
     PCG_CUDA(cudaMemcpyAsync(r, p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -179,3 +179,28 @@ def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10
     eta4modes, eta4cell = ctx.estimate_poisson_primal(0, np.array(mi_ext, dtype=np.int64), xref, w, sf, wf,
                                                       g.ncells, fq)
     return eta4modes, eta4cell, mi_ext
+
+
+def deterministic_sample_solutions(FES, C, samples, rhs=None, bonus_quadorder_a=2, device=0, atol=1e-14, rtol=1e-14):
+    """The deterministic reference solutions of calculate_sampling_error (src/sampling_error.jl:112-128) for the affine
+    coefficient: for every column xi of `samples` (Msamples x nsamples) solve  -div((a_0 + sum_m xi_m a_m) grad u) = f  on
+    the space FES.  The reference runs ExtendableFEM.solve per sample on host threads; here all samples are the columns of
+    one device block system (asgfem_set_samples / asgfem_solve_samples_host).  Returns (u (ndofs x nsamples), stats)."""
+    samples = np.asarray(samples, dtype=np.float64)
+    Ms = samples.shape[0]
+    ctx = _ctx.Context(device)
+    try:
+        g = FES.grid
+        ctx.set_multiindices(0, np.zeros((1, max(Ms, 1)), dtype=np.int64))  # placeholder set: sizes the matrices
+        ctx.set_mesh(g.coords, g.cellnodes + 1)
+        ctx.set_space(FES.order, FES.ndofs, FES.celldofs + 1)
+        ctx.set_coefficient_cosinus(C.mean_value, C.decay_factors, C.b1, C.b2)
+        xref, w = _grids.quadrature_rule(2 * (FES.order - 1) + bonus_quadorder_a)
+        ctx.assemble_stiffness(Ms, xref, w)
+        ctx.set_bdofs(FES.bdofs + 1)
+        ctx.set_samples(samples)
+        b = FES.rhs(rhs)
+        b[FES.bdofs] = 0.0
+        return ctx.solve_samples_host(b, atol, rtol)
+    finally:
+        ctx.close()

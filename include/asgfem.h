@@ -213,6 +213,16 @@ int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ex
  * Vectors have n_local rows; only owned rows are written by apply.  The host layer (torch.distributed /
  * NCCL) exchanges halo rows between the pack/unpack calls and all-reduces the partial dots. */
 int asgfem_set_owned_rows(asgfem_ctx* ctx, int64_t n_owned);
+/* ---- deterministic reference solutions at samples (src/sampling_error.jl:84-128: ExtendableFEM.solve per sample on host
+ * threads).  For the affine coefficient the matrix of sample s is K_0 + sum_m xi[m, s] K_m; with the samples as the columns
+ * of the device vectors all nsamples problems are one block system with a diagonal coupling, solved by the same operator
+ * kernel / multi-RHS mean preconditioner / PCG as the SGFE system.  samples: Msamples x nsamples, column-major (Julia's
+ * Samples[:, s]); Msamples <= number of matrices K_m.  Replaces the multi-index set of the context (use a context of its
+ * own for the sampling space).  out: n x nsamples column-major. */
+int asgfem_set_samples(asgfem_ctx* ctx, int64_t nsamples, int64_t Msamples, const double* samples);
+int asgfem_solve_samples_host(asgfem_ctx* ctx, double* out, const double* b, double atol, double rtol, int64_t itmax,
+                              asgfem_stats* stats);
+
 /* Row-sharded estimator (cells and faces sharded with the rows, totals all-reduced).  The mesh of a
  * rank = its owned cells plus the layer of neighbouring cells whose dofs are its halo rows; owned[c] != 0 marks the cells it
  * owns (NULL: all cells again).  asgfem_estimate_poisson_primal then sums eta4modes over the owned cells, counts an interior

@@ -254,6 +254,23 @@ function estimate(::Type{PoissonProblemPrimal}, sol::SGFEVector, C::StochasticCo
 end
 
 """
+    deterministic_sample_solutions(ctx, Samples, b) -> Matrix (ndofs x nsamples)
+
+The deterministic reference solutions of `calculate_sampling_error` (src/sampling_error.jl:112-128) for the affine
+coefficient: `ctx` holds K_0..K_M of the SAMPLING space (`FES4sampling`), uploaded with `asgfem_set_stiffness_csc` or
+assembled on the device; all samples are solved at once as the columns of one block system.
+"""
+function deterministic_sample_solutions(ctx::Context, Samples::Matrix{Float64}, b::Vector{Float64}; atol = 1.0e-14, rtol = 1.0e-14)
+    check(ctx, ccall((:asgfem_set_samples, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}),
+        ctx.h, size(Samples, 2), size(Samples, 1), Samples))
+    out = zeros(Float64, length(b), size(Samples, 2))
+    stats = Ref{Stats}()
+    check(ctx, ccall((:asgfem_solve_samples_host, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Int64, Ref{Stats}), ctx.h, out, b, atol, rtol, 0, stats))
+    return out
+end
+
+"""
 Row-sharded runs (one Julia task / process per GPU, NCCL inside the library): `comm_init!` with the 128-byte id of
 `asgfem_comm_unique_id` (created on rank 0, distributed by the host layer), `set_halo!` with the 1-based local row lists,
 then `mul!` / `solve_primal!` work on the rank's row shard.  For the estimator the rank's mesh holds its owned cells plus

@@ -290,3 +290,23 @@ def solve_logpoisson_primal_full(A, N0, Nm, b0, G, nmodes, bdofs):
     big = S.assembled(penalty=1.0e60)
     bigb = make_rhs_log(np.zeros(n * nmodes), b0, bdofs, n, nmodes)
     return spla.spsolve(big.tocsc(), bigb)
+
+
+def deterministic_sample_solutions(A0, Am, b, bdofs, samples):
+    """Deterministic reference solutions of calculate_sampling_error (src/sampling_error.jl:112-128: one
+    ExtendableFEM.solve per sample) for the affine coefficient: K(xi) = A0 + sum_m xi_m Am[m], homogeneous Dirichlet data
+    on bdofs (the reference's penalty in exact arithmetic: eliminated rows / columns).  samples: (Msamples, nsamples).
+    Returns u of shape (n, nsamples)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n = A0.shape[0]
+    keep = np.ones(n, dtype=bool)
+    keep[np.asarray(bdofs)] = False
+    out = np.zeros((n, samples.shape[1]))
+    for s in range(samples.shape[1]):
+        K = sp.csr_matrix(A0, copy=True)
+        for m in range(samples.shape[0]):
+            K = K + samples[m, s] * Am[m]
+        K = sp.csc_matrix(K)[keep][:, keep]
+        out[keep, s] = spla.spsolve(K, np.asarray(b)[keep])
+    return out

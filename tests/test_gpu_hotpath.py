@@ -581,6 +581,27 @@ def test_apply_auto_variant_beyond_register_capacity():
     ctx.close()
 
 
+@pytest.mark.parametrize("order", [1, 2])
+def test_deterministic_sample_solutions_match_oracle(order):
+    """Row f4 (src/sampling_error.jl:112-128): the deterministic reference solutions at samples, all samples as columns
+    of one device block system, against one sparse direct solve per sample (1e-10 relative)."""
+    m = omesh.uniform_refine(omesh.grid_unitsquare(), 3)
+    Cc = ocoef.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=6)
+    Ms, ns = 6, 37
+    P = oproblem.build(m, order, [[0] * Ms], opoly.LEGENDRE, Cc, bonus_quadorder_a=2)
+    rng = np.random.default_rng(5)
+    samples = rng.uniform(-1, 1, size=(Ms, ns))
+    ref = osolver.deterministic_sample_solutions(P.A0, P.Am, P.b0, P.bdofs, samples)
+    g = A.Grid(m.coords, m.cellnodes, m.bfacenodes)
+    fes = A.FESpace(g, order)
+    from asgfem_b200 import sgfem
+    u, st = sgfem.deterministic_sample_solutions(fes, A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=6), samples)
+    assert st["solved"] and st["niter"] < 60
+    assert u.shape == ref.shape
+    assert np.max(np.abs(u - ref)) <= 1e-10 * np.max(np.abs(ref))
+    assert np.all(u[P.bdofs] == 0.0)
+
+
 @pytest.mark.parametrize("family", [opoly.LEGENDRE, opoly.HERMITE])
 def test_evaluate_samples_matches_oracle(family):
     """Row f4, set_sample! half (sgfevector.jl:43-69): u(x, xi_s) = sum_k H_k(xi_s) u_k for a batch of samples, with the
