@@ -38,6 +38,7 @@ struct BlkPlan {
     bool usable = false;
     int KS = 0, P = 1, NPW = 0, NG = 0, W = 16;
     bool lists_global = false;
+    bool single = false;  // one pass with a single T buffer (two barriers per dof row)
     uint32_t nwords = 0, off_pair = 0, off_crec = 0, off_gcol = 0, off_pbase = 0, off_srec = 0, off_list = 0, off_roww = 0, tbuf_doubles = 0;
     size_t smem_bytes = 0;
     uint32_t* d_blob = nullptr;
@@ -136,6 +137,8 @@ int apply_blk_build(asgfem_ctx* ctx) {
     if (total_steps == 0) return 0;
 
     auto align4 = [](uint32_t v) { return (v + 3u) & ~3u; };
+    bool try_single = true;
+    if (const char* e = getenv("ASGFEM_BLK_SINGLE")) try_single = atoi(e) != 0;
     // trial = (lists in shared memory, passes 1..8), then (lists in global memory, passes 1..64): the lists of many modes
     // (config 5: 37 k items) do not fit next to two T buffers
     for (int trial = 0; trial < 72; ++trial) {
@@ -376,12 +379,15 @@ int apply_blk_build(asgfem_ctx* ctx) {
         const uint32_t nwords = at;
         if ((off_roww - off_list) * 4u >= (1u << 20)) continue;
         const uint32_t nwords_smem = lists_global ? off_list : nwords;  // words copied into shared memory
-        const size_t smem = (size_t)nwords_smem * 4 + 8ull * (4 + 4 * KS) * 4ull + 3ull * (size_t)(Mp + 1) * krow_bytes + 2ull * tbuf * 8ull + 16;
+        // one pass with the lists in shared memory: a single T buffer (two barriers per dof row) if that is what fits
+        const bool single = npass == 1 && !lists_global && try_single;
+        const size_t smem = (size_t)nwords_smem * 4 + 8ull * (4 + 4 * KS) * 4ull + 3ull * (size_t)(Mp + 1) * krow_bytes +
+                            (single ? 1ull : 2ull) * tbuf * 8ull + 16;
         if (verbose)
             fprintf(stderr,
-                    "[blk] KS=%d W=%d passes=%d lists in %s NPW=%d NG=%d steps=%d T=%u doubles (x2) list rows %.0f (ideal %.0f) bank cost %ld -> %ld "
+                    "[blk] KS=%d W=%d passes=%d%s lists in %s NPW=%d NG=%d steps=%d T=%u doubles (x2) list rows %.0f (ideal %.0f) bank cost %ld -> %ld "
                     "tables=%u B smem=%zu B%s\n",
-                    KS, W, npass, lists_global ? "global memory" : "shared memory", NPW, NG, total_steps, tbuf, rows_total, rows_ideal,
+                    KS, W, npass, single ? " (single T buffer)" : "", lists_global ? "global memory" : "shared memory", NPW, NG, total_steps, tbuf, rows_total, rows_ideal,
                     conflicts_before, conflicts_after, nwords * 4, smem,
                     smem > (size_t)SMEM_LIMIT ? " (too large)" : "");
         if (smem > (size_t)SMEM_LIMIT) continue;
@@ -418,6 +424,7 @@ int apply_blk_build(asgfem_ctx* ctx) {
         B->W = W;
         B->nwords = nwords_smem;
         B->lists_global = lists_global;
+        B->single = single;
         B->off_pair = off_pair;
         B->off_crec = off_crec;
         B->off_gcol = off_gcol;
@@ -476,7 +483,7 @@ struct BlkArgs {
     const double* zero_row;
     const int32_t* rowmeta;
     int64_t nnz, ld, r0, r1;
-    int Mp, P;
+    int Mp, P, single;
     uint32_t nwords, off_pair, off_crec, off_gcol, off_pbase, off_srec, off_list, off_roww, tbuf_doubles;
 };
 
@@ -566,7 +573,7 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
         uint32_t* blob = reinterpret_cast<uint32_t*>(sm);
         for (uint32_t i = tid; i < a.nwords; i += THREADS) blob[i] = a.blob[i];
         double* z = reinterpret_cast<double*>(sm + a.nwords * 4u);
-        for (uint32_t i = tid; i < (RING * ME * 4u + 3u * kbuf_bytes + 2u * tb_bytes) / 8u; i += THREADS) z[i] = 0.0;
+        for (uint32_t i = tid; i < (RING * ME * 4u + 3u * kbuf_bytes + (a.single ? 1u : 2u) * tb_bytes) / 8u; i += THREADS) z[i] = 0.0;
     }
     __syncthreads();
 
@@ -665,9 +672,141 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
     b_cp_async_wait_all();
     __syncthreads();
 
+    int kcur = 0, knew = LA;  // K buffers of row ri and of row ri + LA (LA < KB)
+    // products of (row ri, pass) into T buffer par; X fragments of the next stage are loaded at the end
+    auto do_produce = [&](int ri, int pass, uint32_t par) {
+        if (pass == 0) {
+            if (ri + 2 * LA < nri) meta_fetch(ri + 2 * LA);
+            if (ri + LA < nri) stage_k(ri + LA, knew);
+        }
+        int npass = pass + 1;
+        int nxt = ri;
+        if (npass == a.P) npass = 0, ++nxt;
+        const unsigned tb = tb_s + par * tb_bytes + lane * 16;
+        const unsigned ksrc = ks_s + (unsigned)kcur * kbuf_bytes + kk * (8 * KS);
+        const unsigned sbase = srec_s + b_lds_u32(sm0 + a.off_pbase * 4u + pass * 4) * 32u;
+        uint32_t pw[NPW];
+        if constexpr (NPW == 2) {
+            const uint2 v = b_lds_u32x2(pair_s + pass * (WARPS * NPW * 4));
+            pw[0] = v.x, pw[1] = v.y;
+        } else {
+#pragma unroll
+            for (int p4 = 0; p4 < NPW / 4; ++p4) {
+                const uint4 v = b_lds_u32x4(pair_s + pass * (WARPS * NPW * 4) + p4 * 16);
+                pw[4 * p4] = v.x, pw[4 * p4 + 1] = v.y, pw[4 * p4 + 2] = v.z, pw[4 * p4 + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NPW; ++p) {
+            const uint32_t nst = (pw[p] >> 12) & 0xFu;
+            if (nst != 0) {  // warp-uniform
+                double xe[KS], xo[KS];
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    xe[s] = __shfl_sync(0xffffffffu, X[p][s].x, frag_src);
+                    xo[s] = __shfl_sync(0xffffffffu, X[p][s].y, frag_src);
+                }
+                const uint32_t slot = pw[p] >> 16;
+                unsigned sr = sbase + slot * 32u;
+                unsigned td = tb + slot * 1024u;
+                for (uint32_t st = 0; st < nst; ++st, sr += 32u, td += 1024u) {
+                    const uint32_t w = b_lds_u32(sr);
+                    const unsigned ke = ksrc + (w & 0xFFFFu), ko = ksrc + (w >> 16);
+                    double ae[KS], ao[KS];
+#pragma unroll
+                    for (int s = 0; s < KS; s += 2) {
+                        const double2 ve = b_lds_f64x2(ke + s * 8), vo = b_lds_f64x2(ko + s * 8);
+                        ae[s] = ve.x, ae[s + 1] = ve.y;
+                        ao[s] = vo.x, ao[s + 1] = vo.y;
+                    }
+                    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        b_dmma(c0, c1, ae[s], xe[s]);
+                        b_dmma(c2, c3, ao[s], xo[s]);
+                    }
+                    b_sts_f64x2(td, c0, c1);
+                    b_sts_f64x2(td + 512u, c2, c3);
+                }
+            }
+        }
+        // X fragments of the next stage: one batch of loads, in flight during the list sums / the barrier
+        if (nxt < nri) {
+            if (npass == 0) row_ptrs(nxt, xr);
+            load_x(npass, xr, X);
+        }
+    };
+    // weighted list sums of (row cri, pass cpass) from T buffer par into the accumulators; the last pass writes the Y row
+    auto do_consume = [&](int cri, int cpass, uint32_t par) {
+        // ---- consume the previous stage from the other buffer: weighted list sums of the groups of this warp ---------
+        const int64_t crow = rb + (int64_t)cri * rstep;
+        const bool last = cpass == a.P - 1;
+        uint8_t bm = 0;
+        if (last) bm = a.bmask[crow];  // in flight during the sums
+        const unsigned tbr = tb_s + (par ^ 1u) * tb_bytes;
+        uint32_t cw[NG];
+        if constexpr (NG == 2) {
+            const uint2 v = b_lds_u32x2(crec_s + cpass * (WARPS * NG * 4));
+            cw[0] = v.x, cw[1] = v.y;
+        } else {
+#pragma unroll
+            for (int g4 = 0; g4 < NG / 4; ++g4) {
+                const uint4 v = b_lds_u32x4(crec_s + cpass * (WARPS * NG * 4) + g4 * 16);
+                cw[4 * g4] = v.x, cw[4 * g4 + 1] = v.y, cw[4 * g4 + 2] = v.z, cw[4 * g4 + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint32_t lo = cw[g] & 0xFFFFFu, wo = lo >> 3;
+            double t0 = acc[g], t1 = 0.0;
+            uint32_t r = cw[g] >> 20;
+            while (r >= 2) {  // 4 list rows per trip: independent loads first
+                const uint32_t i0 = ld_idx(lo), i1 = ld_idx(lo + 128);
+                const double2 w0 = ld_w(wo), w1 = ld_w(wo + 16);
+                const double v0 = b_lds_f64(tbr + (i0 & 0xFFFFu) * 8u), v1 = b_lds_f64(tbr + (i0 >> 16) * 8u);
+                const double v2 = b_lds_f64(tbr + (i1 & 0xFFFFu) * 8u), v3 = b_lds_f64(tbr + (i1 >> 16) * 8u);
+                t0 = fma(w0.x, v0, t0);
+                t1 = fma(w0.y, v1, t1);
+                t0 = fma(w1.x, v2, t0);
+                t1 = fma(w1.y, v3, t1);
+                lo += 256, wo += 32, r -= 2;
+            }
+            if (r) {
+                const uint32_t i0 = ld_idx(lo);
+                const double2 w0 = ld_w(wo);
+                const double v0 = b_lds_f64(tbr + (i0 & 0xFFFFu) * 8u), v1 = b_lds_f64(tbr + (i0 >> 16) * 8u);
+                t0 = fma(w0.x, v0, t0);
+                t1 = fma(w0.y, v1, t1);
+            }
+            acc[g] = t0 + t1;
+        }
+        if (last) {
+            unsigned char* yr = reinterpret_cast<unsigned char*>(a.y + crow * a.ld);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (ycol[g] != 0xFFFFFFFFu) *reinterpret_cast<double*>(yr + ycol[g]) = bm ? 0.0 : acc[g];
+                acc[g] = 0.0;
+            }
+        }
+    };
+
+    if (a.single) {
+        // one pass, ONE T buffer: produce | barrier | sum the lists | barrier.  Fewer list rows (no split of a column's list
+        // over passes) and half the per-stage overhead; the two phases no longer overlap.
+        for (int ri = 0; ri < nri; ++ri) {
+            do_produce(ri, 0, 0u);
+            __syncthreads();
+            do_consume(ri, 0, 1u);  // reads buffer (1 ^ 1) = 0
+            b_cp_async_commit();
+            b_cp_async_wait_1();
+            __syncthreads();
+            kcur = kcur + 1 == KB ? 0 : kcur + 1;
+            knew = knew + 1 == KB ? 0 : knew + 1;
+        }
+        return;
+    }
     int pass = 0;
     int ri = 0;
-    int kcur = 0, knew = LA;  // K buffers of row ri and of row ri + LA (LA < KB)
     uint32_t par = 0;  // parity of the stage = T buffer
     bool have_prev = false;
     int cpass = 0;
@@ -677,119 +816,9 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
         // odd warps consume first: the shared-memory reads of one half of the warps overlap the fp64 products of the other
         for (int phase = 0; phase < 2; ++phase) {
             if (phase == (warp & 1)) {
-                if (produce) {
-                    if (pass == 0) {
-                        if (ri + 2 * LA < nri) meta_fetch(ri + 2 * LA);
-                        if (ri + LA < nri) stage_k(ri + LA, knew);
-                    }
-                    int npass = pass + 1;
-                    int nxt = ri;
-                    if (npass == a.P) npass = 0, ++nxt;
-                    const unsigned tb = tb_s + par * tb_bytes + lane * 16;
-                    const unsigned ksrc = ks_s + (unsigned)kcur * kbuf_bytes + kk * (8 * KS);
-                    const unsigned sbase = srec_s + b_lds_u32(sm0 + a.off_pbase * 4u + pass * 4) * 32u;
-                    uint32_t pw[NPW];
-                    if constexpr (NPW == 2) {
-                        const uint2 v = b_lds_u32x2(pair_s + pass * (WARPS * NPW * 4));
-                        pw[0] = v.x, pw[1] = v.y;
-                    } else {
-#pragma unroll
-                        for (int p4 = 0; p4 < NPW / 4; ++p4) {
-                            const uint4 v = b_lds_u32x4(pair_s + pass * (WARPS * NPW * 4) + p4 * 16);
-                            pw[4 * p4] = v.x, pw[4 * p4 + 1] = v.y, pw[4 * p4 + 2] = v.z, pw[4 * p4 + 3] = v.w;
-                        }
-                    }
-#pragma unroll
-                    for (int p = 0; p < NPW; ++p) {
-                        const uint32_t nst = (pw[p] >> 12) & 0xFu;
-                        if (nst != 0) {  // warp-uniform
-                            double xe[KS], xo[KS];
-#pragma unroll
-                            for (int s = 0; s < KS; ++s) {
-                                xe[s] = __shfl_sync(0xffffffffu, X[p][s].x, frag_src);
-                                xo[s] = __shfl_sync(0xffffffffu, X[p][s].y, frag_src);
-                            }
-                            const uint32_t slot = pw[p] >> 16;
-                            unsigned sr = sbase + slot * 32u;
-                            unsigned td = tb + slot * 1024u;
-                            for (uint32_t st = 0; st < nst; ++st, sr += 32u, td += 1024u) {
-                                const uint32_t w = b_lds_u32(sr);
-                                const unsigned ke = ksrc + (w & 0xFFFFu), ko = ksrc + (w >> 16);
-                                double ae[KS], ao[KS];
-#pragma unroll
-                                for (int s = 0; s < KS; s += 2) {
-                                    const double2 ve = b_lds_f64x2(ke + s * 8), vo = b_lds_f64x2(ko + s * 8);
-                                    ae[s] = ve.x, ae[s + 1] = ve.y;
-                                    ao[s] = vo.x, ao[s + 1] = vo.y;
-                                }
-                                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-#pragma unroll
-                                for (int s = 0; s < KS; ++s) {
-                                    b_dmma(c0, c1, ae[s], xe[s]);
-                                    b_dmma(c2, c3, ao[s], xo[s]);
-                                }
-                                b_sts_f64x2(td, c0, c1);
-                                b_sts_f64x2(td + 512u, c2, c3);
-                            }
-                        }
-                    }
-                    // X fragments of the next stage: one batch of loads, in flight during the list sums / the barrier
-                    if (nxt < nri) {
-                        if (npass == 0) row_ptrs(nxt, xr);
-                        load_x(npass, xr, X);
-                    }
-                }
+                if (produce) do_produce(ri, pass, par);
             } else if (have_prev) {
-                // ---- consume the previous stage from the other buffer: weighted list sums of the groups of this warp ---------
-                const int64_t crow = rb + (int64_t)cri * rstep;
-                const bool last = cpass == a.P - 1;
-                uint8_t bm = 0;
-                if (last) bm = a.bmask[crow];  // in flight during the sums
-                const unsigned tbr = tb_s + (par ^ 1u) * tb_bytes;
-                uint32_t cw[NG];
-                if constexpr (NG == 2) {
-                    const uint2 v = b_lds_u32x2(crec_s + cpass * (WARPS * NG * 4));
-                    cw[0] = v.x, cw[1] = v.y;
-                } else {
-#pragma unroll
-                    for (int g4 = 0; g4 < NG / 4; ++g4) {
-                        const uint4 v = b_lds_u32x4(crec_s + cpass * (WARPS * NG * 4) + g4 * 16);
-                        cw[4 * g4] = v.x, cw[4 * g4 + 1] = v.y, cw[4 * g4 + 2] = v.z, cw[4 * g4 + 3] = v.w;
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    uint32_t lo = cw[g] & 0xFFFFFu, wo = lo >> 3;
-                    double t0 = acc[g], t1 = 0.0;
-                    uint32_t r = cw[g] >> 20;
-                    while (r >= 2) {  // 4 list rows per trip: independent loads first
-                        const uint32_t i0 = ld_idx(lo), i1 = ld_idx(lo + 128);
-                        const double2 w0 = ld_w(wo), w1 = ld_w(wo + 16);
-                        const double v0 = b_lds_f64(tbr + (i0 & 0xFFFFu) * 8u), v1 = b_lds_f64(tbr + (i0 >> 16) * 8u);
-                        const double v2 = b_lds_f64(tbr + (i1 & 0xFFFFu) * 8u), v3 = b_lds_f64(tbr + (i1 >> 16) * 8u);
-                        t0 = fma(w0.x, v0, t0);
-                        t1 = fma(w0.y, v1, t1);
-                        t0 = fma(w1.x, v2, t0);
-                        t1 = fma(w1.y, v3, t1);
-                        lo += 256, wo += 32, r -= 2;
-                    }
-                    if (r) {
-                        const uint32_t i0 = ld_idx(lo);
-                        const double2 w0 = ld_w(wo);
-                        const double v0 = b_lds_f64(tbr + (i0 & 0xFFFFu) * 8u), v1 = b_lds_f64(tbr + (i0 >> 16) * 8u);
-                        t0 = fma(w0.x, v0, t0);
-                        t1 = fma(w0.y, v1, t1);
-                    }
-                    acc[g] = t0 + t1;
-                }
-                if (last) {
-                    unsigned char* yr = reinterpret_cast<unsigned char*>(a.y + crow * a.ld);
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        if (ycol[g] != 0xFFFFFFFFu) *reinterpret_cast<double*>(yr + ycol[g]) = bm ? 0.0 : acc[g];
-                        acc[g] = 0.0;
-                    }
-                }
+                do_consume(cri, cpass, par);
             }
         }
         b_cp_async_commit();
@@ -863,6 +892,7 @@ int apply_blk_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
     a.r1 = r1;
     a.Mp = ctx->M + 1;
     a.P = B->P;
+    a.single = B->single ? 1 : 0;
     a.nwords = B->nwords;
     a.off_pair = B->off_pair;
     a.off_crec = B->off_crec;

@@ -18,7 +18,7 @@ mangled = None
 lines = dis.split("\n")
 # find the function whose demangled template args match the kernel name of the report
 m = re.search(r"(k_apply_\w+)<([^>]*)>", kname)
-tag = m.group(1) + "I" + "".join("Li%sE" % a for a in re.findall(r"\(int\)(\d+)", m.group(2))) + "E" if m else ksub
+tag = m.group(1) + "I" + "".join(("Li%sE" if t == "int" else "Lb%sE") % a for t, a in re.findall(r"\((int|bool)\)(\d+)", m.group(2))) + "E" if m else ksub
 start = None
 for i, l in enumerate(lines):
     if l.startswith("_ZN") and tag in l and l.rstrip().endswith(":"):
