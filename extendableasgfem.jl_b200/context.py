@@ -337,6 +337,20 @@ class Context:
             _ptr(wf), _ptr(eta4cell), _ptr(eta4modes)))
         return eta4modes, eta4cell.T  # view as ncells x N_ext
 
+    def estimate_poisson_primal_marking(self, slot_u, mi_ext, xref, w, sf, wf, ncells, sel_cols_1based, f_at_qp=None):
+        """eta4modes and the per-cell sum of eta4cell over the selected columns (no ncells x N_ext transfer)."""
+        mi = _i64(np.asarray(mi_ext))
+        N_ext, M_ext = mi.shape
+        xref, w, sf, wf = _f64(xref), _f64(w), _f64(sf), _f64(wf)
+        fq = None if f_at_qp is None else _f64(f_at_qp)
+        sel = _i64(np.asarray(sel_cols_1based))
+        cellsum = np.zeros(ncells)
+        eta4modes = np.zeros(N_ext)
+        self._ck(self.lib.asgfem_estimate_poisson_primal_marking(
+            self.h, slot_u, N_ext, M_ext, _ptr(mi), len(w), _ptr(xref), _ptr(w), _ptr(fq), len(wf), _ptr(sf),
+            _ptr(wf), len(sel), _ptr(sel), _ptr(cellsum), _ptr(eta4modes)))
+        return eta4modes, cellsum
+
     # ---- multi-GPU helpers -----------------------------------------------------------------------
     def set_owned_rows(self, n_owned):
         self._ck(self.lib.asgfem_set_owned_rows(self.h, n_owned))

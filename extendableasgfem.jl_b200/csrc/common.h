@@ -243,6 +243,7 @@ int assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xre
 // estimate.cu
 int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
                             int32_t nq, const double* xref, const double* w, const double* f_at_qp, int32_t nqf,
-                            const double* sf, const double* wf, double* eta4cell, double* eta4modes);
+                            const double* sf, const double* wf, double* eta4cell, double* eta4modes, int64_t nsel = -1,
+                            const int64_t* sel = nullptr, double* cellsum = nullptr);
 
 }  // namespace asgfem

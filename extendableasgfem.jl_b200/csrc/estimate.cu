@@ -237,6 +237,17 @@ __global__ void k_colsum_partial(const double* __restrict__ A, int64_t nrows, in
     part[(int64_t)blockIdx.x * ncols + j] = s;
 }
 
+// cellsum[c] = sum over the selected columns of E[c, .]   (marking indicator sum(eta4cell[:, actives], dims = 2),
+// scripts/poisson.jl:402), columns in the given order
+__global__ void k_rowsum_selected(const double* __restrict__ E, int64_t ncells, int64_t ldE, const int32_t* __restrict__ sel, int nsel,
+                                  double* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    double s = 0.0;
+    for (int k = 0; k < nsel; ++k) s += E[c * ldE + sel[k]];
+    out[c] = s;
+}
+
 __global__ void k_colsum_final(const double* __restrict__ part, int nchunks, int ncols, double* __restrict__ out) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
@@ -289,7 +300,8 @@ struct DevBuf {
 
 int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
                             int32_t nq, const double* xref, const double* w, const double* f_at_qp, int32_t nqf,
-                            const double* sf, const double* wf, double* eta4cell, double* eta4modes) {
+                            const double* sf, const double* wf, double* eta4cell, double* eta4modes, int64_t nsel,
+                            const int64_t* sel, double* cellsum) {
     const int64_t N = ctx->N, Mact = ctx->mis.M, ncells = ctx->ncells;
     // the active modes must be the first N extended modes (padded with zeros) - estimate.jl relies on this
     for (int64_t j = 0; j < N; ++j)
@@ -458,25 +470,42 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
     std::vector<double> sums((size_t)(2 * N_ext));
     ASG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums.p, sizeof(double) * 2 * N_ext, cudaMemcpyDeviceToHost, ctx->stream));
 
-    // eta4cell to the host in the Julia layout (ncells x N_ext, column-major), chunk of columns at a time.  The caller's
-    // array is pageable; pinning it for the duration of the call turns the copies into direct DMA (large outputs only)
-    const size_t out_bytes = sizeof(double) * (size_t)ncells * (size_t)N_ext;
-    const bool pinned_out = out_bytes >= (64u << 20) && cudaHostRegister(eta4cell, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
-    if (!pinned_out) (void)cudaGetLastError();
-    struct Unpin {
-        void* p;
-        ~Unpin() {
-            if (p) cudaHostUnregister(p);
+    // marking indicator: row sums over the selected columns (what scripts/poisson.jl:402 takes from eta4cell) - ncells doubles
+    // instead of the ncells x N_ext matrix
+    DevBuf d_sel, d_cs;
+    if (cellsum && nsel >= 0) {
+        std::vector<int32_t> sel32((size_t)std::max<int64_t>(nsel, 1), 0);
+        for (int64_t k = 0; k < nsel; ++k) {
+            ASG_CHECK(ctx, sel[k] >= 1 && sel[k] <= N_ext, ASGFEM_EINVAL, "estimate: selected column out of range");
+            sel32[(size_t)k] = (int32_t)(sel[k] - 1);
         }
-    } unpin{pinned_out ? (void*)eta4cell : nullptr};
-    int64_t jc_max = std::max<int64_t>(1, std::min<int64_t>(N_ext, (256ll << 20) / (8 * std::max<int64_t>(ncells, 1))));
-    ASG_CUDA(ctx, cudaMalloc(&d_stage.p, sizeof(double) * ncells * jc_max));
-    for (int64_t j0 = 0; j0 < N_ext; j0 += jc_max) {
-        int jc = (int)std::min<int64_t>(jc_max, N_ext - j0);
-        dim3 g((unsigned)((ncells + 31) / 32), (unsigned)((jc + 31) / 32));
-        k_cols_to_stage<<<g, dim3(32, 8), 0, ctx->stream>>>(a.E, (double*)d_stage.p, ncells, ldE, j0, jc);
-        ASG_CUDA(ctx, cudaMemcpyAsync(eta4cell + ncells * j0, d_stage.p, sizeof(double) * ncells * jc, cudaMemcpyDeviceToHost,
-                                      ctx->stream));
+        if ((rc = upload(d_sel, sel32.data(), sizeof(int32_t) * sel32.size()))) return rc;
+        ASG_CUDA(ctx, cudaMalloc(&d_cs.p, sizeof(double) * (size_t)ncells));
+        k_rowsum_selected<<<(unsigned)((ncells + 127) / 128), 128, 0, ctx->stream>>>(a.E, ncells, ldE, (const int32_t*)d_sel.p, (int)nsel,
+                                                                                  (double*)d_cs.p);
+        ASG_CUDA(ctx, cudaMemcpyAsync(cellsum, d_cs.p, sizeof(double) * (size_t)ncells, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (eta4cell) {
+        // eta4cell to the host in the Julia layout (ncells x N_ext, column-major), chunk of columns at a time.  The caller's
+        // array is pageable; pinning it for the duration of the call turns the copies into direct DMA (large outputs only)
+        const size_t out_bytes = sizeof(double) * (size_t)ncells * (size_t)N_ext;
+        const bool pinned_out = out_bytes >= (64u << 20) && cudaHostRegister(eta4cell, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
+        if (!pinned_out) (void)cudaGetLastError();
+        struct Unpin {
+            void* p;
+            ~Unpin() {
+                if (p) cudaHostUnregister(p);
+            }
+        } unpin{pinned_out ? (void*)eta4cell : nullptr};
+        int64_t jc_max = std::max<int64_t>(1, std::min<int64_t>(N_ext, (256ll << 20) / (8 * std::max<int64_t>(ncells, 1))));
+        ASG_CUDA(ctx, cudaMalloc(&d_stage.p, sizeof(double) * ncells * jc_max));
+        for (int64_t j0 = 0; j0 < N_ext; j0 += jc_max) {
+            int jc = (int)std::min<int64_t>(jc_max, N_ext - j0);
+            dim3 g((unsigned)((ncells + 31) / 32), (unsigned)((jc + 31) / 32));
+            k_cols_to_stage<<<g, dim3(32, 8), 0, ctx->stream>>>(a.E, (double*)d_stage.p, ncells, ldE, j0, jc);
+            ASG_CUDA(ctx, cudaMemcpyAsync(eta4cell + ncells * j0, d_stage.p, sizeof(double) * ncells * jc, cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+        }
     }
     ASG_CUDA(ctx, cudaGetLastError());
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

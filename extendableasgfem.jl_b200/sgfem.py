@@ -159,9 +159,11 @@ def ldiv(ctx: _ctx.Context, b):
     return ctx.precond_apply_host(b)
 
 
-def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10, 2)):
+def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10, 2), marking_columns=None):
     """Returns (eta4modes, eta4cell, multi_indices_extended) like estimate.jl:417.  Requires the device problem
-    (setup_device_problem / solve) so that mesh, space and coefficient are resident."""
+    (setup_device_problem / solve) so that mesh, space and coefficient are resident.  With marking_columns (1-based column
+    ids, e.g. the active modes) the second return value is the per-cell sum of eta4cell over these columns - what the
+    adaptive loop hands to bulk_mark (scripts/poisson.jl:402) - and the ncells x N_ext matrix never leaves the device."""
     ctx, FES = sol.TB.ctx, sol.FES_space
     g = FES.grid
     mi_ext = _mi.add_boundary_modes(sol.TB.multi_indices, tail_extension=tail_extension)
@@ -176,6 +178,10 @@ def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10
         fq = rhs(xq[:, :, 0], xq[:, :, 1])  # (ncells, nq) C-order == nq x ncells column-major
     ctx.vec_alloc(max(1, 1))
     ctx.vec_upload(0, sol.entries)
+    if marking_columns is not None:
+        eta4modes, cellsum = ctx.estimate_poisson_primal_marking(0, np.array(mi_ext, dtype=np.int64), xref, w, sf, wf,
+                                                                 g.ncells, marking_columns, fq)
+        return eta4modes, cellsum, mi_ext
     eta4modes, eta4cell = ctx.estimate_poisson_primal(0, np.array(mi_ext, dtype=np.int64), xref, w, sf, wf,
                                                       g.ncells, fq)
     return eta4modes, eta4cell, mi_ext

@@ -207,6 +207,14 @@ int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ex
                                    const double* f_at_qp, int32_t nqf, const double* sf, const double* wf,
                                    double* eta4cell, double* eta4modes);
 
+/* The same estimator with the outputs the adaptive loop consumes (scripts/poisson.jl:341-420): eta4modes and
+ * cellsum[c] = sum_k eta4cell[c, sel[k]] (sel: 1-based columns, e.g. the active modes - the indicator handed to bulk_mark
+ * at :402) instead of the ncells x N_ext matrix, whose transfer to the host dominates the call above. */
+int asgfem_estimate_poisson_primal_marking(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,
+                                           const int64_t* mi_ext, int32_t nq, const double* xref, const double* w,
+                                           const double* f_at_qp, int32_t nqf, const double* sf, const double* wf,
+                                           int64_t nsel, const int64_t* sel, double* cellsum, double* eta4modes);
+
 /* ---- (e) row-sharded multi-GPU operation --------------------------------------------------------
  * One context per rank/GPU.  The context holds the LOCAL rows of every K_m with local column ids:
  * columns 0..n_owned-1 are the owned dofs, n_owned..n_local-1 the halo dofs (owned by neighbours).

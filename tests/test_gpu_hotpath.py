@@ -383,6 +383,11 @@ def test_estimator_matches_oracle(order, domain):
 
     if domain == "lshape":  # non-degenerate indicators (no exact ties) -> the marked set must be identical
         assert marked(gc[:, act].sum(axis=1)) == marked(ec[:, act].sum(axis=1))
+    # the marking-oriented call: eta4modes and the active-mode row sums only (no ncells x N_ext transfer)
+    gm2, cs, _ = A.estimate(sol, None, rhs=f, bonus_quadorder=2, tail_extension=(10, 2), marking_columns=np.arange(1, P.N + 1))
+    assert np.array_equal(gm2, gm)
+    assert np.abs(cs - gc[:, act].sum(axis=1)).max() <= 1e-14 * np.abs(cs).max()
+    assert np.abs(cs - ec[:, act].sum(axis=1)).max() <= TOL_SOLVE * ec.max()
     TB.ctx.close()
 
 
