@@ -136,7 +136,14 @@ class Context:
 
     # ---- vectors ---------------------------------------------------------------------------------
     def vec_alloc(self, nslots):
+        """Sets the number of device vector slots; slots with index >= nslots are FREED (asgfem_vec_alloc)."""
         self._ck(self.lib.asgfem_vec_alloc(self.h, nslots))
+        self._nslots = nslots
+
+    def vec_ensure(self, nslots):
+        """Grow-only variant for helpers that need scratch slots: existing vectors of the caller survive."""
+        if getattr(self, "_nslots", 0) < nslots:
+            self.vec_alloc(nslots)
 
     def vec_upload(self, slot, host):
         host = _f64(host)

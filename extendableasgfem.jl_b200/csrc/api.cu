@@ -235,6 +235,7 @@ static int install_pattern(asgfem_ctx* ctx, int64_t n, const std::vector<int64_t
     int64_t nnz = (int64_t)row0.size();
     ASG_CHECK(ctx, nnz < (1ll << 31) - 1, ASGFEM_EINVAL, "pattern with >= 2^31 nonzeros not supported");
     if (n != ctx->n) free_vec_storage(ctx);
+    ctx->pattern_from_space = false;  // asgfem_assemble_stiffness sets it for the pattern it derives
     ctx->n = n;
     ctx->nnz = nnz;
     ctx->h_csc_colptr = colptr0;
@@ -395,11 +396,35 @@ extern "C" int asgfem_set_bdofs(asgfem_ctx* ctx, int64_t nb, const int64_t* bdof
 }
 
 // ---- mesh / space / coefficient -----------------------------------------------------------------
+// A pattern derived from celldofs (asgfem_assemble_stiffness without asgfem_set_pattern_csc) belongs to the mesh / space it
+// was built from: a new mesh or space drops it together with the matrices, the operator plans and the preconditioner, so
+// that the next assembly rebuilds it (otherwise a space with the same ndofs but other connectivity would be assembled on
+// the stale pattern).
+static void drop_derived_pattern(asgfem_ctx* ctx) {
+    if (!ctx->pattern_from_space) return;
+    ctx->pattern_from_space = false;
+    ctx->h_rowptr.clear();
+    ctx->h_col.clear();
+    ctx->h_csc_colptr.clear();
+    ctx->h_csc_row.clear();
+    ctx->h_csc2csr.clear();
+    ctx->nnz = 0;
+    ctx->M = -1;
+    if (ctx->d_vals) {
+        cudaFree(ctx->d_vals);
+        ctx->d_vals = nullptr;
+    }
+    apply_free_plan(ctx);
+    precond_free(ctx);
+}
+
 extern "C" int asgfem_set_mesh(asgfem_ctx* ctx, int64_t nnodes, int64_t ncells, const double* coords,
                                const int32_t* cellnodes) {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, nnodes >= 3 && ncells >= 1 && coords && cellnodes, ASGFEM_EINVAL, "set_mesh: bad arguments");
     if (set_device(ctx)) return ASGFEM_ECUDA;
+    drop_derived_pattern(ctx);
+    ctx->h_cell_owned.clear();
     ctx->nnodes = nnodes;
     ctx->ncells = ncells;
     ctx->h_coords.assign(coords, coords + 2 * nnodes);
@@ -423,6 +448,7 @@ extern "C" int asgfem_set_space(asgfem_ctx* ctx, int32_t order, int64_t ndofs, i
               "set_space: only H1Pk{1,2,1} (3 dofs/cell) and H1Pk{1,2,2} (6 dofs/cell) are supported");
     ASG_CHECK(ctx, ndofs >= 3 && celldofs, ASGFEM_EINVAL, "set_space: bad arguments");
     if (set_device(ctx)) return ASGFEM_ECUDA;
+    drop_derived_pattern(ctx);
     ctx->order = order;
     ctx->ndofs4cell = ndofs4cell;
     ctx->ndofs_space = ndofs;
@@ -496,6 +522,7 @@ extern "C" int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq,
         }
         int rc = install_pattern(ctx, n, cp, rv);
         if (rc) return rc;
+        ctx->pattern_from_space = true;
     }
     ASG_CHECK(ctx, ctx->n == ctx->ndofs_space, ASGFEM_EINVAL, "assemble_stiffness: pattern size differs from ndofs of the space");
     int rc = asgfem_set_num_stiffness(ctx, M);

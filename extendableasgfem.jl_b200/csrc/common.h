@@ -74,6 +74,7 @@ struct asgfem_ctx {
     std::vector<int64_t> h_rowptr;
     std::vector<int32_t> h_col;
     std::vector<int64_t> h_csc_colptr;  // caller's CSC (0-based) for get_pattern / set_stiffness
+    bool pattern_from_space = false;    // pattern derived from celldofs by asgfem_assemble_stiffness (dropped by set_mesh / set_space)
     std::vector<int32_t> h_csc_row;
     std::vector<int64_t> h_csc2csr;     // position in CSR of CSC entry p
     int64_t* d_rowptr = nullptr;

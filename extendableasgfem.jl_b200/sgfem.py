@@ -122,7 +122,7 @@ def set_samples(sol: SGFEVector, vals):
     (tensorizedbasis.jl:226-236, the caller's polynomial tables).  Returns the (nsamples, n) array of evaluated spatial
     coefficient vectors (row s = SGFEV.FEV entries for sample s); the sum over the modes runs on the device."""
     ctx = sol.TB.ctx
-    ctx.vec_alloc(1)
+    ctx.vec_ensure(1)  # grow-only: the caller's other device vectors survive (slot 0 is overwritten)
     ctx.vec_upload(0, sol.entries)
     return ctx.evaluate_samples(0, vals)
 
@@ -164,6 +164,8 @@ def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10
     (setup_device_problem / solve) so that mesh, space and coefficient are resident.  With marking_columns (1-based column
     ids, e.g. the active modes) the second return value is the per-cell sum of eta4cell over these columns - what the
     adaptive loop hands to bulk_mark (scripts/poisson.jl:402) - and the ncells x N_ext matrix never leaves the device."""
+    if rhs is None:  # the reference calls rhs(ftemp, x) unconditionally (estimate.jl:322): no silent default
+        raise ValueError("estimate: the right-hand side function rhs(x, y) is required")
     ctx, FES = sol.TB.ctx, sol.FES_space
     g = FES.grid
     mi_ext = _mi.add_boundary_modes(sol.TB.multi_indices, tail_extension=tail_extension)
@@ -176,7 +178,7 @@ def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10
         x1, x2, x3 = g.coords[c[:, 0]], g.coords[c[:, 1]], g.coords[c[:, 2]]
         xq = x1[:, None, :] + xref[None, :, 0:1] * (x2 - x1)[:, None, :] + xref[None, :, 1:2] * (x3 - x1)[:, None, :]
         fq = rhs(xq[:, :, 0], xq[:, :, 1])  # (ncells, nq) C-order == nq x ncells column-major
-    ctx.vec_alloc(max(1, 1))
+    ctx.vec_ensure(1)  # grow-only: the caller's other device vectors survive (slot 0 is overwritten)
     ctx.vec_upload(0, sol.entries)
     if marking_columns is not None:
         eta4modes, cellsum = ctx.estimate_poisson_primal_marking(0, np.array(mi_ext, dtype=np.int64), xref, w, sf, wf,

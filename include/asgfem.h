@@ -103,7 +103,10 @@ int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const doub
 
 /* ---- (a1) SGFEVector storage --------------------------------------------------------------------
  * Device-resident n x N fp64 blocks addressed by slot id (src/sgfevector.jl:18-27, entries 86-106).
- * Slots 0..nslots-1 are user slots; the PCG driver allocates its own work vectors. */
+ * Slots 0..nslots-1 are user slots; the PCG driver allocates its own work vectors.  asgfem_vec_alloc sets the slot COUNT:
+ * slots with index >= nslots are freed, new ones are zero-filled.  The host-vector entry points (asgfem_apply_host,
+ * asgfem_precond_apply_host, asgfem_solve_*_host) use slots 0 and 1 as staging and grow the table if needed: keep device
+ * vectors that must survive such a call in slots >= 2. */
 int asgfem_vec_alloc(asgfem_ctx* ctx, int32_t nslots);
 int asgfem_vec_upload(asgfem_ctx* ctx, int32_t slot, const double* host);   /* host: n*N, reference layout */
 int asgfem_vec_download(asgfem_ctx* ctx, int32_t slot, double* host);
@@ -200,7 +203,8 @@ int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const double* b0, dou
  * (set_multiindices).  mi_ext: M_ext x N_ext column-major extended set (active modes first,
  * asgfem_add_boundary_modes).  Cell rule (xref 2 x nq, w) and face rule (sf nqf points on [0,1], wf) are
  * the caller's QuadratureRule tables of order 2(order-1)+bonus_quadorder (:286-287); f_at_qp is the rhs at the
- * cell quadrature points (nq x ncells column-major; NULL = f == 1).  Outputs: eta4cell ncells x N_ext
+ * cell quadrature points (nq x ncells column-major).  NULL means f == 1 - a convenience of THIS interface; the
+ * reference calls rhs(ftemp, x) unconditionally (:322), so the Python / Julia wrappers refuse a missing rhs.  Outputs: eta4cell ncells x N_ext
  * column-major, eta4modes N_ext (the Julia return values of :417). */
 int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,
                                    const int64_t* mi_ext, int32_t nq, const double* xref, const double* w,

@@ -232,6 +232,7 @@ function estimate(::Type{PoissonProblemPrimal}, sol::SGFEVector, C::StochasticCo
     xref = Matrix{Float64}(reduce(hcat, qf.xref))
     sf = Float64[x[1] for x in qf1.xref]
     # rhs at the quadrature points (the closure cannot cross the C ABI): f_at_qp[q, cell]
+    rhs === nothing && error("estimate: rhs is required (the reference calls rhs(ftemp, x) unconditionally, estimate.jl:322)")
     f_at_qp = ones(Float64, length(qf.w), ncells)
     if rhs !== nothing
         x = zeros(Float64, 2); tmp = zeros(Float64, 1)

@@ -642,3 +642,39 @@ def test_evaluate_samples_matches_oracle(family):
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
     ctx.close()
+
+
+def test_new_space_on_a_context_drops_the_derived_pattern():
+    """a second asgfem_set_mesh / asgfem_set_space on a context must not assemble on the pattern derived
+    from the first space (same ndofs, other connectivity)."""
+    g1 = A.structured_unitsquare(9)
+    perm = np.random.default_rng(3).permutation(g1.nnodes)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    coords2 = np.empty_like(g1.coords)
+    coords2[inv] = g1.coords
+    g2 = A.Grid(coords2, inv[g1.cellnodes], inv[g1.bfacenodes])
+    Cf = A.StochasticCoefficientCosinus(tau=0.9, decay=2.0, mean=1.0, maxm=3)
+    xref, w = A.quadrature_rule(2)
+
+    def assemble(ctx, g):
+        fes = A.FESpace(g, 1)
+        ctx.set_mesh(g.coords, g.cellnodes + 1)
+        ctx.set_space(1, fes.ndofs, fes.celldofs + 1)
+        ctx.set_coefficient_cosinus(Cf.mean_value, Cf.decay_factors, Cf.b1, Cf.b2)
+        ctx.assemble_stiffness(3, xref, w)
+        cp, rv = ctx.pattern_csc()
+        return cp.copy(), rv.copy(), [ctx.get_stiffness(m).copy() for m in range(4)]
+
+    ctx = A.Context()
+    ctx.set_multiindices(A.LEGENDRE, np.array([[0, 0, 0], [1, 0, 0]], dtype=np.int64))
+    assemble(ctx, g1)
+    cp2, rv2, v2 = assemble(ctx, g2)   # reuse of the context
+    fresh = A.Context()
+    fresh.set_multiindices(A.LEGENDRE, np.array([[0, 0, 0], [1, 0, 0]], dtype=np.int64))
+    cpf, rvf, vf = assemble(fresh, g2)
+    assert np.array_equal(cp2, cpf) and np.array_equal(rv2, rvf)
+    for a, b in zip(v2, vf):
+        assert np.array_equal(a, b)
+    ctx.close()
+    fresh.close()
