@@ -72,6 +72,8 @@ PROTOTYPES = {
     "asgfem_set_owned_rows": (c_i32, [vp, c_i64]),
     "asgfem_set_owned_cells": (c_i32, [vp, c_i64, vp]),
     "asgfem_set_samples": (c_i32, [vp, c_i64, c_i64, vp]),
+    "asgfem_assemble_logprimal": (c_i32, [vp, c_i32, c_i32, vp, vp]),
+    "asgfem_assemble_logprimal_rhs": (c_i32, [vp, c_i32, vp, vp, vp, c_i32, c_i32]),
     "asgfem_solve_samples_host": (c_i32, [vp, vp, vp, c_f64, c_f64, c_i64, vp]),
     "asgfem_halo_exchange": (c_i32, [vp, c_i32]),
     "asgfem_vec_device_ptr": (c_i32, [vp, c_i32, P(vp), P(c_i64)]),

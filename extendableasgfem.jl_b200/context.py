@@ -277,6 +277,14 @@ class Context:
         self._ck(self.lib.asgfem_pcg(self.h, _ptr(b0), slot_x, atol, rtol, itmax, C.byref(st)))
         return {k: getattr(st, k) for k, _ in st._fields_ if k != "_pad"}
 
+    def assemble_logprimal(self, M, xref, w):
+        xref, w = _f64(xref), _f64(w)
+        self._ck(self.lib.asgfem_assemble_logprimal(self.h, M, len(w), _ptr(xref), _ptr(w)))
+
+    def assemble_logprimal_rhs(self, xref, w, f_at_qp, ntrunc, slot_b):
+        xref, w, fq = _f64(xref), _f64(w), _f64(f_at_qp)
+        self._ck(self.lib.asgfem_assemble_logprimal_rhs(self.h, len(w), _ptr(xref), _ptr(w), _ptr(fq), int(ntrunc), slot_b))
+
     def set_samples(self, samples):
         """samples: (Msamples, nsamples) - the columns of the device vectors become the samples (asgfem_set_samples)."""
         S = np.asfortranarray(np.asarray(samples, dtype=np.float64))

@@ -530,6 +530,21 @@ extern "C" int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq,
     return assemble_stiffness(ctx, M, nq, xref, w);
 }
 
+// Log-transformed primal problem (logpoisson_primal.jl:95-105): plane 0 = the Laplacian A (= A + N0, N0 is empty in the
+// reference), planes 1..M = the convection matrices N_m, on the pattern derived from celldofs (or the caller's)
+extern "C" int asgfem_assemble_logprimal(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w) {
+    CTX_OR_FAIL(ctx);
+    ASG_CHECK(ctx, ctx->order > 0, ASGFEM_ESTATE, "set_mesh / set_space first");
+    ASG_CHECK(ctx, M >= 0 && M <= ctx->maxm, ASGFEM_EINVAL, "assemble_logprimal: M exceeds maxm of the coefficient");
+    ASG_CHECK(ctx, nq >= 1 && nq <= 64 && xref && w, ASGFEM_EINVAL, "assemble_logprimal: bad quadrature rule");
+    // the stiffness entry point builds the pattern and sizes the value planes; its values are overwritten below
+    int rc = asgfem_assemble_stiffness(ctx, 0, nq, xref, w);
+    if (rc) return rc;
+    if ((rc = asgfem_set_num_stiffness(ctx, M))) return rc;
+    ctx->h_precond_vals.clear();  // the preconditioner is factorised from plane 0 = A
+    return assemble_stiffness(ctx, M, nq, xref, w, 1);
+}
+
 // ---- vectors ------------------------------------------------------------------------------------
 static int check_slot(asgfem_ctx* ctx, int32_t slot) {
     ASG_CHECK(ctx, slot >= 0 && slot < (int32_t)ctx->slots.size() && ctx->slots[slot], ASGFEM_EINVAL,
@@ -851,6 +866,20 @@ extern "C" int asgfem_set_precond_matrix_csc(asgfem_ctx* ctx, const int64_t* col
     }
     ctx->h_precond_vals.swap(csr);
     return 0;
+}
+
+// load vectors b[mu] = (lambda_mu f, phi_i) of the log-transformed primal problem into a device slot (logpoisson_primal.jl:108-127)
+extern "C" int asgfem_assemble_logprimal_rhs(asgfem_ctx* ctx, int32_t nq, const double* xref, const double* w, const double* f_at_qp,
+                                             int32_t ntrunc, int32_t slot_b) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, slot_b)) return ASGFEM_EINVAL;
+    ASG_CHECK(ctx, ctx->order > 0 && ctx->ncells > 0 && ctx->ndofs_space == ctx->n, ASGFEM_ESTATE, "assemble_logprimal_rhs: set_mesh / set_space first");
+    ASG_CHECK(ctx, ctx->mis.N == ctx->N && ctx->N > 0 && !ctx->sample_mode, ASGFEM_ESTATE, "assemble_logprimal_rhs: multi-indices not set");
+    ASG_CHECK(ctx, nq >= 1 && nq <= 64 && xref && w && f_at_qp, ASGFEM_EINVAL, "assemble_logprimal_rhs: bad quadrature rule / rhs values");
+    ASG_CHECK(ctx, ntrunc >= 0 && ntrunc <= ctx->maxm && ctx->mis.M <= ctx->maxm, ASGFEM_EINVAL,
+              "assemble_logprimal_rhs: N_truncate / multi-index length exceed maxm of the coefficient");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    return assemble_logprimal_rhs(ctx, nq, xref, w, f_at_qp, ntrunc, ctx->slots[slot_b]);
 }
 
 extern "C" int asgfem_bicgstab(asgfem_ctx* ctx, int32_t slot_b, int32_t slot_x, double atol, double rtol, int64_t itmax,

@@ -240,7 +240,9 @@ int pcg_solve(asgfem_ctx* ctx, const double* b0_host, double* x, double atol, do
               asgfem_stats* stats);
 int bicgstab_solve(asgfem_ctx* ctx, double* b, double* x, double atol, double rtol, int64_t itmax, asgfem_stats* stats);
 // assemble.cu
-int assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w);
+int assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w, int kind = 0);  // kind 1: A, N_1..N_M
+int assemble_logprimal_rhs(asgfem_ctx* ctx, int32_t nq, const double* xref, const double* w, const double* f_at_qp, int32_t ntrunc,
+                           double* dvec);
 // estimate.cu
 int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
                             int32_t nq, const double* xref, const double* w, const double* f_at_qp, int32_t nqf,

@@ -117,6 +117,37 @@ def solve_logpoisson_primal(sol: SGFEVector, A, N0, Nm, b0, G=None, nmodes=None,
     return (bdofs, stats) if return_stats else bdofs
 
 
+def solve_logpoisson(sol: SGFEVector, C, rhs, bonus_quadorder_a=2, bonus_quadorder_f=0, atol=1.0e-14, rtol=1.0e-14, itmax=0,
+                     return_stats=False):
+    """solve!(LogTransformedPoissonProblemPrimal, sol, C; rhs, ...) (src/modelproblems/logpoisson_primal.jl:75-142) with the
+    Laplacian A, the convection matrices N_m and the load vectors b[mu] = (lambda_mu f, v) assembled on the device, and the
+    system of solve_logpoisson_primal! solved by the device BiCGStab with the preconditioner I (x) chol(A).  The warm start
+    semantics of the reference (b = deepcopy(sol) + b0, :149-152) are kept.  Overwrites sol.entries, returns bdofs."""
+    if rhs is None:
+        raise ValueError("need right-hand side")  # logpoisson_primal.jl:129
+    ctx, FES = sol.TB.ctx, sol.FES_space
+    g = FES.grid
+    ctx.set_mesh(g.coords, g.cellnodes + 1)
+    ctx.set_space(FES.order, FES.ndofs, FES.celldofs + 1)
+    ctx.set_coefficient_cosinus(C.mean_value, C.decay_factors, C.b1, C.b2)
+    xref, w = _grids.quadrature_rule(2 * FES.order - 1 + bonus_quadorder_a)
+    ctx.assemble_logprimal(sol.TB.maxlength_multiindices(), xref, w)
+    bdofs = FES.bdofs + 1
+    ctx.set_bdofs(bdofs)
+    xf, wf = _grids.quadrature_rule(FES.order + bonus_quadorder_f)
+    c = g.cellnodes
+    x1, x2, x3 = g.coords[c[:, 0]], g.coords[c[:, 1]], g.coords[c[:, 2]]
+    xq = x1[:, None, :] + xf[None, :, 0:1] * (x2 - x1)[:, None, :] + xf[None, :, 1:2] * (x3 - x1)[:, None, :]
+    fq = rhs(xq[:, :, 0], xq[:, :, 1])  # (ncells, nq) C-order == nq x ncells column-major
+    ctx.vec_ensure(2)
+    ctx.vec_upload(0, sol.entries)
+    ctx.assemble_logprimal_rhs(xf, wf, fq, len(C.decay_factors), 1)
+    ctx.vec_axpy(1.0, 0, 1)  # b = deepcopy(sol) + b0   (:149-152)
+    stats = ctx.bicgstab(1, 0, atol, rtol, itmax)
+    sol.entries[:] = ctx.vec_download(0)
+    return (bdofs, stats) if return_stats else bdofs
+
+
 def set_samples(sol: SGFEVector, vals):
     """Batched set_sample!(SGFEV, S) (src/sgfevector.jl:43-69): vals[s, m, :] = TB.vals[m] after set_sample!(TB, xi_s)
     (tensorizedbasis.jl:226-236, the caller's polynomial tables).  Returns the (nsamples, n) array of evaluated spatial

@@ -101,6 +101,19 @@ int asgfem_set_coefficient_cosinus(asgfem_ctx* ctx, int64_t maxm, double mean, c
  * Builds the shared pattern from celldofs if none was set. */
 int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w);
 
+/* ---- (f1) assembly of the log-transformed primal problem (src/modelproblems/logpoisson_primal.jl:95-128) -------------------
+ * asgfem_assemble_logprimal: matrix 0 = the Laplacian A = (grad u, grad v) (the reference's N0 is an empty matrix), matrices
+ * 1..M = N_m = -(grad a_m . grad u, v) with grad a_m from get_gradam! (cosinus.jl:67-76); one quadrature rule for all of
+ * them (order 2*order - 1 + bonus_quadorder_a).  The operator, the preconditioner (factorised from matrix 0) and
+ * asgfem_bicgstab then solve the system of solve_logpoisson_primal!.
+ * asgfem_assemble_logprimal_rhs: the load vectors b[mu] = (lambda_mu f, phi_i) of ALL modes into a device slot, lambda_mu =
+ * the PCE coefficient of exp(-a) from expa_PCE_mop (src/coefficients/coefficients.jl:236-262, factor = -1, N_truncate =
+ * ntrunc, normally maxm); f_at_qp = rhs at the quadrature points (nq x ncells column-major), rule of order
+ * order + bonus_quadorder_f. */
+int asgfem_assemble_logprimal(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w);
+int asgfem_assemble_logprimal_rhs(asgfem_ctx* ctx, int32_t nq, const double* xref, const double* w, const double* f_at_qp,
+                                  int32_t ntrunc, int32_t slot_b);
+
 /* ---- (a1) SGFEVector storage --------------------------------------------------------------------
  * Device-resident n x N fp64 blocks addressed by slot id (src/sgfevector.jl:18-27, entries 86-106).
  * Slots 0..nslots-1 are user slots; the PCG driver allocates its own work vectors.  asgfem_vec_alloc sets the slot COUNT:

@@ -255,6 +255,21 @@ function estimate(::Type{PoissonProblemPrimal}, sol::SGFEVector, C::StochasticCo
 end
 
 """
+    assemble_logprimal!(ctx, M, qf) / assemble_logprimal_rhs!(ctx, qf, f_at_qp, ntrunc, slot)
+
+Device assembly of the log-transformed primal problem (src/modelproblems/logpoisson_primal.jl:95-128): matrix 0 = the
+Laplacian A, matrices 1..M = N_m = -(grad a_m . grad u, v), and the load vectors b[mu] = (lambda_mu f, v) of all modes into a
+device vector slot; mesh, space and the cosinus tables must be set (as for `estimate`).  `solve_logpoisson_primal!` then
+needs no matrices from the host: `asgfem_bicgstab(ctx, slot_b, slot_x, ...)`.
+"""
+assemble_logprimal!(ctx::Context, M::Integer, xref::Matrix{Float64}, w::Vector{Float64}) =
+    check(ctx, ccall((:asgfem_assemble_logprimal, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+        ctx.h, M, length(w), xref, w))
+assemble_logprimal_rhs!(ctx::Context, xref::Matrix{Float64}, w::Vector{Float64}, f_at_qp::Matrix{Float64}, ntrunc::Integer, slot::Integer) =
+    check(ctx, ccall((:asgfem_assemble_logprimal_rhs, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint), ctx.h, length(w), xref, w, f_at_qp, ntrunc, slot))
+
+"""
     deterministic_sample_solutions(ctx, Samples, b) -> Matrix (ndofs x nsamples)
 
 The deterministic reference solutions of `calculate_sampling_error` (src/sampling_error.jl:112-128) for the affine

@@ -191,3 +191,71 @@ def assemble_rhs(space: FESpace, f=None, bonus_quadorder: int = 0):
 
 def csr(indptr, indices, vals, n):
     return sp.csr_matrix((vals, indices, indptr), shape=(n, n))
+
+
+# ---- log-transformed primal problem (src/modelproblems/logpoisson_primal.jl:95-128) ---------------------------------------
+def assemble_logprimal_matrices(space: FESpace, coeff, M: int, bonus_quadorder: int = 2):
+    """Returns (indptr, indices, vals) with vals of shape (M+1, nnz) on the pattern of assemble_stiffness:
+    vals[0] = A[i,j] = int grad phi_j . grad phi_i                      (:96-97, BilinearOperator([grad(1)]))
+    vals[m] = N_m[i,j] = - int (grad a_m . grad phi_j) phi_i            (:100-105, kernel get_gradam_x_sigma,
+                                                                         src/coefficients/coefficients.jl:169-176; factor -1)
+    One quadrature rule of order (order - 1) + order + bonus for all planes (exact for A)."""
+    mesh = space.mesh
+    xref, w = quadrature_rule(2 * space.order - 1 + bonus_quadorder)
+    indptr, indices, pos = pattern(space)
+    nnz = len(indices)
+    g = space.lambda_gradients()
+    phi, dphi = space.basis(xref)  # (nq, nd), (nq, nd, 3)
+    gradphi = np.einsum("qdl,clx->cqdx", dphi, g)  # (nc, nq, nd, 2)
+    xq = space.physical_points(xref)
+    vol = mesh.cellvolumes
+    vals = np.zeros((M + 1, nnz))
+    loc = np.einsum("c,q,cqix,cqjx->cij", vol, w, gradphi, gradphi)
+    np.add.at(vals[0], pos.reshape(-1), loc.reshape(-1))
+    for m in range(1, M + 1):
+        gx, gy = coeff.gradam(m, xq[:, :, 0], xq[:, :, 1])  # (nc, nq)
+        conv = gx[:, :, None] * gradphi[:, :, :, 0] + gy[:, :, None] * gradphi[:, :, :, 1]  # grad a_m . grad phi_j: (nc, nq, nd)
+        loc = -np.einsum("c,q,qi,cqj->cij", vol, w, phi, conv)
+        np.add.at(vals[m], pos.reshape(-1), loc.reshape(-1))
+    return indptr, indices, vals
+
+
+def lambda_mu(coeff, multi_indices, x, y, factor=-1.0, n_truncate=None):
+    """lambda_mu of expa_PCE_mop (src/coefficients/coefficients.jl:236-262) for e^{a * factor} at points (x, y):
+    exp(1/2 sum_{m <= N_truncate} a_m^2) * exp(mean * factor) * prod_d a_d^{mu_d} / (sqrt(prod_d mu_d!) * factor^{|mu|}).
+    Returns an array of shape (nmodes,) + x.shape."""
+    from math import factorial
+    n_truncate = coeff.maxm if n_truncate is None else n_truncate
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    s = np.zeros(np.broadcast(x, y).shape)
+    for m in range(1, n_truncate + 1):
+        s = s + coeff.am(m, x, y) ** 2
+    pref = np.exp(s / 2) * np.exp(coeff.mean_value * factor)
+    M = len(multi_indices[0])
+    am = [coeff.am(d, x, y) for d in range(1, M + 1)]
+    out = np.empty((len(multi_indices),) + pref.shape)
+    for k, mu in enumerate(multi_indices):
+        val = np.ones_like(pref)
+        fac = 1.0
+        for d in range(M):
+            val = val * am[d] ** mu[d]
+            fac *= factorial(mu[d])
+        out[k] = val / (np.sqrt(fac) * factor ** sum(mu)) * pref
+    return out
+
+
+def assemble_logprimal_rhs(space: FESpace, coeff, multi_indices, f, bonus_quadorder: int = 0):
+    """b[mu] = (lambda_mu f, phi_i) for every mode (logpoisson_primal.jl:108-127, LinearOperator(kernel_fexp, [id(1)];
+    bonus_quadorder = bonus_quadorder_f)).  Returns (nmodes, ndofs)."""
+    mesh = space.mesh
+    xref, w = quadrature_rule(space.order + bonus_quadorder)
+    phi, _ = space.basis(xref)
+    xq = space.physical_points(xref)
+    lam = lambda_mu(coeff, multi_indices, xq[:, :, 0], xq[:, :, 1])  # (nmodes, nc, nq)
+    fv = f(xq[:, :, 0], xq[:, :, 1])
+    loc = np.einsum("c,q,cq,kcq,qi->kci", mesh.cellvolumes, w, fv, lam, phi)
+    b = np.zeros((len(multi_indices), space.ndofs))
+    for k in range(len(multi_indices)):
+        np.add.at(b[k], space.celldofs.reshape(-1), loc[k].reshape(-1))
+    return b

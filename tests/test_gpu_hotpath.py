@@ -678,3 +678,55 @@ def test_new_space_on_a_context_drops_the_derived_pattern():
         assert np.array_equal(a, b)
     ctx.close()
     fresh.close()
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_logprimal_device_assembly_and_solve_match_oracle(order):
+    """Row f1 completed: the Laplacian, the convection matrices N_m = -(grad a_m . grad u, v) and the load vectors
+    b[mu] = (lambda_mu f, v) (logpoisson_primal.jl:95-128, expa_PCE_mop) assembled on the device against the oracle's
+    restatement (1e-12), then the full solve against the oracle's solve_logpoisson_primal (GMRES) on the oracle's matrices."""
+    m = omesh.uniform_refine(omesh.grid_unitsquare(), 3)
+    Cc = ocoef.StochasticCoefficientCosinus(tau=0.5, decay=2.0, mean=0.0, maxm=10)
+    modes = [[0, 0, 0], [1, 0, 0], [0, 1, 0], [2, 0, 0], [0, 0, 1], [1, 1, 0], [0, 2, 1]]
+    f = lambda x, y: 1.0 + x * y  # noqa: E731
+    space = ofem.FESpace(m, order)
+    ip, idx, vals = ofem.assemble_logprimal_matrices(space, Cc, 3, bonus_quadorder=2)
+    bref = ofem.assemble_logprimal_rhs(space, Cc, modes, f, bonus_quadorder=1)
+    g = A.Grid(m.coords, m.cellnodes, m.bfacenodes)
+    fes = A.FESpace(g, order)
+    TB = A.TensorizedBasis(A.HermitePolynomials, modes)
+    sol = A.SGFEVector(fes, TB)
+    ctx = TB.ctx
+    Cd = A.StochasticCoefficientCosinus(tau=0.5, decay=2.0, mean=0.0, maxm=10)
+    ctx.set_mesh(g.coords, g.cellnodes + 1)
+    ctx.set_space(order, fes.ndofs, fes.celldofs + 1)
+    ctx.set_coefficient_cosinus(Cd.mean_value, Cd.decay_factors, Cd.b1, Cd.b2)
+    xref, w = A.quadrature_rule(2 * order - 1 + 2)
+    ctx.assemble_logprimal(3, xref, w)
+    cp, rv = ctx.pattern_csc()
+    n = fes.ndofs
+    for k in range(4):
+        got = sp.csc_matrix((ctx.get_stiffness(k), rv - 1, cp - 1), shape=(n, n))
+        ref = ofem.csr(ip, idx, vals[k], n)
+        assert abs(got - ref).max() <= 1e-12 * abs(ref).max(), k
+    # load vectors
+    xf, wf = A.quadrature_rule(order + 1)
+    c = g.cellnodes
+    x1, x2, x3 = g.coords[c[:, 0]], g.coords[c[:, 1]], g.coords[c[:, 2]]
+    xq = x1[:, None, :] + xf[None, :, 0:1] * (x2 - x1)[:, None, :] + xf[None, :, 1:2] * (x3 - x1)[:, None, :]
+    ctx.vec_alloc(2)
+    ctx.assemble_logprimal_rhs(xf, wf, f(xq[:, :, 0], xq[:, :, 1]), 10, 1)
+    bgot = ctx.vec_download(1).reshape(len(modes), n)
+    assert np.abs(bgot - bref).max() <= 1e-12 * np.abs(bref).max()
+    # full solve through the mirror of solve!(LogTransformedPoissonProblemPrimal, ...)
+    sol.entries[:] = 0.0
+    bd, st = A.solve_logpoisson(sol, Cd, f, bonus_quadorder_a=2, bonus_quadorder_f=1, return_stats=True)
+    assert st["solved"]
+    Aor = ofem.csr(ip, idx, vals[0], n)
+    Nm = [ofem.csr(ip, idx, vals[k], n) for k in range(1, 4)]
+    G = otb.coupling_matrix(opoly.HERMITE, modes)
+    ref_sol = np.zeros(n * len(modes))
+    osolver.solve_logpoisson_primal(ref_sol, Aor, 0 * Aor, Nm, list(bref), G, len(modes), space.bdofs)
+    assert np.abs(sol.entries - ref_sol).max() <= 1e-10 * np.abs(ref_sol).max()
+    assert np.array_equal(np.sort(np.asarray(bd) - 1), np.sort(space.bdofs))
+    ctx.close()
