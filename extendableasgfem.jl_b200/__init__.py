@@ -10,7 +10,7 @@ from .multiindices import (generate_multiindices, prepare_multi_indices, add_bou
                            classify_modes, graded_lex_multiindices)
 from .grids import (Grid, FESpace, grid_unitsquare, grid_lshape, uniform_refine, structured_unitsquare,  # noqa: F401
                     quadrature_rule, quadrature_rule_1d)
-from .sgfem import (TensorizedBasis, SGFEVector, solve_primal, solve, solve_logpoisson_primal, solve_logpoisson, set_samples,  # noqa: F401
+from .sgfem import (TensorizedBasis, SGFEVector, solve_primal, solve, solve_logpoisson_primal, solve_logpoisson, estimate_logpoisson, set_samples,  # noqa: F401
                     setup_device_problem, mul, ldiv,
                     estimate, LegendrePolynomials, HermitePolynomials)
 

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "asgfem_bicgstab": (c_i32, [vp, c_i32, c_i32, c_f64, c_f64, c_i64, P(Stats)]),
     "asgfem_solve_logprimal_host": (c_i32, [vp, vp, vp, c_f64, c_f64, c_i64, P(Stats)]),
     "asgfem_estimate_poisson_primal": (c_i32, [vp, c_i32, c_i64, c_i64, vp, c_i32, vp, vp, vp, c_i32, vp, vp, vp, vp]),
+    "asgfem_estimate_logpoisson_primal": (c_i32, [vp, c_i32, c_i64, c_i64, vp, c_i32, vp, vp, vp, vp, c_i32, c_i32, vp, vp, vp, vp, vp]),
     "asgfem_estimate_poisson_primal_marking": (c_i32, [vp, c_i32, c_i64, c_i64, vp, c_i32, vp, vp, vp, c_i32, vp, vp, c_i64, vp, vp, vp]),
     "asgfem_set_owned_rows": (c_i32, [vp, c_i64]),
     "asgfem_set_owned_cells": (c_i32, [vp, c_i64, vp]),

@@ -352,6 +352,19 @@ class Context:
             _ptr(wf), _ptr(eta4cell), _ptr(eta4modes)))
         return eta4modes, eta4cell.T  # view as ncells x N_ext
 
+    def estimate_logpoisson_primal(self, slot_u, mi_ext, xref, w, sf, wf, ncells, f_at_qp, ntrunc, lam_at_qp=None):
+        mi = _i64(np.asarray(mi_ext))
+        N_ext, M_ext = mi.shape
+        xref, w, sf, wf, fq = _f64(xref), _f64(w), _f64(sf), _f64(wf), _f64(f_at_qp)
+        lam = None if lam_at_qp is None else _f64(lam_at_qp)
+        eta4cell = np.zeros((N_ext, ncells))
+        eta4modes = np.zeros(N_ext)
+        zeta = np.zeros(3)
+        self._ck(self.lib.asgfem_estimate_logpoisson_primal(
+            self.h, slot_u, N_ext, M_ext, _ptr(mi), len(w), _ptr(xref), _ptr(w), _ptr(fq), _ptr(lam) if lam is not None else None,
+            int(ntrunc), len(wf), _ptr(sf), _ptr(wf), _ptr(eta4cell), _ptr(eta4modes), _ptr(zeta)))
+        return eta4modes, eta4cell.T, zeta
+
     def estimate_poisson_primal_marking(self, slot_u, mi_ext, xref, w, sf, wf, ncells, sel_cols_1based, f_at_qp=None):
         """eta4modes and the per-cell sum of eta4cell over the selected columns (no ncells x N_ext transfer)."""
         mi = _i64(np.asarray(mi_ext))

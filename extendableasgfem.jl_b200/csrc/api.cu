@@ -972,6 +972,25 @@ extern "C" int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, i
                                    eta4cell, eta4modes);
 }
 
+// estimate(::Type{LogTransformedPoissonProblemPrimal}, ...) (src/estimate.jl:70-257)
+extern "C" int asgfem_estimate_logpoisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
+                                                 int32_t nq, const double* xref, const double* w, const double* f_at_qp,
+                                                 const double* lam_at_qp, int32_t ntrunc, int32_t nqf, const double* sf,
+                                                 const double* wf, double* eta4cell, double* eta4modes, double* zeta3) {
+    CTX_OR_FAIL(ctx);
+    if (check_slot(ctx, slot_u)) return ASGFEM_EINVAL;
+    ASG_CHECK(ctx, ctx->order > 0 && ctx->ncells > 0, ASGFEM_ESTATE, "estimate: set_mesh / set_space first");
+    ASG_CHECK(ctx, ctx->ndofs_space == ctx->n, ASGFEM_ESTATE, "estimate: space and pattern sizes differ");
+    ASG_CHECK(ctx, N_ext >= ctx->N && M_ext >= ctx->mis.M && mi_ext, ASGFEM_EINVAL, "estimate: bad extended multi-index set");
+    ASG_CHECK(ctx, M_ext <= ctx->maxm && ntrunc >= 0 && ntrunc <= ctx->maxm, ASGFEM_EINVAL,
+              "estimate: extended multi-indices / N_truncate exceed maxm of the coefficient");
+    ASG_CHECK(ctx, nq >= 1 && nq <= 64 && xref && w && nqf >= 1 && nqf <= 16 && sf && wf && eta4cell && eta4modes && f_at_qp,
+              ASGFEM_EINVAL, "estimate: bad quadrature / output arguments (the rhs values are required)");
+    if (set_device(ctx)) return ASGFEM_ECUDA;
+    return estimate_poisson_primal(ctx, ctx->slots[slot_u], N_ext, M_ext, mi_ext, nq, xref, w, f_at_qp, nqf, sf, wf, eta4cell,
+                                   eta4modes, -1, nullptr, nullptr, 1, lam_at_qp, ntrunc, zeta3);
+}
+
 // The outputs the adaptive loop consumes (scripts/poisson.jl:341-420): eta4modes and, for the spatial marking, the sum of
 // eta4cell over a set of columns (the active modes) - without the D2H of the ncells x N_ext matrix
 extern "C" int asgfem_estimate_poisson_primal_marking(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,

@@ -247,6 +247,7 @@ int assemble_logprimal_rhs(asgfem_ctx* ctx, int32_t nq, const double* xref, cons
 int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
                             int32_t nq, const double* xref, const double* w, const double* f_at_qp, int32_t nqf,
                             const double* sf, const double* wf, double* eta4cell, double* eta4modes, int64_t nsel = -1,
-                            const int64_t* sel = nullptr, double* cellsum = nullptr);
+                            const int64_t* sel = nullptr, double* cellsum = nullptr, int kind = 0, const double* lam_at_qp = nullptr,
+                            int32_t ntrunc = 0, double* zeta3 = nullptr);
 
 }  // namespace asgfem

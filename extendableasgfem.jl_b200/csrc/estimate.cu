@@ -221,6 +221,190 @@ __global__ void __launch_bounds__(256) k_est_jumps(EstArgs a) {
     }
 }
 
+// ---- log-transformed primal problem (estimate(::Type{LogTransformedPoissonProblemPrimal}, ...), src/estimate.jl:70-257) ----
+//   volume part (:134-217)  eta4cell[T,j] = |T|^{2 or 1} sum_q w_q ( lambda_j(x_q) f(x_q) + [j<=N, order>1] Lap u_j
+//                                            + sum_m grad a_m(x_q) . grad w_{j,m}(x_q) )^2,  w_{j,m} = g+ u_{j+e_m} + g- u_{j-e_m}
+//   data part   (:156-175)  zeta1 = sum_T |T| sum_q w_q f^2 exp(2 sum_{m<=maxm} a_m^2),  zeta2 = sum_T |T| sum_q w_q f^2 sum_j lambda_j^2
+//   jump part   (:232-244)  J[F,j] = |F| int_F |[[grad u_j]]|^2 for the active modes, interior faces
+// lambda_j = PCE coefficient of exp(-a) (expa_PCE_mop, factor -1).  The reference interpolates lambda_j into H1Pk{quadorder} and
+// evaluates the interpolant at the quadrature points (the direct evaluation is the commented-out "most expensive line" :184);
+// here lam_qp (the caller's interpolated values, [cell][q][j]) is used when given, else lambda_j is evaluated directly.
+struct EstLogArgs {
+    const int32_t* mi;   // N_ext x M_ext
+    const double* den;   // sqrt(prod mu_d!) * (-1)^|mu|
+    const double* lam_qp;
+    int ntrunc;
+    double* zeta1;  // [ncells]
+    double* Z2;     // ncells x ldE: |T| sum_q w_q f^2 lambda_j^2
+};
+
+__global__ void __launch_bounds__(256) k_estlog_volume(EstArgs a, EstLogArgs L) {
+    extern __shared__ double sm[];
+    double* gu = sm;                       // [N][2]: grad u_k at the current quadrature point
+    double* lap = gu + 2 * (size_t)a.N;    // [N]
+    double* am = lap + a.N;                // [max(ntrunc, M_ext) + 1]
+    const int nam = max(L.ntrunc, a.M_ext);
+    double* gam = am + nam + 1;            // [M_ext + 1][2]
+    __shared__ double s_gl[3][2], s_lapphi[6], s_vol, s_pref, s_S;
+    for (int64_t cell = blockIdx.x; cell < a.ncells; cell += gridDim.x) {
+        __syncthreads();
+        const int32_t* cn = a.cellnodes + 3 * cell;
+        const int32_t* cd = a.celldofs + (int64_t)a.nd * cell;
+        const double x1 = a.coords[2 * cn[0]], y1 = a.coords[2 * cn[0] + 1], x2 = a.coords[2 * cn[1]], y2 = a.coords[2 * cn[1] + 1],
+                     x3 = a.coords[2 * cn[2]], y3 = a.coords[2 * cn[2] + 1];
+        if (threadIdx.x == 0) {
+            double gl[3][2];
+            const double det = lambda_gradients(a.coords, cn, gl);
+            s_vol = 0.5 * fabs(det);
+            for (int i = 0; i < 3; ++i) s_gl[i][0] = gl[i][0], s_gl[i][1] = gl[i][1];
+            for (int d = 0; d < 6; ++d) s_lapphi[d] = 0.0;
+            if (a.order == 2) {
+                for (int i = 0; i < 3; ++i) s_lapphi[i] = 4.0 * (gl[i][0] * gl[i][0] + gl[i][1] * gl[i][1]);
+                for (int f = 0; f < 3; ++f) {
+                    const int i = f, j = (f + 1) % 3;
+                    s_lapphi[3 + f] = 8.0 * (gl[i][0] * gl[j][0] + gl[i][1] * gl[j][1]);
+                }
+            }
+        }
+        __syncthreads();
+        if (a.order > 1)
+            for (int k = threadIdx.x; k < a.N; k += blockDim.x) {
+                double s = 0.0;
+                for (int d = 0; d < a.nd; ++d) s += a.u[(int64_t)cd[d] * a.ld + a.pos[k]] * s_lapphi[d];
+                lap[k] = s;
+            }
+        double acc[8], z2[8];  // extended modes of this thread: j = threadIdx.x + 256 r (N_ext <= 2048)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = z2[r] = 0.0;
+        double zeta1 = 0.0;
+        for (int q = 0; q < a.nq; ++q) {
+            const double xr = e_xref[2 * q], yr = e_xref[2 * q + 1];
+            const double px = x1 + xr * (x2 - x1) + yr * (x3 - x1), py = y1 + xr * (y2 - y1) + yr * (y3 - y1);
+            __syncthreads();  // tables of the previous point are no longer read
+            for (int m = threadIdx.x + 1; m <= nam; m += blockDim.x) am[m] = eval_am(m, px, py, a.mean, a.decay, a.b1, a.b2);
+            for (int m = threadIdx.x + 1; m <= a.M_ext; m += blockDim.x) eval_gradam(m, px, py, a.decay, a.b1, a.b2, gam[2 * m], gam[2 * m + 1]);
+            if (a.order > 1 || q == 0) {
+                const double lam[3] = {1.0 - xr - yr, xr, yr};
+                double gl[3][2];
+                for (int i = 0; i < 3; ++i) gl[i][0] = s_gl[i][0], gl[i][1] = s_gl[i][1];
+                for (int k = threadIdx.x; k < a.N; k += blockDim.x) {
+                    double gx = 0.0, gy = 0.0;
+                    for (int d = 0; d < a.nd; ++d) {
+                        double g2[2];
+                        grad_phi(a.order, d, lam, gl, g2);
+                        const double uv = a.u[(int64_t)cd[d] * a.ld + a.pos[k]];
+                        gx += uv * g2[0];
+                        gy += uv * g2[1];
+                    }
+                    gu[2 * k] = gx, gu[2 * k + 1] = gy;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double S = 0.0;
+                for (int m = 1; m <= L.ntrunc; ++m) S += am[m] * am[m];
+                s_S = S;
+                s_pref = exp(S / 2) * exp(-a.mean);
+            }
+            __syncthreads();
+            const double fval = a.fq[(int64_t)cell * a.nq + q], wq = e_w[q], pref = s_pref;
+            if (threadIdx.x == 0) zeta1 += fval * fval * exp(2.0 * s_S) * wq * s_vol;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int j = threadIdx.x + 256 * r;
+                if (j < a.N_ext) {
+                    double lamj;
+                    if (L.lam_qp) {
+                        lamj = L.lam_qp[((int64_t)cell * a.nq + q) * a.N_ext + j];
+                    } else {
+                        double amu = 1.0;
+                        for (int d = 0; d < a.M_ext; ++d) {
+                            const int e = L.mi[(int64_t)j * a.M_ext + d];
+                            for (int t = 0; t < e; ++t) amu *= am[d + 1];
+                        }
+                        lamj = amu / L.den[j] * pref;
+                    }
+                    double val = lamj * fval;
+                    if (a.order > 1 && j < a.N) val += lap[j];
+                    double sig = 0.0;
+                    for (int e = a.cptr[j]; e < a.cptr[j + 1]; ++e)
+                        sig += a.cg[e] * (gam[2 * a.cm[e]] * gu[2 * a.ck[e]] + gam[2 * a.cm[e] + 1] * gu[2 * a.ck[e] + 1]);
+                    acc[r] += (val + sig) * (val + sig) * wq;
+                    z2[r] += lamj * lamj * fval * fval * wq;
+                }
+            }
+        }
+        const double vol = s_vol;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int j = threadIdx.x + 256 * r;
+            if (j < a.N_ext) {
+                a.E[cell * a.ldE + j] = acc[r] * (j < a.N ? vol * vol : vol);
+                L.Z2[cell * a.ldE + j] = z2[r] * vol;
+            }
+        }
+        if (threadIdx.x == 0) L.zeta1[cell] = zeta1;
+    }
+}
+
+// J[F, k] = |F| int_F |[[grad u_k]]|^2 ds for the active modes on interior faces (jump(grad(1)) of ItemIntegratorDG, :234-241)
+__global__ void __launch_bounds__(256) k_estlog_jumps(EstArgs a) {
+    __shared__ double s_g[2][2][6][2];
+    __shared__ int32_t s_dof[2][6];
+    __shared__ double s_len;
+    const int npt = a.order == 1 ? 1 : 2;
+    for (int64_t face = blockIdx.x; face < a.nfaces; face += gridDim.x) {
+        const int32_t c0 = a.face_cells[2 * face], c1 = a.face_cells[2 * face + 1];
+        if (c1 < 0) {
+            for (int j = threadIdx.x; j < a.N_ext; j += blockDim.x) a.JF[face * a.ldE + j] = 0.0;
+            continue;
+        }
+        __syncthreads();
+        const int32_t na = a.face_nodes[2 * face], nb = a.face_nodes[2 * face + 1];
+        const double ax = a.coords[2 * na], ay = a.coords[2 * na + 1], bx = a.coords[2 * nb], by = a.coords[2 * nb + 1];
+        if (threadIdx.x < 2) {
+            const int side = threadIdx.x;
+            const int32_t cell = side == 0 ? c0 : c1;
+            const int32_t* cn = a.cellnodes + 3 * (int64_t)cell;
+            double gl[3][2];
+            lambda_gradients(a.coords, cn, gl);
+            for (int d = 0; d < a.nd; ++d) s_dof[side][d] = a.celldofs[(int64_t)a.nd * cell + d];
+            for (int pt = 0; pt < 2; ++pt) {
+                const int32_t node = pt == 0 ? na : nb;
+                double lam[3] = {cn[0] == node ? 1.0 : 0.0, cn[1] == node ? 1.0 : 0.0, cn[2] == node ? 1.0 : 0.0};
+                for (int d = 0; d < a.nd; ++d) grad_phi(a.order, d, lam, gl, s_g[side][pt][d]);
+            }
+            if (side == 0) s_len = sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
+        }
+        __syncthreads();
+        const double len = s_len;
+        for (int j = threadIdx.x; j < a.N_ext; j += blockDim.x) {
+            double val = 0.0;
+            if (j < a.N) {
+                const int kc = a.pos[j];
+                double J[2][2];
+                for (int pt = 0; pt < npt; ++pt) {
+                    double gx = 0.0, gy = 0.0;
+                    for (int d = 0; d < a.nd; ++d) {
+                        const double u0 = a.u[(int64_t)s_dof[0][d] * a.ld + kc], u1 = a.u[(int64_t)s_dof[1][d] * a.ld + kc];
+                        gx += u0 * s_g[0][pt][d][0] - u1 * s_g[1][pt][d][0];
+                        gy += u0 * s_g[0][pt][d][1] - u1 * s_g[1][pt][d][1];
+                    }
+                    J[pt][0] = gx, J[pt][1] = gy;
+                }
+                if (npt == 1) J[1][0] = J[0][0], J[1][1] = J[0][1];
+                for (int q = 0; q < a.nqf; ++q) {
+                    const double s = e_sf[q];
+                    const double gx = (1.0 - s) * J[0][0] + s * J[1][0], gy = (1.0 - s) * J[0][1] + s * J[1][1];
+                    val += e_wf[q] * (gx * gx + gy * gy);
+                }
+                val *= len * len;  // integral over the face (length) and jumps4face .*= FaceVolumes
+            }
+            a.JF[face * a.ldE + j] = val;
+        }
+    }
+}
+
 // partial column sums over row chunks: part[chunk][j] = sum_{r in chunk} A[r][j]   (fixed order)
 // wrow (may be null): weight of a row - the share of a cell / face this rank owns in a row-sharded run
 __global__ void k_colsum_partial(const double* __restrict__ A, int64_t nrows, int64_t ld, int ncols, int chunk,
@@ -301,7 +485,7 @@ struct DevBuf {
 int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
                             int32_t nq, const double* xref, const double* w, const double* f_at_qp, int32_t nqf,
                             const double* sf, const double* wf, double* eta4cell, double* eta4modes, int64_t nsel,
-                            const int64_t* sel, double* cellsum) {
+                            const int64_t* sel, double* cellsum, int kind, const double* lam_at_qp, int32_t ntrunc, double* zeta3) {
     const int64_t N = ctx->N, Mact = ctx->mis.M, ncells = ctx->ncells;
     // the active modes must be the first N extended modes (padded with zeros) - estimate.jl relies on this
     for (int64_t j = 0; j < N; ++j)
@@ -427,19 +611,58 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
     size_t smem_jmp = sizeof(double) * ((size_t)N * 4 + (size_t)nqf * (M_ext + 1));
     ASG_CHECK(ctx, smem_vol <= 200 * 1024 && smem_jmp <= 200 * 1024, ASGFEM_EINVAL,
               "estimate: too many active modes for the shared-memory tables (N <= 6000 supported)");
-    ASG_CUDA(ctx, cudaFuncSetAttribute(k_est_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    ASG_CUDA(ctx, cudaFuncSetAttribute(k_est_jumps, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int gridc = (int)std::min<int64_t>(ncells, 148 * 8), gridf = (int)std::min<int64_t>(nfaces, 148 * 8);
-    ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    k_est_volume<<<gridc, 256, smem_vol, ctx->stream>>>(a);
-    k_est_jumps<<<gridf, 256, smem_jmp, ctx->stream>>>(a);
-    ASG_CUDA(ctx, cudaGetLastError());
+    DevBuf d_mi, d_den, d_lam, d_z1, d_Z2;
+    if (kind == 0) {
+        ASG_CUDA(ctx, cudaFuncSetAttribute(k_est_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ASG_CUDA(ctx, cudaFuncSetAttribute(k_est_jumps, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        k_est_volume<<<gridc, 256, smem_vol, ctx->stream>>>(a);
+        k_est_jumps<<<gridf, 256, smem_jmp, ctx->stream>>>(a);
+        ASG_CUDA(ctx, cudaGetLastError());
+    } else {
+        // log-transformed primal problem
+        ASG_CHECK(ctx, N_ext <= 2048, ASGFEM_EINVAL, "estimate (log-primal): at most 2048 extended multi-indices");
+        std::vector<int32_t> mi32((size_t)(N_ext * M_ext));
+        std::vector<double> den((size_t)N_ext);
+        for (int64_t j = 0; j < N_ext; ++j) {
+            double fac = 1.0;
+            int64_t deg = 0;
+            for (int64_t d = 0; d < M_ext; ++d) {
+                const int64_t e = mi_ext[j * M_ext + d];
+                mi32[(size_t)(j * M_ext + d)] = (int32_t)e;
+                for (int64_t r = 2; r <= e; ++r) fac *= (double)r;
+                deg += e;
+            }
+            den[(size_t)j] = std::sqrt(fac) * ((deg & 1) ? -1.0 : 1.0);
+        }
+        if ((rc = upload(d_mi, mi32.data(), mi32.size() * 4))) return rc;
+        if ((rc = upload(d_den, den.data(), den.size() * 8))) return rc;
+        if (lam_at_qp && (rc = upload(d_lam, lam_at_qp, sizeof(double) * (size_t)N_ext * nq * ncells))) return rc;
+        ASG_CUDA(ctx, cudaMalloc(&d_z1.p, sizeof(double) * (size_t)ncells));
+        ASG_CUDA(ctx, cudaMalloc(&d_Z2.p, sizeof(double) * (size_t)ncells * ldE));
+        EstLogArgs L;
+        L.mi = (const int32_t*)d_mi.p;
+        L.den = (const double*)d_den.p;
+        L.lam_qp = lam_at_qp ? (const double*)d_lam.p : nullptr;
+        L.ntrunc = ntrunc;
+        L.zeta1 = (double*)d_z1.p;
+        L.Z2 = (double*)d_Z2.p;
+        const size_t smem_log = sizeof(double) * (3 * (size_t)N + (size_t)std::max<int64_t>(ntrunc, M_ext) + 1 + 2 * ((size_t)M_ext + 1));
+        ASG_CHECK(ctx, smem_log <= 200 * 1024, ASGFEM_EINVAL, "estimate (log-primal): too many active modes for the shared-memory tables");
+        ASG_CUDA(ctx, cudaFuncSetAttribute(k_estlog_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ASG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        k_estlog_volume<<<gridc, 256, smem_log, ctx->stream>>>(a, L);
+        k_estlog_jumps<<<gridf, 256, 0, ctx->stream>>>(a);
+        ASG_CUDA(ctx, cudaGetLastError());
+    }
 
     // column sums: volume part over cells, jump part over faces (each interior face once, :414)
     const int chunk = 256;
     const int ncc = (int)((ncells + chunk - 1) / chunk), nfc = (int)((nfaces + chunk - 1) / chunk);
     ASG_CUDA(ctx, cudaMalloc(&d_part.p, sizeof(double) * (size_t)std::max(ncc, nfc) * N_ext));
-    ASG_CUDA(ctx, cudaMalloc(&d_sums.p, sizeof(double) * 2 * N_ext));
+    ASG_CUDA(ctx, cudaMalloc(&d_sums.p, sizeof(double) * (3 * N_ext + 1)));  // volume, jumps, [log-primal: zeta2 per mode, zeta1]
+    ASG_CUDA(ctx, cudaMemsetAsync(d_sums.p, 0, sizeof(double) * (3 * N_ext + 1), ctx->stream));
     dim3 gb(ncc, (unsigned)((N_ext + 127) / 128));
     // row-sharded run (asgfem_set_owned_cells): a cell counts where it is owned, an interior face with the share of its two
     // cells that this rank owns (1, 1/2 or 0: the neighbour adds the other half); the sums are all-reduced below
@@ -463,12 +686,19 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
     k_colsum_partial<<<gf, 128, 0, ctx->stream>>>(a.JF, nfaces, ldE, (int)N_ext, chunk, (double*)d_part.p, wface);
     k_colsum_final<<<(unsigned)((N_ext + 127) / 128), 128, 0, ctx->stream>>>((double*)d_part.p, nfc, (int)N_ext,
                                                                             (double*)d_sums.p + N_ext);
+    if (kind == 1) {  // data terms: zeta2 per mode over the cells, zeta1 over the cells
+        k_colsum_partial<<<gb, 128, 0, ctx->stream>>>((const double*)d_Z2.p, ncells, ldE, (int)N_ext, chunk, (double*)d_part.p, wcell);
+        k_colsum_final<<<(unsigned)((N_ext + 127) / 128), 128, 0, ctx->stream>>>((double*)d_part.p, ncc, (int)N_ext,
+                                                                                (double*)d_sums.p + 2 * N_ext);
+        k_colsum_partial<<<dim3(ncc, 1), 128, 0, ctx->stream>>>((const double*)d_z1.p, ncells, 1, 1, chunk, (double*)d_part.p, wcell);
+        k_colsum_final<<<1, 128, 0, ctx->stream>>>((double*)d_part.p, ncc, 1, (double*)d_sums.p + 3 * N_ext);
+    }
     k_add_face_jumps<<<gridc, 256, 0, ctx->stream>>>(a.E, a.JF, a.cell_faces, ncells, ldE, (int)N_ext);
     ASG_CUDA(ctx, cudaGetLastError());
     ASG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    if ((rc = dist_allreduce_sum(ctx, (double*)d_sums.p, (size_t)(2 * N_ext)))) return rc;  // no-op without a communicator
-    std::vector<double> sums((size_t)(2 * N_ext));
-    ASG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums.p, sizeof(double) * 2 * N_ext, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = dist_allreduce_sum(ctx, (double*)d_sums.p, (size_t)(3 * N_ext + 1)))) return rc;  // no-op without a communicator
+    std::vector<double> sums((size_t)(3 * N_ext + 1));
+    ASG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums.p, sizeof(double) * (3 * N_ext + 1), cudaMemcpyDeviceToHost, ctx->stream));
 
     // marking indicator: row sums over the selected columns (what scripts/poisson.jl:402 takes from eta4cell) - ncells doubles
     // instead of the ncells x N_ext matrix
@@ -515,8 +745,18 @@ int estimate_poisson_primal(asgfem_ctx* ctx, const double* u, int64_t N_ext, int
         ctx->last_estimate_ms = ms;
     }
     for (int64_t j = 0; j < N_ext; ++j) {
-        double vol = std::sqrt(sums[j]);                       // eta4modes[j] = sqrt(sum(eta4cell[:,j]))  (:362-364)
-        eta4modes[j] = std::sqrt(vol * vol + sums[N_ext + j]);  // sqrt(eta4modes[j]^2 + sum(jumps4face))   (:414)
+        double vol = std::sqrt(sums[j]);                       // eta4modes[j] = sqrt(sum(eta4cell[:,j]))  (:362-364 / :219-221)
+        if (kind == 0)
+            eta4modes[j] = std::sqrt(vol * vol + sums[N_ext + j]);  // sqrt(eta4modes[j]^2 + sum(jumps4face))   (:414)
+        else  // log-primal (:244): eta4modes[j] += sqrt(eta4modes[j]^2 + sum(jumps4face)) for the active modes - "+=" as in the reference
+            eta4modes[j] = j < N ? vol + std::sqrt(vol * vol + sums[N_ext + j]) : vol;
+    }
+    if (kind == 1 && zeta3) {
+        double z2 = 0.0;
+        for (int64_t j = 0; j < N_ext; ++j) z2 += sums[2 * N_ext + j];
+        zeta3[1] = sums[3 * N_ext];
+        zeta3[2] = z2;
+        zeta3[0] = zeta3[1] - zeta3[2];  // zeta_data = zeta_data1 - zeta_data2   (:248, :256)
     }
     return 0;
 }

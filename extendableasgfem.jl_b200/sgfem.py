@@ -220,6 +220,34 @@ def estimate(sol: SGFEVector, C, rhs=None, bonus_quadorder=1, tail_extension=(10
     return eta4modes, eta4cell, mi_ext
 
 
+def estimate_logpoisson(sol: SGFEVector, C, rhs, bonus_quadorder=1, tail_extension=(5, 2), lambda_at_qp=None):
+    """estimate(LogTransformedPoissonProblemPrimal, sol, C; rhs, bonus_quadorder, tail_extension) (src/estimate.jl:70-257):
+    returns (eta4modes, eta4cell, multi_indices_extended, zeta_data).  tail_extension is the two-element form the scripts
+    pass (the reference's scalar default 5 would fail at tail_extension[2] in add_boundary_modes).  Mesh, space and coefficient must be resident
+    (solve_logpoisson).  lambda_at_qp (N_ext, ncells, nq): the caller's interpolated <e^-a, H_nu> at the quadrature points
+    (what the reference's H1Pk{quadorder} interpolation yields); None evaluates lambda_nu directly on the device."""
+    if rhs is None:
+        raise ValueError("estimate: the right-hand side function rhs(x, y) is required")
+    ctx, FES = sol.TB.ctx, sol.FES_space
+    g = FES.grid
+    mi_ext = _mi.add_boundary_modes(sol.TB.multi_indices, tail_extension=tail_extension)
+    quadorder = 2 * (FES.order - 1) + bonus_quadorder
+    xref, w = _grids.quadrature_rule(quadorder)
+    sf, wf = _grids.quadrature_rule_1d(max(quadorder, 2 * (FES.order - 1)))
+    c = g.cellnodes
+    x1, x2, x3 = g.coords[c[:, 0]], g.coords[c[:, 1]], g.coords[c[:, 2]]
+    xq = x1[:, None, :] + xref[None, :, 0:1] * (x2 - x1)[:, None, :] + xref[None, :, 1:2] * (x3 - x1)[:, None, :]
+    fq = rhs(xq[:, :, 0], xq[:, :, 1])
+    lam = None
+    if lambda_at_qp is not None:  # (N_ext, ncells, nq) -> [cell][q][j]
+        lam = np.ascontiguousarray(np.transpose(np.asarray(lambda_at_qp, dtype=np.float64), (1, 2, 0)))
+    ctx.vec_ensure(1)
+    ctx.vec_upload(0, sol.entries)
+    em, ec, zeta = ctx.estimate_logpoisson_primal(0, np.array(mi_ext, dtype=np.int64), xref, w, sf, wf, g.ncells, fq,
+                                                  len(C.decay_factors), lam)
+    return em, ec, mi_ext, float(zeta[0])
+
+
 def deterministic_sample_solutions(FES, C, samples, rhs=None, bonus_quadorder_a=2, device=0, atol=1e-14, rtol=1e-14):
     """The deterministic reference solutions of calculate_sampling_error (src/sampling_error.jl:112-128) for the affine
     coefficient: for every column xi of `samples` (Msamples x nsamples) solve  -div((a_0 + sum_m xi_m a_m) grad u) = f  on

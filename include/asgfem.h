@@ -224,6 +224,17 @@ int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ex
                                    const double* f_at_qp, int32_t nqf, const double* sf, const double* wf,
                                    double* eta4cell, double* eta4modes);
 
+/* (f2) estimate(::Type{LogTransformedPoissonProblemPrimal}, sol, C; rhs, bonus_quadorder, tail_extension) - src/estimate.jl:70-257.
+ * Same tables as above.  lambda_nu = <e^-a, H_nu> (expa_PCE_mop, factor -1, N_truncate = ntrunc): the reference interpolates
+ * it into H1Pk{quadorder} and evaluates the interpolant at the quadrature points; lam_at_qp (N_ext x nq x ncells column-major,
+ * the caller's interpolated values) reproduces that, NULL evaluates lambda_nu directly at the quadrature points (the
+ * commented-out line :184 of the reference).  f_at_qp is required.  zeta3 (3 doubles, may be NULL) = zeta_data,
+ * zeta_data1, zeta_data2 (:156-175, :248).  eta4modes of the active modes reproduces the "+=" of :244. */
+int asgfem_estimate_logpoisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
+                                      int32_t nq, const double* xref, const double* w, const double* f_at_qp,
+                                      const double* lam_at_qp, int32_t ntrunc, int32_t nqf, const double* sf, const double* wf,
+                                      double* eta4cell, double* eta4modes, double* zeta3);
+
 /* The same estimator with the outputs the adaptive loop consumes (scripts/poisson.jl:341-420): eta4modes and
  * cellsum[c] = sum_k eta4cell[c, sel[k]] (sel: 1-based columns, e.g. the active modes - the indicator handed to bulk_mark
  * at :402) instead of the ncells x N_ext matrix, whose transfer to the host dominates the call above. */

@@ -270,6 +270,29 @@ assemble_logprimal_rhs!(ctx::Context, xref::Matrix{Float64}, w::Vector{Float64},
         (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint), ctx.h, length(w), xref, w, f_at_qp, ntrunc, slot))
 
 """
+    estimate_logpoisson(ctx, sol, C, mi_ext, qf, qf1, f_at_qp; lam_at_qp = nothing)
+
+Drop-in for `estimate(::Type{LogTransformedPoissonProblemPrimal}, sol, C; ...)` (src/estimate.jl:70-257).  `lam_at_qp[j, q, cell]`
+= the caller's H1Pk{quadorder} interpolant of <e^-a, H_nu_j> at the cell quadrature points (what :117-131 builds with
+`interpolate!`); `nothing` evaluates lambda_nu directly on the device.  Returns (eta4modes, eta4cell, zeta_data).
+"""
+function estimate_logpoisson(ctx::Context, sol::SGFEVector, C, mi_ext::Matrix{Int64}, xref::Matrix{Float64}, w::Vector{Float64},
+        sf::Vector{Float64}, wf::Vector{Float64}, f_at_qp::Matrix{Float64}; lam_at_qp = nothing)
+    ncells = size(f_at_qp, 2)
+    check(ctx, ccall((:asgfem_vec_alloc, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.h, 1))
+    check(ctx, ccall((:asgfem_vec_upload, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), ctx.h, 0, sol.entries))
+    eta4cell = zeros(Float64, ncells, size(mi_ext, 2))
+    eta4modes = zeros(Float64, size(mi_ext, 2))
+    zeta = zeros(Float64, 3)
+    check(ctx, ccall((:asgfem_estimate_logpoisson_primal, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint,
+            Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.h, 0, size(mi_ext, 2), size(mi_ext, 1), mi_ext, length(w), xref, w, f_at_qp,
+        lam_at_qp === nothing ? C_NULL : lam_at_qp, length(C.decay_factors), length(wf), sf, wf, eta4cell, eta4modes, zeta))
+    return eta4modes, eta4cell, zeta[1]
+end
+
+"""
     deterministic_sample_solutions(ctx, Samples, b) -> Matrix (ndofs x nsamples)
 
 The deterministic reference solutions of `calculate_sampling_error` (src/sampling_error.jl:112-128) for the affine

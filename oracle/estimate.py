@@ -131,3 +131,97 @@ def estimate_poisson_primal(space, sol, multi_indices, family, coeff, f=None, bo
         eta4cell[:, j] += jf[mesh.cellfaces].sum(axis=1)
         eta4modes[j] = np.sqrt(eta4modes[j] ** 2 + jf.sum())
     return eta4modes, eta4cell, mi_ext
+
+
+def estimate_logpoisson_primal(space, sol, multi_indices, family, coeff, f, bonus_quadorder=1, tail_extension=(5, 2),
+                               lambda_at_qp=None):
+    """estimate(::Type{LogTransformedPoissonProblemPrimal}, ...) (src/estimate.jl:70-257).  Returns (eta4modes, eta4cell,
+    multi_indices_extended, (zeta_data, zeta_data1, zeta_data2)).
+
+    * :134-217 volume term per (cell, mode, qp): (lambda_j f + [j <= N, order > 1] Lap u_j + sum_m grad a_m . grad w_{j,m})^2 with
+      w_{j,m} = G-weighted active neighbours of j in direction m; scaling |T|^2 (active) / |T| (boundary modes); eta4modes =
+      sqrt of the column sums (:219-221);
+    * :156-175 zeta_data1 = sum |T| w_q f^2 exp(2 sum_{m <= maxm} a_m^2), zeta_data2 = sum |T| w_q f^2 sum_j lambda_j^2;
+    * :232-244 jumps of grad u_j over interior faces times |F| for the active modes, added to the three faces of a cell;
+      eta4modes[j] += sqrt(eta4modes[j]^2 + sum(jumps))  ("+=" as written in the reference).
+    lambda_j(x_q): the reference evaluates an H1Pk{quadorder} interpolant of lambda_j (third-party interpolate!, parity
+    unpinned); `lambda_at_qp` (N_ext, ncells, nq) supplies such values, None evaluates lambda_j directly (the reference's
+    commented-out line :184)."""
+    mesh = space.mesh
+    order = space.order
+    n = space.ndofs
+    N = len(multi_indices)
+    ncells = mesh.ncells
+    U = sol.reshape(N, n)
+    mi_ext = mi_mod.add_boundary_modes([list(m) for m in multi_indices], tail_extension=tail_extension)
+    M_ext = len(mi_ext[0])
+    N_ext = len(mi_ext)
+    G = tb_mod.coupling_matrix(family, mi_ext).tocsr()
+    PLUS, MINUS = mi_mod.get_neighbours(mi_ext)
+    couplings = []
+    for j in range(N_ext):
+        lst = []
+        for m in range(M_ext):
+            for tab in (PLUS, MINUS):
+                k = tab[m, j]
+                if 0 < k <= N:
+                    lst.append((m + 1, k - 1, G[m * N_ext + j, k - 1]))
+        couplings.append(lst)
+    quadorder = 2 * (order - 1) + bonus_quadorder
+    xref, w = fem.quadrature_rule(quadorder)
+    xq = space.physical_points(xref)
+    vol = mesh.cellvolumes
+    cd = space.celldofs
+    fq = f(xq[:, :, 0], xq[:, :, 1])
+    lam = fem.lambda_mu(coeff, mi_ext, xq[:, :, 0], xq[:, :, 1]) if lambda_at_qp is None else np.asarray(lambda_at_qp)
+    kmL2 = np.zeros(xq.shape[:2])
+    for m in range(1, coeff.maxm + 1):
+        kmL2 = kmL2 + coeff.am(m, xq[:, :, 0], xq[:, :, 1]) ** 2
+    zeta1 = float(np.einsum("cq,cq,q,c->", fq ** 2, np.exp(2 * kmL2), w, vol))
+    zeta2 = float(np.einsum("jcq,cq,q,c->", lam ** 2, fq ** 2, w, vol))
+    # gradients of the active modes at the quadrature points
+    g = space.lambda_gradients()
+    _, dphi = space.basis(xref)
+    gradphi = np.einsum("qdl,clx->cqdx", dphi, g)  # (nc, nq, nd, 2)
+    gradU = np.einsum("mcd,cqdx->mcqx", U[:, cd], gradphi)  # (N, nc, nq, 2)
+    lapU = np.einsum("mcd,cd->mc", U[:, cd], space.laplacians()) if order > 1 else None
+    gradam = {m: np.stack(coeff.gradam(m, xq[:, :, 0], xq[:, :, 1]), axis=-1) for m in range(1, M_ext + 1)}  # (nc, nq, 2)
+    eta4cell = np.zeros((ncells, N_ext))
+    for j in range(N_ext):
+        ftemp = lam[j] * fq
+        if order > 1 and j < N:
+            ftemp = ftemp + lapU[j][:, None]
+        sig = np.zeros(xq.shape[:2])
+        for (m, k, gw) in couplings[j]:
+            sig = sig + gw * np.einsum("cqx,cqx->cq", gradam[m], gradU[k])
+        eta4cell[:, j] = ((ftemp + sig) ** 2) @ w
+        eta4cell[:, j] *= vol ** 2 if j < N else vol
+    eta4modes = np.sqrt(eta4cell.sum(axis=0))
+    # jumps of grad u_j (active modes), exact face integrals with the 1-D rule
+    s_q, w_f = fem.quadrature_rule_1d(max(quadorder, 2 * (order - 1)))
+    interior = np.where(mesh.facecells[:, 1] >= 0)[0]
+    fa = mesh.coords[mesh.facenodes[interior, 0]]
+    fb = mesh.coords[mesh.facenodes[interior, 1]]
+    xf = fa[:, None, :] + s_q[None, :, None] * (fb - fa)[:, None, :]
+    grads = []
+    for side in (0, 1):
+        cells = mesh.facecells[interior, side]
+        x1 = mesh.coords[mesh.cellnodes[cells, 0]]
+        gl = g[cells]
+        lamb = np.einsum("fix,fqx->fqi", gl, xf - x1[:, None, :])
+        lamb[:, :, 0] += 1.0
+        ref = lamb[:, :, 1:3]
+        nif, nqf = ref.shape[:2]
+        _, dph = space.basis(ref.reshape(-1, 2))
+        dph = dph.reshape(nif, nqf, -1, 3)
+        gphi = np.einsum("fqdl,flx->fqdx", dph, gl)
+        grads.append(np.einsum("mfd,fqdx->mfqx", U[:, cd[cells]], gphi))
+    jump = grads[0] - grads[1]
+    flen = mesh.facevolumes
+    for j in range(N):
+        jf = np.zeros(mesh.nfaces)
+        jf[interior] = flen[interior] * np.einsum("q,fqx,fqx->f", w_f, jump[j], jump[j])  # integral over the face
+        jf *= flen                                                                       # jumps4face .*= FaceVolumes
+        eta4cell[:, j] += jf[mesh.cellfaces].sum(axis=1)
+        eta4modes[j] += np.sqrt(eta4modes[j] ** 2 + jf.sum())
+    return eta4modes, eta4cell, mi_ext, (zeta1 - zeta2, zeta1, zeta2)

@@ -730,3 +730,43 @@ def test_logprimal_device_assembly_and_solve_match_oracle(order):
     assert np.abs(sol.entries - ref_sol).max() <= 1e-10 * np.abs(ref_sol).max()
     assert np.array_equal(np.sort(np.asarray(bd) - 1), np.sort(space.bdofs))
     ctx.close()
+
+
+@pytest.mark.parametrize("order,domain", [(1, "square"), (2, "square"), (2, "lshape")])
+def test_logprimal_estimator_matches_oracle(order, domain):
+    """Row f2: estimate(LogTransformedPoissonProblemPrimal, ...) (src/estimate.jl:70-257) on the device against the oracle's
+    restatement: eta4cell, eta4modes (with the reference's '+=' for the active modes), zeta_data; 1e-10 relative."""
+    from oracle import estimate as oest
+    base = omesh.grid_unitsquare() if domain == "square" else omesh.grid_lshape()
+    m = omesh.uniform_refine(base, 3)
+    Cc = ocoef.StochasticCoefficientCosinus(tau=0.5, decay=2.0, mean=0.0, maxm=12)
+    modes = [[0, 0, 0], [1, 0, 0], [0, 1, 0], [2, 0, 0], [0, 0, 1], [1, 1, 0]]
+    f = lambda x, y: 1.0 + x * y  # noqa: E731
+    space = ofem.FESpace(m, order)
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal(len(modes) * space.ndofs) * 0.1
+    em, ec, ext, zeta = oest.estimate_logpoisson_primal(space, u, modes, opoly.HERMITE, Cc, f, bonus_quadorder=2, tail_extension=(5, 2))
+    g = A.Grid(m.coords, m.cellnodes, m.bfacenodes)
+    fes = A.FESpace(g, order)
+    TB = A.TensorizedBasis(A.HermitePolynomials, modes)
+    sol = A.SGFEVector(fes, TB)
+    Cd = A.StochasticCoefficientCosinus(tau=0.5, decay=2.0, mean=0.0, maxm=12)
+    ctx = TB.ctx
+    ctx.set_mesh(g.coords, g.cellnodes + 1)
+    ctx.set_space(order, fes.ndofs, fes.celldofs + 1)
+    ctx.set_coefficient_cosinus(Cd.mean_value, Cd.decay_factors, Cd.b1, Cd.b2)
+    sol.entries[:] = u
+    gm, gc, gext, gz = A.estimate_logpoisson(sol, Cd, f, bonus_quadorder=2, tail_extension=(5, 2))
+    assert gext == ext
+    assert gc.shape == ec.shape
+    assert np.abs(gm - em).max() <= TOL_SOLVE * em.max()
+    assert np.abs(gc - ec).max() <= TOL_SOLVE * ec.max()
+    assert abs(gz - zeta[0]) <= 1e-9 * max(abs(zeta[1]), abs(zeta[2]))
+    # caller-supplied lambda values at the quadrature points (the reference's interpolation hand-off): same numbers when
+    # the exact values are passed in
+    xref, _ = A.quadrature_rule(2 * (order - 1) + 2)
+    xq = space.physical_points(xref)
+    lam = ofem.lambda_mu(Cc, ext, xq[:, :, 0], xq[:, :, 1])
+    gm2, gc2, _, gz2 = A.estimate_logpoisson(sol, Cd, f, bonus_quadorder=2, tail_extension=(5, 2), lambda_at_qp=lam)
+    assert np.abs(gm2 - gm).max() <= 1e-12 * gm.max() and np.abs(gc2 - gc).max() <= 1e-12 * gc.max()
+    ctx.close()
