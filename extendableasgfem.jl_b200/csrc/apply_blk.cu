@@ -483,7 +483,7 @@ struct BlkArgs {
     const double* zero_row;
     const int32_t* rowmeta;
     int64_t nnz, ld, r0, r1;
-    int Mp, P, single;
+    int Mp, P, single, fullks;
     uint32_t nwords, off_pair, off_crec, off_gcol, off_pbase, off_srec, off_list, off_roww, tbuf_doubles;
 };
 
@@ -620,9 +620,12 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
     // (lane 4 q + kk <- lane 8 kk + q).  Slots beyond the row read a row of zeros.
     const int lrow = lane >> 3, lchunk = lane & 7;
     const int frag_src = (kk << 3) | q;
+    // rows shorter than 4 (KS - 1) entries need fewer k-steps (P2: 19 entries at vertex dofs, 9 at edge dofs = 75 % of the rows)
+    int ks_x = KS;  // k-steps of the dof row whose X fragments are in the registers
     auto row_ptrs = [&](int ri, const char* (&xr)[KS]) {
         const unsigned m = meta_s + (unsigned)((ri & (RING - 1)) * ME) * 4u;
         const int len = b_lds_s32(m + 8);
+        if constexpr (KS > 2) ks_x = a.fullks ? KS : max(1, (len + 3) >> 2);
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             const int slot = 4 * s + lrow;
@@ -647,7 +650,8 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
             if (pw[p] & 0xF000u) {
                 const uint32_t cb = (pw[p] & 0xFFFu) * 128u;
 #pragma unroll
-                for (int s = 0; s < KS; ++s) X[p][s] = b_ldg_f64x2(xr[s] + cb);
+                for (int s = 0; s < KS; ++s)
+                    if (KS <= 2 || s < ks_x) X[p][s] = b_ldg_f64x2(xr[s] + cb);
             }
         }
     };
@@ -685,6 +689,7 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
         const unsigned tb = tb_s + par * tb_bytes + lane * 16;
         const unsigned ksrc = ks_s + (unsigned)kcur * kbuf_bytes + kk * (8 * KS);
         const unsigned sbase = srec_s + b_lds_u32(sm0 + a.off_pbase * 4u + pass * 4) * 32u;
+        const int ks = ks_x;  // the X fragments in the registers belong to this stage's row
         uint32_t pw[NPW];
         if constexpr (NPW == 2) {
             const uint2 v = b_lds_u32x2(pair_s + pass * (WARPS * NPW * 4));
@@ -703,8 +708,10 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
                 double xe[KS], xo[KS];
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
-                    xe[s] = __shfl_sync(0xffffffffu, X[p][s].x, frag_src);
-                    xo[s] = __shfl_sync(0xffffffffu, X[p][s].y, frag_src);
+                    if (KS <= 2 || s < ks) {  // warp-uniform
+                        xe[s] = __shfl_sync(0xffffffffu, X[p][s].x, frag_src);
+                        xo[s] = __shfl_sync(0xffffffffu, X[p][s].y, frag_src);
+                    }
                 }
                 const uint32_t slot = pw[p] >> 16;
                 unsigned sr = sbase + slot * 32u;
@@ -715,15 +722,19 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
                     double ae[KS], ao[KS];
 #pragma unroll
                     for (int s = 0; s < KS; s += 2) {
-                        const double2 ve = b_lds_f64x2(ke + s * 8), vo = b_lds_f64x2(ko + s * 8);
-                        ae[s] = ve.x, ae[s + 1] = ve.y;
-                        ao[s] = vo.x, ao[s + 1] = vo.y;
+                        if (KS <= 2 || s < ks) {
+                            const double2 ve = b_lds_f64x2(ke + s * 8), vo = b_lds_f64x2(ko + s * 8);
+                            ae[s] = ve.x, ae[s + 1] = ve.y;
+                            ao[s] = vo.x, ao[s + 1] = vo.y;
+                        }
                     }
                     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
-                        b_dmma(c0, c1, ae[s], xe[s]);
-                        b_dmma(c2, c3, ao[s], xo[s]);
+                        if (KS <= 2 || s < ks) {
+                            b_dmma(c0, c1, ae[s], xe[s]);
+                            b_dmma(c2, c3, ao[s], xo[s]);
+                        }
                     }
                     b_sts_f64x2(td, c0, c1);
                     b_sts_f64x2(td + 512u, c2, c3);
@@ -893,6 +904,7 @@ int apply_blk_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
     a.Mp = ctx->M + 1;
     a.P = B->P;
     a.single = B->single ? 1 : 0;
+    a.fullks = getenv("ASGFEM_BLK_FULLKS") ? 1 : 0;  // measurement knob: all k-steps for every row
     a.nwords = B->nwords;
     a.off_pair = B->off_pair;
     a.off_crec = B->off_crec;
