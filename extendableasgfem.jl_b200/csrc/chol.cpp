@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstring>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <numeric>
@@ -218,9 +220,23 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
 
 }  // namespace
 
+namespace {
+// phase timing on stderr with ASGFEM_CHOL_VERBOSE=1
+struct CholTick {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    bool on = std::getenv("ASGFEM_CHOL_VERBOSE") != nullptr;
+    void operator()(const char* what) {
+        auto now = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[chol] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
 int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,
                      const uint8_t* is_boundary, const double* coords_full, int32_t max_block, CholFactor& F,
                      std::string& err) {
+    CholTick chol_tick;
     // ---- reduced numbering -----------------------------------------------------------------------
     std::vector<int32_t> red((size_t)n_full, -1), full;
     for (int64_t i = 0; i < n_full; ++i)
@@ -262,7 +278,9 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
             xy[2 * r + 1] = coords_full[2 * (int64_t)full[r] + 1];
         }
     }
+    chol_tick("graph");
     nested_dissection(g, perm, coords_full ? xy.data() : nullptr, F.blocks, max_block);
+    chol_tick("nested dissection");
     {
         int32_t at = 0;
         for (const BlockRec& b : F.blocks) {
@@ -310,6 +328,7 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         }
     }
 
+    chol_tick("permuted matrix");
     // ---- elimination tree (Liu) ---------------------------------------------------------------------
     std::vector<int32_t> parent((size_t)n, -1), anc((size_t)n, -1);
     for (int32_t k = 0; k < n; ++k)
@@ -323,6 +342,7 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
             }
         }
 
+    chol_tick("elimination tree");
     // ---- row patterns by row-subtree traversal (ereach); pass 1 counts, pass 2 factorises ------------
     std::vector<int32_t> flag((size_t)n, -1), stack((size_t)n), rowlen((size_t)n, 0);
     std::vector<int64_t> colcount((size_t)n, 1);  // diagonal
@@ -348,6 +368,7 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         lnz += n - top;
         for (int32_t q = top; q < n; ++q) colcount[stack[q]]++;
     }
+    chol_tick("symbolic (row counts)");
     // column storage for the numeric phase (diagonal first), row storage for the output
     std::vector<int64_t> Lcp((size_t)n + 1, 0);
     for (int32_t j = 0; j < n; ++j) Lcp[j + 1] = Lcp[j] + colcount[j];
@@ -619,6 +640,7 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
     }
     F.perm.resize((size_t)n);
     for (int32_t k = 0; k < n; ++k) F.perm[k] = full[perm[k]];
+    chol_tick("numeric + row sort");
     return 0;
 }
 
