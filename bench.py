@@ -388,7 +388,7 @@ def run_gpu(args):
                       "note": "end-to-end leg is measured at N=1 only"}
     # ---- PCG solve time (second half of the BASELINE metric): f = 1, zero start, atol = rtol = 1e-14 -------------
     if world > 1 and not args.no_pcg:
-        # sharded solve: rank-local mean preconditioner (block-Jacobi over the strips), all-reduced inner products
+        # sharded solve inside the library: exact mean preconditioner (row-shard <-> mode-shard swap), all-reduced inner products
         try:
             t0 = time.perf_counter()
             # exact mean preconditioner: K_0 of the GLOBAL 1024 x (1024 world) mesh, assembled by a throw-away context

@@ -8,6 +8,12 @@ reference has no distributed path at all (dead `using Distributed`, src/Extendab
 Everything here is host-side bookkeeping (integer partitions, halo lists, the Krylov recurrence on scalars); all
 arithmetic on vectors happens in the per-rank `Context` (libasgfem_cuda.so).  The backend object is injectable so
 that the exchange/partition logic is tested with gloo on CPU (tests/test_distributed_cpu.py).
+
+Since round 2 the production path is INSIDE the library (csrc/dist.cu: asgfem_comm_init / asgfem_set_halo /
+asgfem_precond_setup_global - NCCL halo exchange, all-reduced inner products, exact mean preconditioner); what remains
+here is the partitioner (`LocalProblem`, `strip_shard`), the context setup helpers and `DistributedOperator` / `pcg`
+as the host-driven reference implementation of the same algorithm (rank-local block-Jacobi preconditioner) that the
+gloo tests exercise without a GPU.
 """
 from __future__ import annotations
 
