@@ -39,7 +39,7 @@ struct BlkPlan {
     int KS = 0, P = 1, NPW = 0, NG = 0, W = 16;
     bool lists_global = false;
     bool single = false;  // one pass with a single T buffer (two barriers per dof row)
-    uint32_t nwords = 0, off_pair = 0, off_crec = 0, off_gcol = 0, off_pbase = 0, off_srec = 0, off_list = 0, off_roww = 0, off_lpass = 0, lslot_words = 0, tbuf_doubles = 0;
+    uint32_t nwords = 0, off_pair = 0, off_crec = 0, off_gcol = 0, off_pbase = 0, off_srec = 0, off_list = 0, off_roww = 0, tbuf_doubles = 0;
     size_t smem_bytes = 0;
     uint32_t* d_blob = nullptr;
     double* d_zero = nullptr;
@@ -365,8 +365,6 @@ int apply_blk_build(asgfem_ctx* ctx) {
         at = align4(at + (uint32_t)W * NG);
         const uint32_t off_pbase = at;
         at = align4(at + (uint32_t)npass);
-        const uint32_t off_lpass = at;
-        at = align4(at + 2u * (uint32_t)npass);
         const uint32_t off_srec = at;
         at = align4(at + (uint32_t)srec.size());
         const uint32_t off_list = at;
@@ -375,31 +373,16 @@ int apply_blk_build(asgfem_ctx* ctx) {
             list_off[k] = at;
             at += (uint32_t)glist[k].idx.size() / 2u;
         }
-        const uint32_t off_roww_unaligned = at;
         at = align4(at);
         const uint32_t off_roww = at;
         at = align4(at + (at - off_list) / 8u);  // 2 doubles per 32-word list row pair
         const uint32_t nwords = at;
         if ((off_roww - off_list) * 4u >= (1u << 20)) continue;
-        // lists in global memory: the lists of ONE pass are staged into a ring of three shared-memory slots by cp.async, one
-        // stage before the products of that pass (the first version read them from global memory in the consumer loop: 208
-        // (group, pass) segments per warp and dof row at config 5, each paying a global-memory round trip = 211 k cycles per row)
-        std::vector<uint32_t> lpass((size_t)npass * 2, 0u);  // per pass: first list word (relative to off_list), list words
-        uint32_t lslot_words = 0;
-        for (int pass = 0; pass < npass; ++pass) {
-            const uint32_t w0 = list_off[(size_t)pass * ngroups] - off_list;
-            const uint32_t w1 = (pass + 1 < npass ? list_off[(size_t)(pass + 1) * ngroups] : off_roww_unaligned) - off_list;
-            lpass[(size_t)pass * 2] = w0;
-            lpass[(size_t)pass * 2 + 1] = w1 - w0;
-            lslot_words = std::max(lslot_words, w1 - w0);
-        }
-        lslot_words = (lslot_words + 31u) & ~31u;
-        const uint32_t ring_words = lists_global ? 3u * (lslot_words + lslot_words / 8u) : 0u;
         const uint32_t nwords_smem = lists_global ? off_list : nwords;  // words copied into shared memory
         // one pass with the lists in shared memory: a single T buffer (two barriers per dof row) if that is what fits
         const bool single = npass == 1 && !lists_global && try_single;
         const size_t smem = (size_t)nwords_smem * 4 + 8ull * (4 + 4 * KS) * 4ull + 3ull * (size_t)(Mp + 1) * krow_bytes +
-                            (single ? 1ull : 2ull) * tbuf * 8ull + (size_t)ring_words * 4 + 16;
+                            (single ? 1ull : 2ull) * tbuf * 8ull + 16;
         if (verbose)
             fprintf(stderr,
                     "[blk] KS=%d W=%d passes=%d%s lists in %s NPW=%d NG=%d steps=%d T=%u doubles (x2) list rows %.0f (ideal %.0f) bank cost %ld -> %ld "
@@ -412,7 +395,6 @@ int apply_blk_build(asgfem_ctx* ctx) {
         std::vector<uint32_t> blob((size_t)nwords, 0u);
         std::memcpy(&blob[off_pair], pword.data(), pword.size() * 4);
         std::memcpy(&blob[off_pbase], passbase.data(), passbase.size() * 4);
-        std::memcpy(&blob[off_lpass], lpass.data(), lpass.size() * 4);
         std::memcpy(&blob[off_srec], srec.data(), srec.size() * 4);
         for (int w = 0; w < W; ++w)
             for (int k = 0; k < NG; ++k) {
@@ -450,8 +432,6 @@ int apply_blk_build(asgfem_ctx* ctx) {
         B->off_srec = off_srec;
         B->off_list = off_list;
         B->off_roww = off_roww;
-        B->off_lpass = off_lpass;
-        B->lslot_words = lslot_words;
         B->tbuf_doubles = tbuf;
         B->smem_bytes = smem;
         B->dmma_per_row = 2.0 * KS * total_steps;
@@ -503,8 +483,8 @@ struct BlkArgs {
     const double* zero_row;
     const int32_t* rowmeta;
     int64_t nnz, ld, r0, r1;
-    int Mp, P, single, fullks;
-    uint32_t nwords, off_pair, off_crec, off_gcol, off_pbase, off_srec, off_list, off_roww, off_lpass, lslot_words, tbuf_doubles;
+    int Mp, P, single;
+    uint32_t nwords, off_pair, off_crec, off_gcol, off_pbase, off_srec, off_list, off_roww, tbuf_doubles;
 };
 
 __device__ __forceinline__ void b_cp_async8(unsigned s, const void* gsrc) {
@@ -600,23 +580,11 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
     const unsigned pair_s = sm0 + a.off_pair * 4u + warp * (NPW * 4);  // + pass * WARPS * NPW * 4
     const unsigned crec_s = sm0 + a.off_crec * 4u + warp * (NG * 4);   // + pass * WARPS * NG * 4
     const unsigned srec_s = sm0 + a.off_srec * 4u + q * 4;             // + global step * 32
-    // lists: resident in shared memory, or (GL) the lists of one pass staged into a ring of three slots behind the T buffers
-    const unsigned ring_s = tb_s + 2u * tb_bytes;
-    const uint32_t lslot_bytes = a.lslot_words * 4u, rslot_bytes = a.lslot_words / 2u;  // 16 bytes of weights per 128 bytes of list
-    unsigned list_s = sm0 + a.off_list * 4u + lane * 4, roww_s = sm0 + a.off_roww * 4u;  // GL: set per consumed stage
-    auto ld_idx = [&](uint32_t off) { return b_lds_u32(list_s + off); };
-    auto ld_w = [&](uint32_t off) { return b_lds_f64x2(roww_s + off); };
-    // lists of `pass` -> ring slot (asynchronously; part of the cp.async group of the current stage)
-    auto stage_lists = [&](int pass, int slot) {
-        if constexpr (GL) {
-            const uint32_t w0 = b_lds_u32(sm0 + a.off_lpass * 4u + pass * 8), nw = b_lds_u32(sm0 + a.off_lpass * 4u + pass * 8 + 4);
-            const unsigned dl = ring_s + (unsigned)slot * (lslot_bytes + rslot_bytes), dr = dl + lslot_bytes;
-            const uint32_t* gl = a.blob + a.off_list + w0;
-            const uint32_t* gr = a.blob + a.off_roww + w0 / 8u;
-            for (uint32_t i = tid; i < nw / 4u; i += THREADS) b_cp_async16(dl + i * 16u, gl + i * 4u);
-            for (uint32_t i = tid; i < nw / 32u; i += THREADS) b_cp_async16(dr + i * 16u, gr + i * 4u);
-        }
-    };
+    const unsigned list_s = sm0 + a.off_list * 4u + lane * 4, roww_s = sm0 + a.off_roww * 4u;
+    const unsigned char* list_g = reinterpret_cast<const unsigned char*>(a.blob + a.off_list) + lane * 4;
+    const unsigned char* roww_g = reinterpret_cast<const unsigned char*>(a.blob + a.off_roww);
+    auto ld_idx = [&](uint32_t off) { return GL ? b_ldg_u32(list_g + off) : b_lds_u32(list_s + off); };
+    auto ld_w = [&](uint32_t off) { return GL ? b_ldg_f64x2(reinterpret_cast<const char*>(roww_g + off)) : b_lds_f64x2(roww_s + off); };
 
     uint32_t ycol[NG];  // byte offset of this thread's column of group g inside a row of Y (0xFFFFFFFF: unused slot)
 #pragma unroll
@@ -652,12 +620,9 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
     // (lane 4 q + kk <- lane 8 kk + q).  Slots beyond the row read a row of zeros.
     const int lrow = lane >> 3, lchunk = lane & 7;
     const int frag_src = (kk << 3) | q;
-    // rows shorter than 4 (KS - 1) entries need fewer k-steps (P2: 19 entries at vertex dofs, 9 at edge dofs = 75 % of the rows)
-    int ks_x = KS;  // k-steps of the dof row whose X fragments are in the registers
     auto row_ptrs = [&](int ri, const char* (&xr)[KS]) {
         const unsigned m = meta_s + (unsigned)((ri & (RING - 1)) * ME) * 4u;
         const int len = b_lds_s32(m + 8);
-        if constexpr (KS > 2) ks_x = a.fullks ? KS : max(1, (len + 3) >> 2);
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             const int slot = 4 * s + lrow;
@@ -682,8 +647,7 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
             if (pw[p] & 0xF000u) {
                 const uint32_t cb = (pw[p] & 0xFFFu) * 128u;
 #pragma unroll
-                for (int s = 0; s < KS; ++s)
-                    if (KS <= 2 || s < ks_x) X[p][s] = b_ldg_f64x2(xr[s] + cb);
+                for (int s = 0; s < KS; ++s) X[p][s] = b_ldg_f64x2(xr[s] + cb);
             }
         }
     };
@@ -705,8 +669,6 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
     const char* xr[KS];  // X rows of the dof row of the NEXT stage
     row_ptrs(0, xr);
     load_x(0, xr, X);
-    int tstage = 0;  // stages begun so far; the lists of the pass produced in stage t use ring slot t % 3
-    stage_lists(0, 0);
     b_cp_async_wait_all();
     __syncthreads();
 
@@ -723,7 +685,6 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
         const unsigned tb = tb_s + par * tb_bytes + lane * 16;
         const unsigned ksrc = ks_s + (unsigned)kcur * kbuf_bytes + kk * (8 * KS);
         const unsigned sbase = srec_s + b_lds_u32(sm0 + a.off_pbase * 4u + pass * 4) * 32u;
-        const int ks = ks_x;  // the X fragments in the registers belong to this stage's row
         uint32_t pw[NPW];
         if constexpr (NPW == 2) {
             const uint2 v = b_lds_u32x2(pair_s + pass * (WARPS * NPW * 4));
@@ -742,10 +703,8 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
                 double xe[KS], xo[KS];
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
-                    if (KS <= 2 || s < ks) {  // warp-uniform
-                        xe[s] = __shfl_sync(0xffffffffu, X[p][s].x, frag_src);
-                        xo[s] = __shfl_sync(0xffffffffu, X[p][s].y, frag_src);
-                    }
+                    xe[s] = __shfl_sync(0xffffffffu, X[p][s].x, frag_src);
+                    xo[s] = __shfl_sync(0xffffffffu, X[p][s].y, frag_src);
                 }
                 const uint32_t slot = pw[p] >> 16;
                 unsigned sr = sbase + slot * 32u;
@@ -756,19 +715,15 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
                     double ae[KS], ao[KS];
 #pragma unroll
                     for (int s = 0; s < KS; s += 2) {
-                        if (KS <= 2 || s < ks) {
-                            const double2 ve = b_lds_f64x2(ke + s * 8), vo = b_lds_f64x2(ko + s * 8);
-                            ae[s] = ve.x, ae[s + 1] = ve.y;
-                            ao[s] = vo.x, ao[s + 1] = vo.y;
-                        }
+                        const double2 ve = b_lds_f64x2(ke + s * 8), vo = b_lds_f64x2(ko + s * 8);
+                        ae[s] = ve.x, ae[s + 1] = ve.y;
+                        ao[s] = vo.x, ao[s + 1] = vo.y;
                     }
                     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
-                        if (KS <= 2 || s < ks) {
-                            b_dmma(c0, c1, ae[s], xe[s]);
-                            b_dmma(c2, c3, ao[s], xo[s]);
-                        }
+                        b_dmma(c0, c1, ae[s], xe[s]);
+                        b_dmma(c2, c3, ao[s], xo[s]);
                     }
                     b_sts_f64x2(td, c0, c1);
                     b_sts_f64x2(td + 512u, c2, c3);
@@ -779,7 +734,6 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
         if (nxt < nri) {
             if (npass == 0) row_ptrs(nxt, xr);
             load_x(npass, xr, X);
-            stage_lists(npass, (tstage + 1) % 3);  // consumed two stages from now: complete after the next stage's wait
         }
     };
     // weighted list sums of (row cri, pass cpass) from T buffer par into the accumulators; the last pass writes the Y row
@@ -800,12 +754,6 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
                 const uint4 v = b_lds_u32x4(crec_s + cpass * (WARPS * NG * 4) + g4 * 16);
                 cw[4 * g4] = v.x, cw[4 * g4 + 1] = v.y, cw[4 * g4 + 2] = v.z, cw[4 * g4 + 3] = v.w;
             }
-        }
-        if constexpr (GL) {
-            const uint32_t w0b = b_lds_u32(sm0 + a.off_lpass * 4u + cpass * 8) * 4u;  // byte offset of the pass inside the lists
-            const unsigned slot_s = ring_s + (unsigned)((tstage + 2) % 3) * (lslot_bytes + rslot_bytes);  // stage tstage - 1
-            list_s = slot_s - w0b + lane * 4;
-            roww_s = slot_s + lslot_bytes - (w0b >> 3);
         }
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -880,7 +828,6 @@ __global__ void __launch_bounds__(512, 1) k_apply_blk(const BlkArgs a) {
         cpass = pass;
         cri = ri;
         par ^= 1u;
-        ++tstage;
         if (produce && ++pass == a.P) {
             pass = 0, ++ri;
             kcur = kcur + 1 == KB ? 0 : kcur + 1;
@@ -946,7 +893,6 @@ int apply_blk_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
     a.Mp = ctx->M + 1;
     a.P = B->P;
     a.single = B->single ? 1 : 0;
-    a.fullks = getenv("ASGFEM_BLK_FULLKS") ? 1 : 0;  // measurement knob: all k-steps for every row
     a.nwords = B->nwords;
     a.off_pair = B->off_pair;
     a.off_crec = B->off_crec;
@@ -955,8 +901,6 @@ int apply_blk_launch(asgfem_ctx* ctx, const double* x, double* y, int64_t r0, in
     a.off_srec = B->off_srec;
     a.off_list = B->off_list;
     a.off_roww = B->off_roww;
-    a.off_lpass = B->off_lpass;
-    a.lslot_words = B->lslot_words;
     a.tbuf_doubles = B->tbuf_doubles;
     switch (B->KS * 2 + (B->lists_global ? 1 : 0)) {
         case 4: return launch_blk_np<2, false>(ctx, B, a);
