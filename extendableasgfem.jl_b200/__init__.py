@@ -4,7 +4,7 @@ The compute lives in libasgfem_cuda.so (hand-written CUDA for sm_100a, C ABI in 
 package is the host-side mirror of the reference's operator interface plus the ctypes binding.
 """
 from . import _lib
-from .context import Context, LEGENDRE, HERMITE, coupling_weights  # noqa: F401
+from .context import Context, LEGENDRE, HERMITE, coupling_weights, host_factor_solve  # noqa: F401
 from .coefficients import StochasticCoefficientCosinus  # noqa: F401
 from .multiindices import (generate_multiindices, prepare_multi_indices, add_boundary_modes,  # noqa: F401
                            classify_modes, graded_lex_multiindices)

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "asgfem_last_apply_ms": (c_i32, [vp, P(c_f64)]),
     "asgfem_last_estimate_ms": (c_i32, [vp, P(c_f64)]),
     "asgfem_precond_setup": (c_i32, [vp]),
+    "asgfem_host_factor_solve": (c_i32, [c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_i32]),
     "asgfem_precond_apply": (c_i32, [vp, c_i32, c_i32]),
     "asgfem_precond_apply_host": (c_i32, [vp, vp, vp]),
     "asgfem_pcg": (c_i32, [vp, vp, c_i32, c_f64, c_f64, c_i64, P(Stats)]),

@@ -419,6 +419,27 @@ def coupling_weights(family, maxdeg):
     return gp, gm
 
 
+def host_factor_solve(indptr, indices, data, bdofs_1based, b, coords_2xn=None):
+    """Host-only diagnostic of the factorisation behind Context.precond_setup (asgfem_host_factor_solve): K (CSR, 0-based,
+    symmetric) without the rows/columns bdofs, multifrontal Cholesky on the host cores, one solve.  Returns (x, lnz)."""
+    lib = _lib.load()
+    ip, ix, dv = _i64(indptr), _i32(indices), _f64(data)
+    n = len(ip) - 1
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[np.asarray(bdofs_1based, dtype=np.int64) - 1] = 1
+    bb = _f64(b)
+    assert bb.shape == (n,)
+    xy = None if coords_2xn is None else _f64(np.asarray(coords_2xn, dtype=np.float64).T.copy())  # (n, 2): x0 y0 x1 y1 ...
+    x = np.zeros(n)
+    lnz = C.c_int64(0)
+    err = C.create_string_buffer(256)
+    rc = lib.asgfem_host_factor_solve(n, _ptr(ip), _ptr(ix), _ptr(dv), _ptr(mask), None if xy is None else _ptr(xy), _ptr(bb),
+                                      _ptr(x), C.addressof(lnz), C.addressof(err), 256)
+    if rc:
+        raise _lib.AsgfemError(rc, err.value.decode() or "asgfem_host_factor_solve")
+    return x, lnz.value
+
+
 def add_boundary_modes(multi_indices, p_extension=1, tail_extension=(10, 2)):
     lib = _lib.load()
     mi = _i64(np.asarray(multi_indices))

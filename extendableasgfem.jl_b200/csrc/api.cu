@@ -771,6 +771,40 @@ extern "C" int asgfem_precond_setup(asgfem_ctx* ctx) {
     return precond_setup(ctx);
 }
 
+extern "C" int asgfem_host_factor_solve(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val,
+                                        const uint8_t* is_boundary, const double* coords, const double* b, double* x,
+                                        int64_t* lnz, char* err, int32_t errlen) {
+    auto fail = [&](int rc, const std::string& msg) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", msg.c_str());
+        return rc;
+    };
+    if (n < 0 || !rowptr || !col || !val || !is_boundary || !b || !x) return fail(ASGFEM_EINVAL, "host_factor_solve: null pointer or negative size");
+    try {
+        CholFactor F;
+        std::string msg;
+        int rc = cholesky_reduced(n, rowptr, col, val, is_boundary, coords, 256, F, msg);
+        if (rc) return fail(rc, msg);
+        std::vector<double> w((size_t)F.n);
+        for (int64_t k = 0; k < F.n; ++k) w[(size_t)k] = b[F.perm[(size_t)k]];
+        for (int64_t k = 0; k < F.n; ++k) {  // L w = b
+            double v = w[(size_t)k];
+            for (int64_t p = F.Lp[(size_t)k]; p < F.Lp[(size_t)k + 1]; ++p) v -= F.Lx[(size_t)p] * w[(size_t)F.Li[(size_t)p]];
+            w[(size_t)k] = v * F.dinv[(size_t)k];
+        }
+        for (int64_t k = F.n - 1; k >= 0; --k) {  // L^T x = w
+            const double v = w[(size_t)k] * F.dinv[(size_t)k];
+            w[(size_t)k] = v;
+            for (int64_t p = F.Lp[(size_t)k]; p < F.Lp[(size_t)k + 1]; ++p) w[(size_t)F.Li[(size_t)p]] -= F.Lx[(size_t)p] * v;
+        }
+        for (int64_t i = 0; i < n; ++i) x[i] = 0.0;
+        for (int64_t k = 0; k < F.n; ++k) x[F.perm[(size_t)k]] = w[(size_t)k];
+        if (lnz) *lnz = (int64_t)F.Li.size();
+    } catch (const std::exception& e) {
+        return fail(ASGFEM_ENOMEM, std::string("host_factor_solve: ") + e.what());
+    }
+    return 0;
+}
+
 extern "C" int asgfem_precond_apply(asgfem_ctx* ctx, int32_t sr, int32_t sz) {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, sr) || check_slot(ctx, sz)) return ASGFEM_EINVAL;

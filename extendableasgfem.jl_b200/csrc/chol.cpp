@@ -6,7 +6,10 @@
 // factorised as P K P^T = L L^T once per refinement level:
 //   1. fill-reducing ordering: graph nested dissection with BFS level-set separators (no METIS in the image),
 //   2. elimination tree + column counts by row-subtree traversal,
-//   3. up-looking numeric factorisation.
+//   3. numeric factorisation: multifrontal over the dissection tree (every leaf / separator is one relaxed supernode
+//      whose frontal matrix is factorised by the blocked dense kernels of dense_chol.cpp; subtrees in parallel at the
+//      bottom of the tree, threaded dense kernels at the top).  ASGFEM_CHOL_UPLOOKING=1 selects the scalar
+//      up-looking sweep it replaced (kept as the cross-check of tools/chol_bench.cpp).
 // The factor is returned row-wise (strictly lower part + inverse diagonal) for the device triangular solves.
 #include <algorithm>
 #include <cmath>
@@ -20,6 +23,7 @@
 #include <thread>
 
 #include "common.h"
+#include "dense_chol.h"
 
 namespace asgfem {
 
@@ -233,6 +237,187 @@ struct CholTick {
 };
 }  // namespace
 
+namespace {
+
+// One node of the dissection tree = one relaxed supernode: columns [lo, hi) of the elimination order, treated as dense.
+struct Front {
+    int32_t lo, hi;
+    int32_t parent = -1;            // front that holds the smallest row of `rows`
+    std::vector<int32_t> rows;      // rows k >= hi with L[k, j] != 0 for some column j of the front (sorted)
+    std::vector<int32_t> children;
+    std::vector<double> update;     // Schur complement on `rows` (rows.size()^2, column-major lower triangle)
+    double work = 0.0, subtree = 0.0;
+};
+
+// Multifrontal numeric phase.  C = P A P^T by columns of its upper triangle (Cp, Ci, Cx); F.Lp / F.Li hold the exact,
+// column-sorted row patterns of L and F.Lx / F.dinv receive the values.  Every front assembles the entries of A in its
+// columns plus the update matrices of its children (extend-add through the global-row -> front-row map), factorises its
+// columns with dense_partial_cholesky and leaves its own update matrix for the parent.  Entries of the dense front that
+// are structurally zero in L stay exactly zero and are simply not copied out.
+int32_t multifrontal_numeric(int32_t n, const std::vector<int64_t>& Cp, const std::vector<int32_t>& Ci, const std::vector<double>& Cx,
+                             std::vector<Front>& fronts, CholFactor& F, DensePool* pool) {
+    const int nthreads = dense_pool_threads(pool);
+    const int slack = dense_front_slack();
+    // strict lower triangle by columns (= transpose of the strict upper triangle held in C) and the diagonal
+    std::vector<int64_t> Tp((size_t)n + 1, 0);
+    std::vector<double> diag((size_t)n, 0.0);
+    for (int32_t k = 0; k < n; ++k)
+        for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p)
+            if (Ci[p] < k) Tp[(size_t)Ci[p] + 1]++;
+    for (int32_t k = 0; k < n; ++k) Tp[(size_t)k + 1] += Tp[(size_t)k];
+    std::vector<int32_t> Ti((size_t)Tp[(size_t)n]);
+    std::vector<double> Tx((size_t)Tp[(size_t)n]);
+    {
+        std::vector<int64_t> at(Tp.begin(), Tp.end() - 1);
+        for (int32_t k = 0; k < n; ++k)
+            for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+                if (Ci[p] == k) {
+                    diag[(size_t)k] += Cx[p];
+                } else if (Ci[p] < k) {
+                    const int64_t q = at[(size_t)Ci[p]]++;
+                    Ti[(size_t)q] = k;
+                    Tx[(size_t)q] = Cx[p];
+                }
+            }
+    }
+    struct Scratch {
+        std::vector<double> front, pack, diag0;
+        std::vector<int32_t> pos, idx;
+    };
+    std::vector<Scratch> scratch((size_t)nthreads);
+    for (Scratch& sc : scratch) sc.pos.assign((size_t)n, 0);
+    std::atomic<int32_t> bad_pivot{-1};
+
+    auto process = [&](int32_t t, int th, DensePool* pl) {
+        Front& fr = fronts[(size_t)t];
+        Scratch& sc = scratch[(size_t)th];
+        const int32_t s = fr.hi - fr.lo, r = (int32_t)fr.rows.size(), m = s + r;
+        int64_t ld = ((int64_t)m + slack + 7) / 8 * 8;
+        if (ld % 512 == 0) ld += 8;  // keep the columns of big fronts off the same cache sets
+        const size_t need = (size_t)ld * (size_t)(m + slack);
+        if (sc.front.size() < need) sc.front.resize(need);
+        const int64_t npack = dense_pack_size(m, s);
+        if ((int64_t)sc.pack.size() < npack) sc.pack.resize((size_t)npack);
+        double* a = sc.front.data();
+        int32_t* pos = sc.pos.data();
+        for (int32_t i = 0; i < s; ++i) pos[fr.lo + i] = i;
+        for (int32_t i = 0; i < r; ++i) pos[fr.rows[(size_t)i]] = s + i;
+        // zero + entries of A, by columns
+        const int32_t cchunk = 64, ncchunk = (m + cchunk - 1) / cchunk;
+        auto init = [&](int, int c) {
+            const int32_t c0 = c * cchunk, c1 = std::min(m, c0 + cchunk);
+            std::memset(a + (int64_t)c0 * ld, 0, sizeof(double) * (size_t)ld * (size_t)(c1 - c0));
+            for (int32_t j = c0; j < std::min(c1, s); ++j) {
+                double* col = a + (int64_t)j * ld;
+                col[j] = diag[(size_t)(fr.lo + j)];
+                for (int64_t p = Tp[(size_t)(fr.lo + j)]; p < Tp[(size_t)(fr.lo + j) + 1]; ++p) col[pos[Ti[(size_t)p]]] += Tx[(size_t)p];
+            }
+        };
+        if (pl && m >= 512)
+            dense_pool_run(pl, ncchunk, init);
+        else
+            for (int32_t c = 0; c < ncchunk; ++c) init(0, c);
+        // extend-add of the children
+        for (int32_t ch : fr.children) {
+            Front& cf = fronts[(size_t)ch];
+            const int32_t rc = (int32_t)cf.rows.size();
+            if (rc == 0) continue;
+            if ((int32_t)sc.idx.size() < rc) sc.idx.resize((size_t)rc);
+            int32_t* idx = sc.idx.data();
+            for (int32_t i = 0; i < rc; ++i) idx[i] = pos[cf.rows[(size_t)i]];
+            const double* u = cf.update.data();
+            auto add = [&](int, int c) {
+                const int32_t b0 = c * cchunk, b1 = std::min(rc, b0 + cchunk);
+                for (int32_t b = b0; b < b1; ++b) {
+                    double* col = a + (int64_t)idx[b] * ld;
+                    const double* ub = u + (int64_t)b * rc;
+                    for (int32_t i = b; i < rc; ++i) col[idx[i]] += ub[i];
+                }
+            };
+            const int32_t nadd = (rc + cchunk - 1) / cchunk;
+            if (pl && rc >= 512)
+                dense_pool_run(pl, nadd, add);
+            else
+                for (int32_t c = 0; c < nadd; ++c) add(0, c);
+            std::vector<double>().swap(cf.update);
+        }
+        if ((int32_t)sc.diag0.size() < s) sc.diag0.resize((size_t)s);
+        for (int32_t i = 0; i < s; ++i) sc.diag0[(size_t)i] = std::fabs(diag[(size_t)(fr.lo + i)]);
+        const int bad = dense_partial_cholesky(a, m, s, ld, sc.diag0.data(), pl, sc.pack.data());
+        if (bad >= 0) {
+            int32_t expect = -1;
+            bad_pivot.compare_exchange_strong(expect, fr.lo + bad);
+        }
+        // values of L in the (exact) row patterns; the update matrix for the parent
+        if (r > 0) fr.update.resize((size_t)r * (size_t)r);
+        double* u = fr.update.data();
+        const int32_t rchunk = 64, nrchunk = (m + rchunk - 1) / rchunk;
+        auto extract = [&](int, int c) {
+            const int32_t i0 = c * rchunk, i1 = std::min(m, i0 + rchunk);
+            for (int32_t i = i0; i < i1; ++i) {
+                if (i < s) {
+                    const int32_t k = fr.lo + i;
+                    F.dinv[(size_t)k] = 1.0 / a[i + (int64_t)i * ld];
+                    for (int64_t p = F.Lp[(size_t)k + 1] - 1; p >= F.Lp[(size_t)k] && F.Li[(size_t)p] >= fr.lo; --p)
+                        F.Lx[(size_t)p] = a[i + (int64_t)(F.Li[(size_t)p] - fr.lo) * ld];
+                } else {
+                    const int32_t k = fr.rows[(size_t)(i - s)];
+                    const int32_t* b = F.Li.data() + F.Lp[(size_t)k];
+                    const int32_t* e = F.Li.data() + F.Lp[(size_t)k + 1];
+                    for (const int32_t* q = std::lower_bound(b, e, fr.lo); q < e && *q < fr.hi; ++q)
+                        F.Lx[(size_t)(q - F.Li.data())] = a[i + (int64_t)(*q - fr.lo) * ld];
+                    const int32_t bcol = i - s;  // column bcol of the update matrix: rows bcol..r-1
+                    std::memcpy(u + (int64_t)bcol * r + bcol, a + i + (int64_t)i * ld, sizeof(double) * (size_t)(r - bcol));
+                }
+            }
+        };
+        if (pl && m >= 512)
+            dense_pool_run(pl, nrchunk, extract);
+        else
+            for (int32_t c = 0; c < nrchunk; ++c) extract(0, c);
+    };
+
+    // subtrees below the work threshold go to one thread each; what remains on top runs front by front, threaded inside
+    const int32_t nf = (int32_t)fronts.size();
+    double total = 0.0;
+    for (int32_t t = 0; t < nf; ++t) {
+        Front& fr = fronts[(size_t)t];
+        const double s = fr.hi - fr.lo, m = s + (double)fr.rows.size();
+        fr.work = s * m * m - s * s * m + s * s * s / 3.0 + 50.0 * m;
+        fr.subtree += fr.work;
+        if (fr.parent >= 0) fronts[(size_t)fr.parent].subtree += fr.subtree;
+        total += fr.work;
+    }
+    double div = 8.0;
+    if (const char* e = std::getenv("ASGFEM_CHOL_SPLIT")) div = std::max(0.25, atof(e));
+    const double thresh = nthreads > 1 ? total / (div * nthreads) : 2.0 * total;
+    std::vector<int32_t> group((size_t)nf, -1), roots;
+    for (int32_t t = nf - 1; t >= 0; --t) {
+        const Front& fr = fronts[(size_t)t];
+        if (fr.subtree > thresh) continue;  // top
+        if (fr.parent < 0 || group[(size_t)fr.parent] < 0) {
+            group[(size_t)t] = (int32_t)roots.size();
+            roots.push_back(t);
+        } else {
+            group[(size_t)t] = group[(size_t)fr.parent];
+        }
+    }
+    std::vector<std::vector<int32_t>> members(roots.size());
+    for (int32_t t = 0; t < nf; ++t)
+        if (group[(size_t)t] >= 0) members[(size_t)group[(size_t)t]].push_back(t);
+    std::vector<int32_t> order(roots.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return fronts[(size_t)roots[(size_t)x]].subtree > fronts[(size_t)roots[(size_t)y]].subtree; });
+    dense_pool_run(pool, (int)order.size(), [&](int th, int g) {
+        for (int32_t t : members[(size_t)order[(size_t)g]]) process(t, th, nullptr);
+    });
+    for (int32_t t = 0; t < nf; ++t)
+        if (group[(size_t)t] < 0) process(t, 0, pool);
+    return bad_pivot.load();
+}
+
+}  // namespace
+
 int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,
                      const uint8_t* is_boundary, const double* coords_full, int32_t max_block, CholFactor& F,
                      std::string& err) {
@@ -360,6 +545,153 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
             while (len > 0) stack[--top] = stack[--len];
         }
     };
+    const bool uplooking = std::getenv("ASGFEM_CHOL_UPLOOKING") != nullptr;
+    if (!uplooking) {
+        // fronts of the multifrontal phase: the nodes of the dissection tree (chunks of one separator joined again)
+        std::vector<Front> fronts;
+        for (const BlockRec& b : F.blocks) {
+            if (!fronts.empty() && b.chunk > 0 && fronts.back().hi == b.start)
+                fronts.back().hi = b.start + b.len;
+            else {
+                fronts.emplace_back();
+                fronts.back().lo = b.start;
+                fronts.back().hi = b.start + b.len;
+            }
+        }
+        std::vector<int32_t> frontof((size_t)n);
+        for (int32_t t = 0; t < (int32_t)fronts.size(); ++t)
+            for (int32_t k = fronts[(size_t)t].lo; k < fronts[(size_t)t].hi; ++k) frontof[(size_t)k] = t;
+        int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+        if (const char* e = std::getenv("ASGFEM_CHOL_THREADS")) nthreads = std::max(1, atoi(e));
+        if (n < 20000) nthreads = 1;
+        chol_tick("fronts");
+        DensePool* pool = dense_pool_create(nthreads);
+        struct PoolGuard {
+            DensePool* p;
+            ~PoolGuard() { dense_pool_destroy(p); }
+        } pool_guard{pool};
+        // Row patterns by row-subtree traversal, in parallel over chunks of rows.  The pattern of row k is the union of
+        // the tree paths that start at the entries of row k of A; every path ascends, so the pattern is sorted by merging
+        // these runs.  Pass 1 counts and records which fronts a row belongs to, pass 2 writes the sorted patterns.
+        struct Sym {
+            std::vector<int32_t> flag, stack, tmp, seen;
+            std::vector<int32_t> runs;
+        };
+        std::vector<Sym> sym((size_t)nthreads);
+        const int32_t nchunk = (int32_t)std::min<int64_t>(n, 8 * (int64_t)nthreads);
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> member((size_t)nchunk);  // (front, row) per chunk, rows ascending
+        auto row_pattern = [&](Sym& w, int32_t k, int32_t tag) -> int32_t {  // unsorted pattern in w.stack, run starts in w.runs
+            int32_t* fl = w.flag.data();
+            int32_t* st = w.stack.data();
+            int32_t len = 0;
+            w.runs.clear();
+            fl[k] = tag;
+            for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+                const int32_t before = len;
+                for (int32_t i = Ci[p]; i < k && fl[i] != tag; i = parent[i]) {
+                    st[len++] = i;
+                    fl[i] = tag;
+                }
+                if (len > before) w.runs.push_back(before);
+            }
+            return len;
+        };
+        auto sym_init = [&](Sym& w) {
+            if (w.flag.empty()) {
+                w.flag.assign((size_t)n, -1);
+                w.stack.resize((size_t)n);
+                w.tmp.resize((size_t)n);
+                w.seen.assign(fronts.size(), -1);
+            }
+        };
+        dense_pool_run(pool, nchunk, [&](int th, int c) {
+            Sym& w = sym[(size_t)th];
+            sym_init(w);
+            const int32_t k0 = (int32_t)((int64_t)n * c / nchunk), k1 = (int32_t)((int64_t)n * (c + 1) / nchunk);
+            for (int32_t k = k0; k < k1; ++k) {
+                const int32_t len = row_pattern(w, k, k);
+                rowlen[k] = len;
+                const int32_t own = frontof[(size_t)k];
+                for (int32_t q = 0; q < len; ++q) {
+                    const int32_t t = frontof[(size_t)w.stack[(size_t)q]];
+                    if (t != own && w.seen[(size_t)t] != k) {
+                        w.seen[(size_t)t] = k;
+                        member[(size_t)c].push_back({t, k});
+                    }
+                }
+            }
+        });
+        chol_tick("symbolic (row counts, parallel part)");
+        for (int32_t c = 0; c < nchunk; ++c) {
+            for (const std::pair<int32_t, int32_t>& tk : member[(size_t)c]) fronts[(size_t)tk.first].rows.push_back(tk.second);
+            std::vector<std::pair<int32_t, int32_t>>().swap(member[(size_t)c]);
+        }
+        chol_tick("symbolic (row counts)");
+        int64_t lnz = 0;
+        try {
+            F.Lp.assign((size_t)n + 1, 0);
+            for (int32_t k = 0; k < n; ++k) F.Lp[k + 1] = F.Lp[k] + rowlen[k];
+            lnz = F.Lp[(size_t)n];
+            F.Li.resize((size_t)lnz);  // not value-initialised: first touched by the threads that fill them
+            F.Lx.resize((size_t)lnz);
+            F.dinv.resize((size_t)n);
+        } catch (const std::bad_alloc&) {
+            err = "out of host memory for the Cholesky factor";
+            return ASGFEM_ENOMEM;
+        }
+        // parent = the front of the smallest outside row; the rows of a front must be covered by its parent (columns
+        // or rows), which holds for dissection orderings and is enforced here for anything else (explicit zeros)
+        std::vector<int32_t> merged;
+        for (int32_t t = 0; t < (int32_t)fronts.size(); ++t) {
+            Front& fr = fronts[(size_t)t];
+            if (fr.rows.empty()) continue;
+            fr.parent = frontof[(size_t)fr.rows[0]];
+            Front& pf = fronts[(size_t)fr.parent];
+            pf.children.push_back(t);
+            auto first_out = std::lower_bound(fr.rows.begin(), fr.rows.end(), pf.hi);
+            if (!std::includes(pf.rows.begin(), pf.rows.end(), first_out, fr.rows.end())) {
+                merged.clear();
+                std::set_union(pf.rows.begin(), pf.rows.end(), first_out, fr.rows.end(), std::back_inserter(merged));
+                pf.rows = merged;
+            }
+        }
+        chol_tick("front tree");
+        dense_pool_run(pool, nchunk, [&](int th, int c) {
+            Sym& w = sym[(size_t)th];
+            sym_init(w);
+            const int32_t k0 = (int32_t)((int64_t)n * c / nchunk), k1 = (int32_t)((int64_t)n * (c + 1) / nchunk);
+            for (int32_t k = k0; k < k1; ++k) {
+                const int32_t len = row_pattern(w, k, n + k);  // tags distinct from those of pass 1
+                // merge the ascending runs pairwise until one is left
+                int32_t* src = w.stack.data();
+                int32_t* dst = w.tmp.data();
+                std::vector<int32_t>& runs = w.runs;
+                runs.push_back(len);
+                while (runs.size() > 2) {
+                    size_t nr = 0;
+                    for (size_t q = 0; q + 1 < runs.size(); q += 2) {
+                        const int32_t a0 = runs[q], a1 = runs[q + 1], b1 = q + 2 < runs.size() ? runs[q + 2] : a1;
+                        std::merge(src + a0, src + a1, src + a1, src + b1, dst + a0);
+                        runs[nr++] = a0;
+                    }
+                    runs[nr++] = len;
+                    runs.resize(nr);
+                    std::swap(src, dst);
+                }
+                std::copy(src, src + len, F.Li.begin() + F.Lp[k]);
+            }
+        });
+        chol_tick("symbolic (row patterns)");
+        const int32_t bad = multifrontal_numeric(n, Cp, Ci, Cx, fronts, F, pool);
+        chol_tick("numeric (multifrontal)");
+        if (bad >= 0) {
+            err = "K_0 restricted to the interior dofs is not positive definite (pivot " + std::to_string(bad) + ")";
+            return ASGFEM_ENUMERIC;
+        }
+        F.perm.resize((size_t)n);
+        for (int32_t k = 0; k < n; ++k) F.perm[k] = full[perm[k]];
+        return 0;
+    }
     int64_t lnz = 0;
     for (int32_t k = 0; k < n; ++k) {
         int32_t top;

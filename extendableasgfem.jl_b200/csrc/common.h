@@ -42,12 +42,31 @@ struct BlockRec {
     int32_t depth;          // depth of the owning node in the dissection tree (same depth => independent)
     int32_t chunk, nchunks;  // long separators are cut into sequentially dependent chunks
 };
+// std::vector whose resize() leaves new elements uninitialised: the big factor arrays are first touched by the threads
+// that fill them instead of being zeroed serially
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = DefaultInitAlloc<U>;
+    };
+    template <class U, class... Args>
+    void construct(U* p, Args&&... args) {
+        if constexpr (sizeof...(Args) == 0)
+            ::new ((void*)p) U;
+        else
+            ::new ((void*)p) U(std::forward<Args>(args)...);
+    }
+};
+template <class T>
+using RawVec = std::vector<T, DefaultInitAlloc<T>>;
+
 struct CholFactor {
     int64_t n = 0;                 // reduced dimension
     std::vector<int32_t> perm;     // perm[k] = original (full) row id of the k-th eliminated unknown
     std::vector<int64_t> Lp;       // CSR of L (strictly lower part), rows in elimination order
-    std::vector<int32_t> Li;
-    std::vector<double> Lx;
+    RawVec<int32_t> Li;
+    RawVec<double> Lx;
     std::vector<double> dinv;      // 1 / L_kk
     std::vector<BlockRec> blocks;  // leaves and separators of the dissection tree, sorted by start
 };

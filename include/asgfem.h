@@ -156,6 +156,13 @@ int asgfem_last_estimate_ms(asgfem_ctx* ctx, double* ms);
 int asgfem_precond_setup(asgfem_ctx* ctx);
 int asgfem_precond_apply(asgfem_ctx* ctx, int32_t slot_r, int32_t slot_z);
 int asgfem_precond_apply_host(asgfem_ctx* ctx, const double* b, double* y);
+/* Host-only diagnostic of the factorisation behind asgfem_precond_setup (no context, no GPU): K (n x n CSR, 0-based,
+ * symmetric, both triangles stored) is reduced by the rows/columns with is_boundary != 0, factorised exactly as the setup
+ * does (nested dissection steered by coords[2 n] if not NULL, multifrontal Cholesky on the host cores) and
+ * K_red x = b is solved for one vector; boundary rows of x are 0 like the preconditioner's.  *lnz = nonzeros of the strict
+ * lower triangle of the factor.  Returns 0 or ASGFEM_E*; err (may be NULL) receives the message. */
+int asgfem_host_factor_solve(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, const uint8_t* is_boundary,
+                             const double* coords, const double* b, double* x, int64_t* lnz, char* err, int32_t errlen);
 
 /* ---- (a9) Krylov driver -------------------------------------------------------------------------
  * solve_primal! (solvers_poisson_primal.jl:130-169) with PCG in place of Krylov.gmres:
