@@ -64,16 +64,17 @@ int32_t bfs(const Graph& g, int32_t start, const std::vector<int32_t>& tag, int3
     return (int32_t)out.size();
 }
 
-// nested dissection ordering; returns perm (elimination order -> node)
+// nested dissection ordering; returns perm (elimination order -> node).  The tree is built level by level with the
+// subdomains of a level in parallel (they own disjoint node sets and disjoint ranges of perm).
 void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double* xy, std::vector<BlockRec>& blocks,
-                       int32_t max_block) {
+                       int32_t max_block, DensePool* pool) {
     const int32_t n = g.n;
     // dissection stops at subdomains of <= LEAF unknowns (dense leaf blocks of the triangular sweeps); measured at config 4
     // (sptrsv.cu, DMMA sweeps): see DESIGN.md section 5
     int32_t LEAF = 24;
     if (const char* e = std::getenv("ASGFEM_CHOL_LEAF")) LEAF = std::max(4, atoi(e));
     perm.assign((size_t)n, -1);
-    std::vector<int32_t> tag((size_t)n, 0), dist((size_t)n, -1), bfsout, lv, tmp;
+    std::vector<int32_t> tag((size_t)n, 0), dist((size_t)n, -1);
     struct Task {
         std::vector<int32_t> nodes;
         int32_t lo;     // this set occupies perm[lo, lo + nodes.size())
@@ -82,33 +83,39 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
     // blocks for the tree-parallel triangular solves: every leaf and every separator of the dissection tree is a
     // block (separators longer than max_block are cut into sequentially dependent chunks)
     blocks.clear();
-    auto emit_range = [&](int32_t lo, int32_t len, int32_t depth) {
-        if (len <= 0) return;
-        int32_t nch = (len + max_block - 1) / max_block;
-        for (int32_t c = 0; c < nch; ++c)
-            blocks.push_back({lo + c * max_block, std::min(max_block, len - c * max_block), depth, c, nch});
+    struct Scratch {
+        std::vector<int32_t> bfsout, lv, tmp;
+        std::vector<BlockRec> blocks;
+        std::vector<Task> out;
     };
-    std::vector<Task> stack;
+    std::vector<Scratch> scratch((size_t)dense_pool_threads(pool));
+    std::vector<Task> frontier;
     {
         Task t;
         t.nodes.resize((size_t)n);
         std::iota(t.nodes.begin(), t.nodes.end(), 0);
         t.lo = 0;
         t.depth = 0;
-        stack.push_back(std::move(t));
+        frontier.push_back(std::move(t));
     }
-    int32_t next_id = 1;
-    while (!stack.empty()) {
-        Task t = std::move(stack.back());
-        stack.pop_back();
+    std::atomic<int32_t> next_id{1};
+    auto process = [&](Task& t, Scratch& sc) {
+        std::vector<int32_t>&bfsout = sc.bfsout, &lv = sc.lv, &tmp = sc.tmp;
+        std::vector<Task>& stack = sc.out;
+        auto emit_range = [&](int32_t lo, int32_t len, int32_t depth) {
+            if (len <= 0) return;
+            int32_t nch = (len + max_block - 1) / max_block;
+            for (int32_t c = 0; c < nch; ++c)
+                sc.blocks.push_back({lo + c * max_block, std::min(max_block, len - c * max_block), depth, c, nch});
+        };
         const int32_t sz = (int32_t)t.nodes.size();
-        if (sz == 0) continue;
+        if (sz == 0) return;
         if (sz <= LEAF) {
             for (int32_t k = 0; k < sz; ++k) perm[t.lo + k] = t.nodes[k];
             emit_range(t.lo, sz, t.depth);
-            continue;
+            return;
         }
-        const int32_t id = next_id++;
+        const int32_t id = next_id.fetch_add(1);
         for (int32_t v : t.nodes) {
             tag[v] = id;
             dist[v] = -1;
@@ -161,7 +168,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
                         emit_range(seplo, (int32_t)sep.size(), t.depth);
                         stack.push_back(std::move(a));
                         stack.push_back(std::move(b));
-                        continue;
+                        return;
                     }
                     // the two sides are not connected: fall through to the component split below
                 }
@@ -181,7 +188,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
             a.depth = b.depth = t.depth + 1;
             stack.push_back(std::move(a));
             stack.push_back(std::move(b));
-            continue;
+            return;
         }
         // pseudo-peripheral start: two more sweeps from the farthest node
         for (int sweep = 0; sweep < 2; ++sweep) {
@@ -193,7 +200,7 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
         if (nlev < 3) {  // (nearly) complete graph: no useful separator
             for (int32_t k = 0; k < sz; ++k) perm[t.lo + k] = t.nodes[k];
             emit_range(t.lo, sz, t.depth);
-            continue;
+            return;
         }
         // separator = the level whose removal balances the two sides best
         int32_t best = 1;
@@ -218,7 +225,18 @@ void nested_dissection(const Graph& g, std::vector<int32_t>& perm, const double*
         emit_range(seplo, nsep, t.depth);
         stack.push_back(std::move(a));
         stack.push_back(std::move(b));
+    };
+    while (!frontier.empty()) {
+        dense_pool_run(pool, (int)frontier.size(), [&](int th, int i) { process(frontier[(size_t)i], scratch[(size_t)th]); });
+        frontier.clear();
+        for (Scratch& sc : scratch) {
+            for (Task& t : sc.out) frontier.push_back(std::move(t));
+            sc.out.clear();
+        }
+        // big subdomains first: the pool hands tasks out in order
+        std::sort(frontier.begin(), frontier.end(), [](const Task& x, const Task& y) { return x.nodes.size() > y.nodes.size(); });
     }
+    for (Scratch& sc : scratch) blocks.insert(blocks.end(), sc.blocks.begin(), sc.blocks.end());
     std::sort(blocks.begin(), blocks.end(), [](const BlockRec& x, const BlockRec& y) { return x.start < y.start; });
 }
 
@@ -436,23 +454,45 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
     F.Li.clear();
     F.Lx.clear();
     F.dinv.clear();
+    F.node_lo.clear(), F.node_hi.clear(), F.node_rows.clear();
+    F.node_rptr.assign(1, 0);
     if (n == 0) return 0;
 
+    int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (const char* e = std::getenv("ASGFEM_CHOL_THREADS")) nthreads = std::max(1, atoi(e));
+    if (n < 20000) nthreads = 1;
+    DensePool* pool = dense_pool_create(nthreads);
+    struct PoolGuard {
+        DensePool* p;
+        ~PoolGuard() { dense_pool_destroy(p); }
+    } pool_guard{pool};
+
+    // loops over the rows of a matrix, in parallel over chunks of rows
+    auto for_rows = [&](int32_t nrows, const std::function<void(int32_t, int32_t)>& body) {
+        const int32_t nchunk = (int32_t)std::min<int64_t>(std::max<int32_t>(nrows, 1), 8 * (int64_t)nthreads);
+        dense_pool_run(pool, nchunk, [&](int, int c) {
+            body((int32_t)((int64_t)nrows * c / nchunk), (int32_t)((int64_t)nrows * (c + 1) / nchunk));
+        });
+    };
     Graph g;
     g.n = n;
     g.ptr.assign((size_t)n + 1, 0);
-    for (int32_t r = 0; r < n; ++r) {
-        int64_t i = full[r];
-        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
-            if (red[col[p]] >= 0 && col[p] != i) g.ptr[r + 1]++;
-    }
+    for_rows(n, [&](int32_t r0, int32_t r1) {
+        for (int32_t r = r0; r < r1; ++r) {
+            int64_t i = full[r], cnt = 0;
+            for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) cnt += red[col[p]] >= 0 && col[p] != i;
+            g.ptr[r + 1] = cnt;
+        }
+    });
     for (int32_t r = 0; r < n; ++r) g.ptr[r + 1] += g.ptr[r];
     g.adj.resize((size_t)g.ptr[n]);
-    for (int32_t r = 0; r < n; ++r) {
-        int64_t i = full[r], q = g.ptr[r];
-        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
-            if (red[col[p]] >= 0 && col[p] != i) g.adj[q++] = red[col[p]];
-    }
+    for_rows(n, [&](int32_t r0, int32_t r1) {
+        for (int32_t r = r0; r < r1; ++r) {
+            int64_t i = full[r], q = g.ptr[r];
+            for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
+                if (red[col[p]] >= 0 && col[p] != i) g.adj[q++] = red[col[p]];
+        }
+    });
 
     std::vector<int32_t> perm;
     std::vector<double> xy;
@@ -464,7 +504,7 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         }
     }
     chol_tick("graph");
-    nested_dissection(g, perm, coords_full ? xy.data() : nullptr, F.blocks, max_block);
+    nested_dissection(g, perm, coords_full ? xy.data() : nullptr, F.blocks, max_block, pool);
     chol_tick("nested dissection");
     {
         int32_t at = 0;
@@ -491,27 +531,32 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
 
     // ---- permuted upper triangle by columns: C = P A P^T, column k holds rows i <= k ----------------
     std::vector<int64_t> Cp((size_t)n + 1, 0);
-    for (int32_t k = 0; k < n; ++k) {
-        int64_t i = full[perm[k]];
-        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
-            int32_t rj = red[col[p]];
-            if (rj >= 0 && iperm[rj] <= k) Cp[k + 1]++;
+    for_rows(n, [&](int32_t k0, int32_t k1) {
+        for (int32_t k = k0; k < k1; ++k) {
+            int64_t i = full[perm[k]], cnt = 0;
+            for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+                int32_t rj = red[col[p]];
+                cnt += rj >= 0 && iperm[rj] <= k;
+            }
+            Cp[k + 1] = cnt;
         }
-    }
+    });
     for (int32_t k = 0; k < n; ++k) Cp[k + 1] += Cp[k];
     std::vector<int32_t> Ci((size_t)Cp[n]);
     std::vector<double> Cx((size_t)Cp[n]);
-    for (int32_t k = 0; k < n; ++k) {
-        int64_t i = full[perm[k]], q = Cp[k];
-        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
-            int32_t rj = red[col[p]];
-            if (rj >= 0 && iperm[rj] <= k) {
-                Ci[q] = iperm[rj];
-                Cx[q] = val[p];  // A symmetric: A[i, j] used as C[j', k]
-                ++q;
+    for_rows(n, [&](int32_t k0, int32_t k1) {
+        for (int32_t k = k0; k < k1; ++k) {
+            int64_t i = full[perm[k]], q = Cp[k];
+            for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+                int32_t rj = red[col[p]];
+                if (rj >= 0 && iperm[rj] <= k) {
+                    Ci[q] = iperm[rj];
+                    Cx[q] = val[p];  // A symmetric: A[i, j] used as C[j', k]
+                    ++q;
+                }
             }
         }
-    }
+    });
 
     chol_tick("permuted matrix");
     // ---- elimination tree (Liu) ---------------------------------------------------------------------
@@ -561,15 +606,7 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         std::vector<int32_t> frontof((size_t)n);
         for (int32_t t = 0; t < (int32_t)fronts.size(); ++t)
             for (int32_t k = fronts[(size_t)t].lo; k < fronts[(size_t)t].hi; ++k) frontof[(size_t)k] = t;
-        int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
-        if (const char* e = std::getenv("ASGFEM_CHOL_THREADS")) nthreads = std::max(1, atoi(e));
-        if (n < 20000) nthreads = 1;
         chol_tick("fronts");
-        DensePool* pool = dense_pool_create(nthreads);
-        struct PoolGuard {
-            DensePool* p;
-            ~PoolGuard() { dense_pool_destroy(p); }
-        } pool_guard{pool};
         // Row patterns by row-subtree traversal, in parallel over chunks of rows.  The pattern of row k is the union of
         // the tree paths that start at the entries of row k of A; every path ascends, so the pattern is sorted by merging
         // these runs.  Pass 1 counts and records which fronts a row belongs to, pass 2 writes the sorted patterns.
@@ -604,6 +641,8 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
                 w.seen.assign(fronts.size(), -1);
             }
         };
+        dense_pool_run(pool, nthreads, [&](int th, int) { sym_init(sym[(size_t)th]); });
+        chol_tick("symbolic (scratch)");
         dense_pool_run(pool, nchunk, [&](int th, int c) {
             Sym& w = sym[(size_t)th];
             sym_init(w);
@@ -612,8 +651,12 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
                 const int32_t len = row_pattern(w, k, k);
                 rowlen[k] = len;
                 const int32_t own = frontof[(size_t)k];
+                int32_t cur_lo = fronts[(size_t)own].lo, cur_hi = fronts[(size_t)own].hi;  // columns known to need no lookup
                 for (int32_t q = 0; q < len; ++q) {
-                    const int32_t t = frontof[(size_t)w.stack[(size_t)q]];
+                    const int32_t i = w.stack[(size_t)q];
+                    if (i >= cur_lo && i < cur_hi) continue;  // tree paths ascend: mostly the front of the previous column
+                    const int32_t t = frontof[(size_t)i];
+                    cur_lo = fronts[(size_t)t].lo, cur_hi = fronts[(size_t)t].hi;
                     if (t != own && w.seen[(size_t)t] != k) {
                         w.seen[(size_t)t] = k;
                         member[(size_t)c].push_back({t, k});
@@ -655,6 +698,14 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
                 pf.rows = merged;
             }
         }
+        F.node_lo.clear(), F.node_hi.clear(), F.node_rows.clear();
+        F.node_rptr.assign(1, 0);
+        for (const Front& fr : fronts) {
+            F.node_lo.push_back(fr.lo);
+            F.node_hi.push_back(fr.hi);
+            F.node_rows.insert(F.node_rows.end(), fr.rows.begin(), fr.rows.end());
+            F.node_rptr.push_back((int64_t)F.node_rows.size());
+        }
         chol_tick("front tree");
         dense_pool_run(pool, nchunk, [&](int th, int c) {
             Sym& w = sym[(size_t)th];
@@ -693,12 +744,41 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         return 0;
     }
     int64_t lnz = 0;
-    for (int32_t k = 0; k < n; ++k) {
-        int32_t top;
-        ereach(k, top);
-        rowlen[k] = n - top;
-        lnz += n - top;
-        for (int32_t q = top; q < n; ++q) colcount[stack[q]]++;
+    {
+        F.node_lo.clear(), F.node_hi.clear();
+        for (const BlockRec& b : F.blocks) {
+            if (!F.node_lo.empty() && b.chunk > 0 && F.node_hi.back() == b.start)
+                F.node_hi.back() = b.start + b.len;
+            else {
+                F.node_lo.push_back(b.start);
+                F.node_hi.push_back(b.start + b.len);
+            }
+        }
+        const size_t nn = F.node_lo.size();
+        std::vector<int32_t> nodeof((size_t)n), seen(nn, -1);
+        for (size_t t = 0; t < nn; ++t)
+            for (int32_t k = F.node_lo[t]; k < F.node_hi[t]; ++k) nodeof[(size_t)k] = (int32_t)t;
+        std::vector<std::vector<int32_t>> rows(nn);
+        for (int32_t k = 0; k < n; ++k) {
+            int32_t top;
+            ereach(k, top);
+            rowlen[k] = n - top;
+            lnz += n - top;
+            for (int32_t q = top; q < n; ++q) {
+                colcount[stack[q]]++;
+                const int32_t t = nodeof[(size_t)stack[q]];
+                if (t != nodeof[(size_t)k] && seen[(size_t)t] != k) {
+                    seen[(size_t)t] = k;
+                    rows[(size_t)t].push_back(k);
+                }
+            }
+        }
+        F.node_rows.clear();
+        F.node_rptr.assign(1, 0);
+        for (size_t t = 0; t < nn; ++t) {
+            F.node_rows.insert(F.node_rows.end(), rows[t].begin(), rows[t].end());
+            F.node_rptr.push_back((int64_t)F.node_rows.size());
+        }
     }
     chol_tick("symbolic (row counts)");
     // column storage for the numeric phase (diagonal first), row storage for the output
@@ -736,9 +816,6 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
     }
     std::vector<std::vector<int32_t>> level((size_t)maxdepth + 1);
     for (int32_t t = 0; t < (int32_t)tasks.size(); ++t) level[(size_t)tasks[(size_t)t].depth].push_back(t);
-    int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
-    if (const char* e = std::getenv("ASGFEM_CHOL_THREADS")) nthreads = std::max(1, atoi(e));
-    if (n < 20000) nthreads = 1;
     struct Work {
         std::vector<double> x;
         std::vector<int32_t> flag, stack;

@@ -69,11 +69,20 @@ struct CholFactor {
     RawVec<double> Lx;
     std::vector<double> dinv;      // 1 / L_kk
     std::vector<BlockRec> blocks;  // leaves and separators of the dissection tree, sorted by start
+    // nodes of the dissection tree (= blocks with the chunks of one separator joined): columns [node_lo, node_hi) and the
+    // sorted rows >= node_hi that hold an entry in one of these columns (a superset: rows added to close the tree are
+    // allowed) - lets the sweep-task builder find the rows below a column range without a column copy of L
+    std::vector<int32_t> node_lo, node_hi, node_rows;
+    std::vector<int64_t> node_rptr;
 };
 // A: full n_full x n_full CSR (rowptr int64, col int32), keep[i] != 0 for interior rows. Returns 0 or ASGFEM_E*.
 int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, const double* val,
                      const uint8_t* is_boundary, const double* coords_full, int32_t max_block, CholFactor& F,
                      std::string& err);
+
+// sweep tasks of a factor on the host (sptrsv.cu), for tools/chol_bench.cpp: parallel builder or its serial reference
+void precond_tasks_host(const CholFactor& F, bool serial_reference, std::vector<unsigned char>& blk_bytes, RawVec<unsigned char>& rec,
+                        std::vector<std::array<int, 3>>& launches);
 
 // ---- device-side plans --------------------------------------------------------------------------
 struct PrecondPlan;  // sptrsv.cu
@@ -181,8 +190,8 @@ inline int fail(asgfem_ctx* ctx, int code, const std::string& msg) {
         if (!(cond)) return asgfem::fail((ctx), (code), (msg)); \
     } while (0)
 
-template <class T>
-int dev_upload(asgfem_ctx* ctx, T** dptr, const std::vector<T>& h) {
+template <class T, class Alloc>
+int dev_upload(asgfem_ctx* ctx, T** dptr, const std::vector<T, Alloc>& h) {
     if (*dptr) {
         cudaFree(*dptr);
         *dptr = nullptr;

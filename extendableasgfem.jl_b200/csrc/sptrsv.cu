@@ -28,7 +28,12 @@
 #include <algorithm>
 #include <array>
 
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
 #include "common.h"
+#include "dense_chol.h"
 
 namespace asgfem {
 
@@ -520,18 +525,209 @@ void launch_small(const std::array<int, 3>& L, int tiles, int split, cudaStream_
 }
 
 // Cuts the blocks of the dissection tree into sub-blocks of <= SMALL_W columns and builds their tasks (records with the
-// inverse triangle and the dense panel) in launch order.  Lp/Li/Lx: rows of L; cptr/cidx/cval: columns of L with
-// ascending rows.
-int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx,
-                const std::vector<double>& cval, SmallDev& D, std::vector<std::array<int, 3>>& launches, int64_t* rec_bytes) {
+// inverse triangle and the dense panel) in launch order, on the host cores: pass A finds the rows below every sub-block
+// that its columns touch (candidates = the later rows of its tree node and the node's outside rows, F.node_rows; a
+// candidate counts if its sorted row of L has an entry in the column range), a serial sweep lays the records out, pass B
+// fills them.  Both passes run over the sub-blocks in parallel; no column copy of L is needed.
+void build_tasks_host(const CholFactor& F, std::vector<SmallBlk>& blk, RawVec<unsigned char>& rec,
+                      std::vector<std::array<int, 3>>& launches) {
+    struct Sub {
+        int32_t j0, w, node, wcl;
+        int64_t base_key;
+        int32_t first_task, ntask;
+    };
+    struct Task {
+        SmallBlk blk;
+        int64_t key;  // launch order
+        int wclass;
+        int32_t a_lo;  // first panel row of this task in the row list of its sub-block
+    };
+    auto wclass_of = [](int w) { return w <= 8 ? 8 : (w <= 16 ? 16 : (w <= 24 ? 24 : 32)); };
+    int maxdepth = 0;
+    for (const BlockRec& b : F.blocks) maxdepth = std::max(maxdepth, b.depth);
+    std::vector<Sub> subs;
+    {
+        int32_t node = 0;
+        for (const BlockRec& B : F.blocks) {
+            while (node + 1 < (int32_t)F.node_lo.size() && B.start >= F.node_hi[(size_t)node]) ++node;
+            const int nsub = (B.len + SMALL_W - 1) / SMALL_W;
+            for (int sub = 0; sub < nsub; ++sub) {
+                Sub s;
+                s.j0 = B.start + sub * SMALL_W;
+                s.w = std::min(SMALL_W, B.start + B.len - s.j0);
+                s.node = node;
+                // the top of the tree (few, long separators: a chain of small dependent launches) uses the 32-column kernel
+                // for all widths, so that its launches can be merged into one kernel; below, a sub-block keeps its width class
+                s.wcl = B.depth <= TOP_DEPTH ? 32 : wclass_of(s.w);
+                // launch key: deepest level first; chunks of a separator and sub-blocks of a chunk in order; solve before push
+                s.base_key = ((((int64_t)(maxdepth - B.depth) * 4096 + B.chunk) * 16 + sub) * 2);
+                s.first_task = s.ntask = 0;
+                subs.push_back(s);
+            }
+        }
+    }
+    const int32_t nsubs = (int32_t)subs.size();
+    int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (const char* e = std::getenv("ASGFEM_CHOL_THREADS")) nthreads = std::max(1, atoi(e));
+    if (F.n < 20000) nthreads = 1;
+    DensePool* pool = dense_pool_create(nthreads);
+    const int32_t grain = 16, njobs = (nsubs + grain - 1) / grain;
+    // ---- pass A: rows below every sub-block
+    std::vector<std::vector<int32_t>> lists((size_t)nsubs);
+    dense_pool_run(pool, njobs, [&](int, int job) {
+        for (int32_t q = job * grain; q < std::min(nsubs, (job + 1) * grain); ++q) {
+            const Sub& s = subs[(size_t)q];
+            std::vector<int32_t>& list = lists[(size_t)q];
+            const int32_t c0 = s.j0, c1 = s.j0 + s.w;
+            auto touches = [&](int32_t i) {
+                const int32_t* b = F.Li.data() + F.Lp[(size_t)i];
+                const int32_t* e = F.Li.data() + F.Lp[(size_t)i + 1];
+                const int32_t* at = std::lower_bound(b, e, c0);
+                return at < e && *at < c1;
+            };
+            for (int32_t i = c1; i < F.node_hi[(size_t)s.node]; ++i)
+                if (touches(i)) list.push_back(i);
+            for (int64_t p = F.node_rptr[(size_t)s.node]; p < F.node_rptr[(size_t)s.node + 1]; ++p)
+                if (touches(F.node_rows[(size_t)p])) list.push_back(F.node_rows[(size_t)p]);
+        }
+    });
+    // ---- layout of the records, in sub-block order
+    std::vector<Task> tasks;
+    int64_t rec_size = 0;
+    auto record_bytes = [](int w, int wcl, int kind, int cnt) {
+        const SmallGeom g = small_geom(w, small_buf_bytes(wcl), kind);
+        const int nch = (cnt + g.R - 1) / g.R;
+        size_t bytes = (size_t)g.invB;
+        for (int c = 0; c < nch; ++c) bytes += (size_t)g.arB + (size_t)((std::min(g.R, cnt - c * g.R) + 7) & ~7) * g.wp * 8;
+        return bytes;
+    };
+    for (int32_t q = 0; q < nsubs; ++q) {
+        Sub& s = subs[(size_t)q];
+        const int nA = (int)lists[(size_t)q].size();
+        s.first_task = (int32_t)tasks.size();
+        auto emit = [&](int kind, int a_lo, int a_hi, int phase) {
+            Task T;
+            T.blk.j0 = s.j0;
+            T.blk.w = s.w;
+            T.blk.nA = a_hi - a_lo;
+            T.blk.kind = kind;
+            T.blk.rec_off = rec_size;
+            T.blk.pad1 = 0;
+            T.key = s.base_key + phase;
+            T.wclass = s.wcl;
+            T.a_lo = a_lo;
+            rec_size += (int64_t)record_bytes(s.w, s.wcl, kind, a_hi - a_lo);
+            tasks.push_back(T);
+        };
+        if (nA <= SPLIT_ROWS) {
+            emit(TASK_FUSED, 0, nA, 0);
+        } else {
+            emit(TASK_SOLVE_ONLY, 0, 0, 0);
+            const int nparts = (nA + SPLIT_ROWS - 1) / SPLIT_ROWS;
+            for (int p = 0; p < nparts; ++p)
+                emit(TASK_PUSH_ONLY, (int)((int64_t)nA * p / nparts), (int)((int64_t)nA * (p + 1) / nparts), 1);
+        }
+        s.ntask = (int32_t)tasks.size() - s.first_task;
+    }
+    rec.resize((size_t)rec_size);  // not value-initialised: zeroed record by record in pass B
+    // ---- pass B: inverse triangles and panels
+    struct Scratch {
+        std::vector<double> Ld, X;
+    };
+    std::vector<Scratch> scratch((size_t)nthreads);
+    dense_pool_run(pool, njobs, [&](int th, int job) {
+        Scratch& sc = scratch[(size_t)th];
+        for (int32_t q = job * grain; q < std::min(nsubs, (job + 1) * grain); ++q) {
+            const Sub& s = subs[(size_t)q];
+            const std::vector<int32_t>& list = lists[(size_t)q];
+            const int32_t j0 = s.j0, w = s.w;
+            // inverse of the diagonal triangle
+            sc.Ld.assign((size_t)w * w, 0.0);
+            sc.X.assign((size_t)w * w, 0.0);
+            double* Ld = sc.Ld.data();
+            double* X = sc.X.data();
+            for (int32_t r = 0; r < w; ++r) {
+                Ld[(size_t)r * w + r] = 1.0 / F.dinv[(size_t)j0 + r];
+                for (int64_t p = F.Lp[(size_t)j0 + r]; p < F.Lp[(size_t)j0 + r + 1]; ++p)
+                    if (F.Li[p] >= j0) Ld[(size_t)r * w + (F.Li[p] - j0)] = F.Lx[p];
+            }
+            for (int32_t j = 0; j < w; ++j) {
+                X[(size_t)j * w + j] = 1.0 / Ld[(size_t)j * w + j];
+                for (int32_t r = j + 1; r < w; ++r) {
+                    double sum = 0.0;
+                    for (int32_t k = j; k < r; ++k) sum += Ld[(size_t)r * w + k] * X[(size_t)k * w + j];
+                    X[(size_t)r * w + j] = -sum / Ld[(size_t)r * w + r];
+                }
+            }
+            for (int32_t t = s.first_task; t < s.first_task + s.ntask; ++t) {
+                const Task& T = tasks[(size_t)t];
+                const SmallGeom g = small_geom(w, small_buf_bytes(s.wcl), T.blk.kind);
+                const int cnt = T.blk.nA;
+                unsigned char* base = rec.data() + T.blk.rec_off;
+                std::memset(base, 0, record_bytes(w, s.wcl, T.blk.kind, cnt));
+                if (g.invB) {
+                    double* inv = reinterpret_cast<double*>(base);
+                    for (int32_t r = 0; r < w; ++r)
+                        for (int32_t c = 0; c <= r; ++c) inv[(size_t)r * g.wp + c] = X[(size_t)r * w + c];
+                }
+                for (int a = 0; a < cnt; ++a) {
+                    unsigned char* ch = base + g.invB + (size_t)(a / g.R) * g.chunkB;
+                    const int32_t i = list[(size_t)(T.a_lo + a)];
+                    reinterpret_cast<int32_t*>(ch)[a % g.R] = i;
+                    double* prow = reinterpret_cast<double*>(ch + g.arB) + (size_t)(a % g.R) * g.wp;
+                    const int32_t* b = F.Li.data() + F.Lp[(size_t)i];
+                    const int32_t* e = F.Li.data() + F.Lp[(size_t)i + 1];
+                    for (const int32_t* at = std::lower_bound(b, e, j0); at < e && *at < j0 + w; ++at)
+                        prow[*at - j0] = F.Lx[(size_t)(at - F.Li.data())];
+                }
+            }
+        }
+    });
+    dense_pool_destroy(pool);
+    std::vector<int32_t> order(tasks.size());
+    for (size_t k = 0; k < order.size(); ++k) order[k] = (int32_t)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return tasks[a].key != tasks[b].key ? tasks[a].key < tasks[b].key : tasks[a].wclass < tasks[b].wclass;
+    });
+    blk.resize(tasks.size());
+    launches.clear();
+    for (size_t k = 0, k0 = 0; k < order.size(); ++k) {
+        blk[k] = tasks[(size_t)order[k]].blk;
+        const Task& cur = tasks[(size_t)order[k]];
+        if (k + 1 == order.size() || tasks[(size_t)order[k + 1]].key != cur.key || tasks[(size_t)order[k + 1]].wclass != cur.wclass) {
+            launches.push_back({(int)k0, (int)k + 1, cur.wclass});
+            k0 = k + 1;
+        }
+    }
+}
+
+// The serial builder the parallel one above replaced, working on a column copy of L: kept as its cross-check
+// (ASGFEM_TASKS_SERIAL=1, tools/chol_bench.cpp compares the two byte by byte).
+void build_tasks_serial(const CholFactor& F, std::vector<SmallBlk>& blk, RawVec<unsigned char>& rec,
+                        std::vector<std::array<int, 3>>& launches) {
     const int64_t n = F.n;
+    // columns of L (rows ascending inside every column)
+    std::vector<int64_t> cptr((size_t)n + 1, 0);
+    for (int32_t j : F.Li) cptr[j + 1]++;
+    for (int64_t k = 0; k < n; ++k) cptr[k + 1] += cptr[k];
+    std::vector<int32_t> cidx(F.Li.size());
+    std::vector<double> cval(F.Li.size());
+    {
+        std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
+        for (int64_t k = 0; k < n; ++k)
+            for (int64_t p = F.Lp[k]; p < F.Lp[k + 1]; ++p) {
+                int64_t at = fill[F.Li[p]]++;
+                cidx[at] = (int32_t)k;
+                cval[at] = F.Lx[p];
+            }
+    }
     struct Task {
         SmallBlk blk;
         int64_t key;  // launch order
         int wclass;
     };
     std::vector<Task> tasks;
-    std::vector<unsigned char> rec;
+    rec.clear();
     std::vector<int32_t> mark((size_t)n, -1), list;
     std::vector<double> Ld, X;
     auto wclass_of = [](int w) { return w <= 8 ? 8 : (w <= 16 ? 16 : (w <= 24 ? 24 : 32)); };
@@ -589,7 +785,11 @@ int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>
                 T.wclass = wcl;
                 size_t bytes = (size_t)g.invB;
                 for (int c = 0; c < nch; ++c) bytes += (size_t)g.arB + (size_t)((std::min(g.R, cnt - c * g.R) + 7) & ~7) * g.wp * 8;
-                rec.resize(rec.size() + bytes, 0);
+                {
+                    const size_t old_size = rec.size();
+                    rec.resize(old_size + bytes);
+                    std::memset(rec.data() + old_size, 0, bytes);
+                }
                 unsigned char* base = rec.data() + T.blk.rec_off;
                 if (g.invB) {
                     double* inv = reinterpret_cast<double*>(base);
@@ -628,7 +828,7 @@ int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         return tasks[a].key != tasks[b].key ? tasks[a].key < tasks[b].key : tasks[a].wclass < tasks[b].wclass;
     });
-    std::vector<SmallBlk> blk(tasks.size());
+    blk.resize(tasks.size());
     launches.clear();
     for (size_t k = 0, k0 = 0; k < order.size(); ++k) {
         blk[k] = tasks[(size_t)order[k]].blk;
@@ -638,6 +838,15 @@ int build_tasks(asgfem_ctx* ctx, const CholFactor& F, const std::vector<int64_t>
             k0 = k + 1;
         }
     }
+}
+
+int build_tasks(asgfem_ctx* ctx, const CholFactor& F, SmallDev& D, std::vector<std::array<int, 3>>& launches, int64_t* rec_bytes) {
+    std::vector<SmallBlk> blk;
+    RawVec<unsigned char> rec;
+    if (std::getenv("ASGFEM_TASKS_SERIAL"))
+        build_tasks_serial(F, blk, rec, launches);
+    else
+        build_tasks_host(F, blk, rec, launches);
     D.nblocks = (int)blk.size();
     int rc = 0;
     rc |= dev_upload(ctx, &D.blk, blk);
@@ -690,6 +899,17 @@ int precond_setup(asgfem_ctx* ctx) {
     return 0;
 }
 
+// host-only access to the task builders for tools/chol_bench.cpp (task descriptors as raw bytes)
+void precond_tasks_host(const CholFactor& F, bool serial_reference, std::vector<unsigned char>& blk_bytes, RawVec<unsigned char>& rec,
+                        std::vector<std::array<int, 3>>& launches) {
+    std::vector<SmallBlk> blk;
+    if (serial_reference)
+        build_tasks_serial(F, blk, rec, launches);
+    else
+        build_tasks_host(F, blk, rec, launches);
+    blk_bytes.assign(reinterpret_cast<const unsigned char*>(blk.data()), reinterpret_cast<const unsigned char*>(blk.data() + blk.size()));
+}
+
 // Factorises the Dirichlet-reduced matrix (rows / columns with bmask != 0 eliminated) on the host and uploads the sweep tasks.
 // Used for the matrix of this context (precond_setup) and for the GLOBAL mean matrix of a row-sharded run (dist.cu).
 int precond_build(asgfem_ctx* ctx, int64_t nfull, const int64_t* rowptr, const int32_t* col, const double* k0,
@@ -703,23 +923,7 @@ int precond_build(asgfem_ctx* ctx, int64_t nfull, const int64_t* rowptr, const i
     PrecondPlan* P = new PrecondPlan();
     P->nred = F.n;
     P->lnz = (int64_t)F.Li.size();
-    const int64_t n = F.n;
-    // columns of L (rows ascending inside every column)
-    std::vector<int64_t> cptr((size_t)n + 1, 0);
-    for (int32_t j : F.Li) cptr[j + 1]++;
-    for (int64_t k = 0; k < n; ++k) cptr[k + 1] += cptr[k];
-    std::vector<int32_t> cidx(F.Li.size());
-    std::vector<double> cval(F.Li.size());
-    {
-        std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
-        for (int64_t k = 0; k < n; ++k)
-            for (int64_t p = F.Lp[k]; p < F.Lp[k + 1]; ++p) {
-                int64_t at = fill[F.Li[p]]++;
-                cidx[at] = (int32_t)k;
-                cval[at] = F.Lx[p];
-            }
-    }
-    rc = build_tasks(ctx, F, cptr, cidx, cval, P->small, P->launches, &P->rec_bytes);
+    rc = build_tasks(ctx, F, P->small, P->launches, &P->rec_bytes);
     if (!rc) rc = dev_upload(ctx, &P->d_perm, F.perm);
     if (rc) {
         precond_free_plan(P);

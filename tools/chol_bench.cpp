@@ -1,11 +1,13 @@
 // CPU-only timing and cross-check of the host Cholesky (csrc/chol.cpp) on the 7-point pattern of a structured P1 mesh
 // (nx x nx nodes): the multifrontal factor against the scalar up-looking one (same patterns, values to rounding) and the
-// residual of L L^T x = b.  Build/run: tools/chol_bench.sh [nx] [check]
+// residual of L L^T x = b; then the sweep-task builder of sptrsv.cu (parallel, from the rows of L) against its serial
+// reference (column copy of L), byte by byte.  Links libasgfem_cuda.so; no GPU needed.  Build/run: tools/chol_bench.sh [nx] [check]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "common.h"
@@ -54,7 +56,17 @@ int main(int argc, char** argv) {
     int rc = cholesky_reduced(n, rp.data(), col.data(), val.data(), bnd.data(), xy.data(), 256, F, err);
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("nx=%d rc=%d lnz=%zu time %.2f s %s\n", nx, rc, F.Li.size(), s, err.c_str());
-    if (!check || rc != 0) return rc;
+    if (rc != 0) return rc;
+    if (!check) {
+        std::vector<unsigned char> b1;
+        RawVec<unsigned char> r1;
+        std::vector<std::array<int, 3>> l1;
+        t0 = std::chrono::steady_clock::now();
+        precond_tasks_host(F, false, b1, r1, l1);
+        s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("sweep tasks: %zu tasks, %zu launches, %.1f MB of records, %.2f s\n", b1.size() / 32, l1.size(), r1.size() / 1.0e6, s);
+        return 0;
+    }
     // residual of the solve with the factor: P A P^T = L L^T
     const int64_t nr = F.n;
     std::vector<double> b((size_t)nr), x((size_t)nr);
@@ -99,5 +111,22 @@ int main(int argc, char** argv) {
         for (size_t k = 0; k < F.dinv.size(); ++k) dmax = std::max(dmax, std::fabs(F.dinv[k] - G.dinv[k]) / std::fabs(G.dinv[k]));
     }
     printf("patterns identical: %s, max value difference %.3e\n", same ? "yes" : "NO", dmax);
-    return same && dmax < 1e-9 && rmax / bmax < 1e-8 ? 0 : 1;
+    // sweep tasks: parallel builder against the serial reference, for both factors
+    bool tasks_same = true;
+    for (const CholFactor* Q : {&F, &G}) {
+        std::vector<unsigned char> b1, b2;
+        RawVec<unsigned char> r1, r2;
+        std::vector<std::array<int, 3>> l1, l2;
+        t0 = std::chrono::steady_clock::now();
+        precond_tasks_host(*Q, false, b1, r1, l1);
+        const double s1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        t0 = std::chrono::steady_clock::now();
+        precond_tasks_host(*Q, true, b2, r2, l2);
+        const double s2 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const bool eq = b1 == b2 && r1 == r2 && l1 == l2;
+        printf("sweep tasks: %zu tasks, %zu launches, %.1f MB of records; parallel %.2f s, serial reference %.2f s, identical: %s\n",
+               b1.size() / 32, l1.size(), r1.size() / 1.0e6, s1, s2, eq ? "yes" : "NO");
+        tasks_same = tasks_same && eq;
+    }
+    return same && tasks_same && dmax < 1e-9 && rmax / bmax < 1e-8 ? 0 : 1;
 }
