@@ -36,5 +36,8 @@ def run(nx, N, M=20, variant=0):
 
 
 if __name__ == "__main__":
-    for nx, N in [(129, 200), (257, 500), (513, 1000)] + ([(1024, 2000)] if len(sys.argv) > 1 else []):
+    sizes = [(129, 200), (257, 500), (513, 1000)] + ([(1024, 2000)] if len(sys.argv) > 1 else [])
+    if len(sys.argv) > 1 and sys.argv[1] == "c4":  # config 4 only
+        sizes = [(1024, 2000)]
+    for nx, N in sizes:
         run(nx, N)
