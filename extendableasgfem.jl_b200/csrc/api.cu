@@ -21,7 +21,7 @@ extern "C" const char* asgfem_version(void) { return "asgfem-b200 0.1.0 (sm_100a
 
 extern "C" const char* asgfem_last_error(const asgfem_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-extern "C" int asgfem_create(asgfem_ctx** out, int device) {
+extern "C" int asgfem_create(asgfem_ctx** out, int device) try {
     if (!out) return ASGFEM_EINVAL;
     *out = nullptr;
     int count = 0;
@@ -46,6 +46,7 @@ extern "C" int asgfem_create(asgfem_ctx** out, int device) {
     *out = ctx;
     return 0;
 }
+ASG_BOUNDARY_CATCH(nullptr)
 
 static void free_vec_storage(asgfem_ctx* ctx) {
     for (double* p : ctx->slots)
@@ -53,7 +54,7 @@ static void free_vec_storage(asgfem_ctx* ctx) {
     ctx->slots.clear();
 }
 
-extern "C" int asgfem_destroy(asgfem_ctx* ctx) {
+extern "C" int asgfem_destroy(asgfem_ctx* ctx) try {
     CTX_OR_FAIL(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -73,6 +74,7 @@ extern "C" int asgfem_destroy(asgfem_ctx* ctx) {
     delete ctx;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- samples as columns (deterministic reference solutions of the MC error, src/sampling_error.jl:84-128) -----------
 // For the affine coefficient a(x, xi) = a_0(x) + sum_m xi_m a_m(x) the deterministic problem of sample s has the matrix
@@ -80,7 +82,7 @@ extern "C" int asgfem_destroy(asgfem_ctx* ctx) {
 // all nsamples systems are ONE block system with a diagonal coupling (G_m = diag(xi_{.,m})): the operator kernel, the
 // multi-RHS mean preconditioner K_0^-1 and the PCG of the SGFE solve apply unchanged (the reference solves the samples
 // one by one on host threads with ExtendableFEM.solve).
-extern "C" int asgfem_set_samples(asgfem_ctx* ctx, int64_t nsamples, int64_t Msamples, const double* samples) {
+extern "C" int asgfem_set_samples(asgfem_ctx* ctx, int64_t nsamples, int64_t Msamples, const double* samples) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, nsamples >= 1 && nsamples < 65536 && Msamples >= 0 && (samples || Msamples == 0), ASGFEM_EINVAL, "set_samples: bad arguments");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -122,9 +124,10 @@ extern "C" int asgfem_set_samples(asgfem_ctx* ctx, int64_t nsamples, int64_t Msa
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- multi-indices ----------------------------------------------------------------------------
-extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t N, int64_t M, const int64_t* mi) {
+extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t N, int64_t M, const int64_t* mi) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, family == ASGFEM_LEGENDRE || family == ASGFEM_HERMITE, ASGFEM_EINVAL, "unknown polynomial family");
     ASG_CHECK(ctx, N >= 1 && M >= 1 && mi, ASGFEM_EINVAL, "set_multiindices: need N >= 1, M >= 1");
@@ -182,15 +185,17 @@ extern "C" int asgfem_set_multiindices(asgfem_ctx* ctx, int32_t family, int64_t 
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_get_coupling_nnz(asgfem_ctx* ctx, int64_t* nnz) {
+extern "C" int asgfem_get_coupling_nnz(asgfem_ctx* ctx, int64_t* nnz) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->N > 0 && nnz, ASGFEM_ESTATE, "multi-indices not set");
     *nnz = (int64_t)ctx->coup.m.size();
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_get_coupling_csc(asgfem_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval) {
+extern "C" int asgfem_get_coupling_csc(asgfem_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->N > 0, ASGFEM_ESTATE, "multi-indices not set");
     ASG_CHECK(ctx, colptr && rowval && nzval, ASGFEM_EINVAL, "null output");
@@ -218,8 +223,9 @@ extern "C" int asgfem_get_coupling_csc(asgfem_ctx* ctx, int64_t* colptr, int64_t
     colptr[N] = p + 1;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_get_neighbours(asgfem_ctx* ctx, int64_t* plus, int64_t* minus) {
+extern "C" int asgfem_get_neighbours(asgfem_ctx* ctx, int64_t* plus, int64_t* minus) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->N > 0, ASGFEM_ESTATE, "multi-indices not set");
     ASG_CHECK(ctx, plus && minus, ASGFEM_EINVAL, "null output");
@@ -227,6 +233,7 @@ extern "C" int asgfem_get_neighbours(asgfem_ctx* ctx, int64_t* plus, int64_t* mi
     std::memcpy(minus, ctx->mis.minus.data(), sizeof(int64_t) * ctx->mis.minus.size());
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- pattern and values -------------------------------------------------------------------------
 static int install_pattern(asgfem_ctx* ctx, int64_t n, const std::vector<int64_t>& colptr0,
@@ -271,7 +278,7 @@ static int install_pattern(asgfem_ctx* ctx, int64_t n, const std::vector<int64_t
     return 0;
 }
 
-extern "C" int asgfem_set_pattern_csc(asgfem_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval) {
+extern "C" int asgfem_set_pattern_csc(asgfem_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, n >= 1 && colptr && rowval, ASGFEM_EINVAL, "set_pattern_csc: bad arguments");
     ASG_CHECK(ctx, n < (1ll << 31) - 1, ASGFEM_EINVAL, "n too large");
@@ -294,8 +301,9 @@ extern "C" int asgfem_set_pattern_csc(asgfem_ctx* ctx, int64_t n, const int64_t*
         }
     return install_pattern(ctx, n, cp, rv);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_set_num_stiffness(asgfem_ctx* ctx, int32_t M) {
+extern "C" int asgfem_set_num_stiffness(asgfem_ctx* ctx, int32_t M) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0, ASGFEM_ESTATE, "pattern not set");
     ASG_CHECK(ctx, M >= 0 && M < 4096, ASGFEM_EINVAL, "bad number of KLE terms");
@@ -310,6 +318,7 @@ extern "C" int asgfem_set_num_stiffness(asgfem_ctx* ctx, int32_t M) {
     precond_free(ctx);
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 static int upload_values_csr(asgfem_ctx* ctx, int32_t m, const std::vector<double>& csr) {
     ASG_CUDA(ctx, cudaMemcpyAsync(ctx->d_vals + (size_t)m * ctx->nnz, csr.data(), sizeof(double) * ctx->nnz,
@@ -319,7 +328,7 @@ static int upload_values_csr(asgfem_ctx* ctx, int32_t m, const std::vector<doubl
     return 0;
 }
 
-extern "C" int asgfem_set_stiffness(asgfem_ctx* ctx, int32_t m, const double* nzval) {
+extern "C" int asgfem_set_stiffness(asgfem_ctx* ctx, int32_t m, const double* nzval) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->M >= 0, ASGFEM_ESTATE, "set_num_stiffness first");
     ASG_CHECK(ctx, m >= 0 && m <= ctx->M && nzval, ASGFEM_EINVAL, "set_stiffness: m out of range");
@@ -328,9 +337,10 @@ extern "C" int asgfem_set_stiffness(asgfem_ctx* ctx, int32_t m, const double* nz
     for (int64_t p = 0; p < ctx->nnz; ++p) csr[ctx->h_csc2csr[p]] = nzval[p];
     return upload_values_csr(ctx, m, csr);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_set_stiffness_csc(asgfem_ctx* ctx, int32_t m, const int64_t* colptr, const int64_t* rowval,
-                                        const double* nzval) {
+                                        const double* nzval) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->M >= 0, ASGFEM_ESTATE, "set_num_stiffness first");
     ASG_CHECK(ctx, m >= 0 && m <= ctx->M && colptr && rowval && nzval, ASGFEM_EINVAL, "set_stiffness_csc: bad arguments");
@@ -348,8 +358,9 @@ extern "C" int asgfem_set_stiffness_csc(asgfem_ctx* ctx, int32_t m, const int64_
     }
     return upload_values_csr(ctx, m, csr);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_get_stiffness(asgfem_ctx* ctx, int32_t m, double* nzval) {
+extern "C" int asgfem_get_stiffness(asgfem_ctx* ctx, int32_t m, double* nzval) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->M >= 0 && m >= 0 && m <= ctx->M && nzval, ASGFEM_EINVAL, "get_stiffness: m out of range");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -360,23 +371,26 @@ extern "C" int asgfem_get_stiffness(asgfem_ctx* ctx, int32_t m, double* nzval) {
     for (int64_t p = 0; p < ctx->nnz; ++p) nzval[p] = csr[ctx->h_csc2csr[p]];
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_get_pattern_nnz(asgfem_ctx* ctx, int64_t* nnz) {
+extern "C" int asgfem_get_pattern_nnz(asgfem_ctx* ctx, int64_t* nnz) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0 && nnz, ASGFEM_ESTATE, "pattern not set");
     *nnz = ctx->nnz;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_get_pattern_csc(asgfem_ctx* ctx, int64_t* colptr, int64_t* rowval) {
+extern "C" int asgfem_get_pattern_csc(asgfem_ctx* ctx, int64_t* colptr, int64_t* rowval) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0 && colptr && rowval, ASGFEM_ESTATE, "pattern not set");
     for (int64_t c = 0; c <= ctx->n; ++c) colptr[c] = ctx->h_csc_colptr[c] + 1;
     for (int64_t p = 0; p < ctx->nnz; ++p) rowval[p] = ctx->h_csc_row[p] + 1;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_set_bdofs(asgfem_ctx* ctx, int64_t nb, const int64_t* bdofs) {
+extern "C" int asgfem_set_bdofs(asgfem_ctx* ctx, int64_t nb, const int64_t* bdofs) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0, ASGFEM_ESTATE, "pattern not set");
     ASG_CHECK(ctx, nb >= 0 && (nb == 0 || bdofs), ASGFEM_EINVAL, "set_bdofs: bad arguments");
@@ -394,6 +408,7 @@ extern "C" int asgfem_set_bdofs(asgfem_ctx* ctx, int64_t nb, const int64_t* bdof
     precond_free(ctx);
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- mesh / space / coefficient -----------------------------------------------------------------
 // A pattern derived from celldofs (asgfem_assemble_stiffness without asgfem_set_pattern_csc) belongs to the mesh / space it
@@ -419,7 +434,7 @@ static void drop_derived_pattern(asgfem_ctx* ctx) {
 }
 
 extern "C" int asgfem_set_mesh(asgfem_ctx* ctx, int64_t nnodes, int64_t ncells, const double* coords,
-                               const int32_t* cellnodes) {
+                               const int32_t* cellnodes) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, nnodes >= 3 && ncells >= 1 && coords && cellnodes, ASGFEM_EINVAL, "set_mesh: bad arguments");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -439,9 +454,10 @@ extern "C" int asgfem_set_mesh(asgfem_ctx* ctx, int64_t nnodes, int64_t ncells, 
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_set_space(asgfem_ctx* ctx, int32_t order, int64_t ndofs, int32_t ndofs4cell,
-                                const int32_t* celldofs) {
+                                const int32_t* celldofs) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->ncells > 0, ASGFEM_ESTATE, "set_mesh first");
     ASG_CHECK(ctx, (order == 1 && ndofs4cell == 3) || (order == 2 && ndofs4cell == 6), ASGFEM_EINVAL,
@@ -466,9 +482,10 @@ extern "C" int asgfem_set_space(asgfem_ctx* ctx, int32_t order, int64_t ndofs, i
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_set_coefficient_cosinus(asgfem_ctx* ctx, int64_t maxm, double mean, const double* decay_factors,
-                                              const int64_t* b1, const int64_t* b2) {
+                                              const int64_t* b1, const int64_t* b2) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, maxm >= 0 && (maxm == 0 || (decay_factors && b1 && b2)), ASGFEM_EINVAL, "set_coefficient: bad arguments");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -489,8 +506,9 @@ extern "C" int asgfem_set_coefficient_cosinus(asgfem_ctx* ctx, int64_t maxm, dou
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w) {
+extern "C" int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->order > 0, ASGFEM_ESTATE, "set_mesh / set_space first");
     ASG_CHECK(ctx, M >= 0 && M <= ctx->maxm, ASGFEM_EINVAL, "assemble_stiffness: M exceeds maxm of the coefficient");
@@ -529,10 +547,11 @@ extern "C" int asgfem_assemble_stiffness(asgfem_ctx* ctx, int32_t M, int32_t nq,
     if (rc) return rc;
     return assemble_stiffness(ctx, M, nq, xref, w);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // Log-transformed primal problem (logpoisson_primal.jl:95-105): plane 0 = the Laplacian A (= A + N0, N0 is empty in the
 // reference), planes 1..M = the convection matrices N_m, on the pattern derived from celldofs (or the caller's)
-extern "C" int asgfem_assemble_logprimal(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w) {
+extern "C" int asgfem_assemble_logprimal(asgfem_ctx* ctx, int32_t M, int32_t nq, const double* xref, const double* w) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->order > 0, ASGFEM_ESTATE, "set_mesh / set_space first");
     ASG_CHECK(ctx, M >= 0 && M <= ctx->maxm, ASGFEM_EINVAL, "assemble_logprimal: M exceeds maxm of the coefficient");
@@ -544,6 +563,7 @@ extern "C" int asgfem_assemble_logprimal(asgfem_ctx* ctx, int32_t M, int32_t nq,
     ctx->h_precond_vals.clear();  // the preconditioner is factorised from plane 0 = A
     return assemble_stiffness(ctx, M, nq, xref, w, 1);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- vectors ------------------------------------------------------------------------------------
 static int check_slot(asgfem_ctx* ctx, int32_t slot) {
@@ -552,7 +572,7 @@ static int check_slot(asgfem_ctx* ctx, int32_t slot) {
     return 0;
 }
 
-extern "C" int asgfem_vec_alloc(asgfem_ctx* ctx, int32_t nslots) {
+extern "C" int asgfem_vec_alloc(asgfem_ctx* ctx, int32_t nslots) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0 && ctx->N > 0, ASGFEM_ESTATE, "pattern and multi-indices must be set before vec_alloc");
     ASG_CHECK(ctx, nslots >= 0 && nslots <= 64, ASGFEM_EINVAL, "bad slot count");
@@ -571,24 +591,27 @@ extern "C" int asgfem_vec_alloc(asgfem_ctx* ctx, int32_t nslots) {
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_upload(asgfem_ctx* ctx, int32_t slot, const double* host) {
+extern "C" int asgfem_vec_upload(asgfem_ctx* ctx, int32_t slot, const double* host) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, host, ASGFEM_EINVAL, "null host pointer");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return vec_to_device_layout(ctx, host, ctx->slots[slot]);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_download(asgfem_ctx* ctx, int32_t slot, double* host) {
+extern "C" int asgfem_vec_download(asgfem_ctx* ctx, int32_t slot, double* host) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, host, ASGFEM_EINVAL, "null host pointer");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return vec_to_host_layout(ctx, ctx->slots[slot], host);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_zero(asgfem_ctx* ctx, int32_t slot) {
+extern "C" int asgfem_vec_zero(asgfem_ctx* ctx, int32_t slot) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -596,8 +619,9 @@ extern "C" int asgfem_vec_zero(asgfem_ctx* ctx, int32_t slot) {
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_fill_random(asgfem_ctx* ctx, int32_t slot, uint64_t seed) {
+extern "C" int asgfem_vec_fill_random(asgfem_ctx* ctx, int32_t slot, uint64_t seed) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -606,24 +630,27 @@ extern "C" int asgfem_vec_fill_random(asgfem_ctx* ctx, int32_t slot, uint64_t se
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_dot(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) {
+extern "C" int asgfem_vec_dot(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, a) || check_slot(ctx, b)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, out, ASGFEM_EINVAL, "null output");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return vec_dot(ctx, ctx->slots[a], ctx->slots[b], ctx->n, out);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_dot_owned(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) {
+extern "C" int asgfem_vec_dot_owned(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, a) || check_slot(ctx, b)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, out, ASGFEM_EINVAL, "null output");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return vec_dot(ctx, ctx->slots[a], ctx->slots[b], ctx->n_owned >= 0 ? ctx->n_owned : ctx->n, out);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_axpy(asgfem_ctx* ctx, double alpha, int32_t x, int32_t y) {
+extern "C" int asgfem_vec_axpy(asgfem_ctx* ctx, double alpha, int32_t x, int32_t y) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, x) || check_slot(ctx, y)) return ASGFEM_EINVAL;
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -632,8 +659,9 @@ extern "C" int asgfem_vec_axpy(asgfem_ctx* ctx, double alpha, int32_t x, int32_t
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_xpay(asgfem_ctx* ctx, int32_t x, double beta, int32_t y) {
+extern "C" int asgfem_vec_xpay(asgfem_ctx* ctx, int32_t x, double beta, int32_t y) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, x) || check_slot(ctx, y)) return ASGFEM_EINVAL;
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -642,8 +670,9 @@ extern "C" int asgfem_vec_xpay(asgfem_ctx* ctx, int32_t x, double beta, int32_t 
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_copy(asgfem_ctx* ctx, int32_t src, int32_t dst) {
+extern "C" int asgfem_vec_copy(asgfem_ctx* ctx, int32_t src, int32_t dst) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, src) || check_slot(ctx, dst)) return ASGFEM_EINVAL;
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -653,6 +682,7 @@ extern "C" int asgfem_vec_copy(asgfem_ctx* ctx, int32_t src, int32_t dst) {
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- operator -----------------------------------------------------------------------------------
 static int ensure_ready_for_apply(asgfem_ctx* ctx) {
@@ -668,14 +698,15 @@ static int ensure_ready_for_apply(asgfem_ctx* ctx) {
     return 0;
 }
 
-extern "C" int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant) {
+extern "C" int asgfem_set_apply_variant(asgfem_ctx* ctx, int32_t variant) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, variant == 0 || variant == 1 || variant == 7 || variant == 9, ASGFEM_EINVAL, "apply variant must be 0 (automatic), 1, 7 or 9");
     ctx->apply_variant = variant;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_apply(asgfem_ctx* ctx, int32_t sx, int32_t sy) {
+extern "C" int asgfem_apply(asgfem_ctx* ctx, int32_t sx, int32_t sy) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, sx) || check_slot(ctx, sy)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, sx != sy, ASGFEM_EINVAL, "apply: x and y must be different slots");
@@ -708,8 +739,9 @@ extern "C" int asgfem_apply(asgfem_ctx* ctx, int32_t sx, int32_t sy) {
     ctx->last_apply_ms = ms;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_apply_rows(asgfem_ctx* ctx, int32_t sx, int32_t sy, int64_t row0, int64_t row1) {
+extern "C" int asgfem_apply_rows(asgfem_ctx* ctx, int32_t sx, int32_t sy, int64_t row0, int64_t row1) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, sx) || check_slot(ctx, sy)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, sx != sy, ASGFEM_EINVAL, "apply_rows: x and y must be different slots");
@@ -728,27 +760,30 @@ extern "C" int asgfem_apply_rows(asgfem_ctx* ctx, int32_t sx, int32_t sy, int64_
     ctx->last_apply_ms = ms;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms) {
+extern "C" int asgfem_last_apply_ms(asgfem_ctx* ctx, double* ms) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ms, ASGFEM_EINVAL, "null output");
     *ms = ctx->last_apply_ms;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_last_estimate_ms(asgfem_ctx* ctx, double* ms) {
+extern "C" int asgfem_last_estimate_ms(asgfem_ctx* ctx, double* ms) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ms, ASGFEM_EINVAL, "null output");
     *ms = ctx->last_estimate_ms;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 static int ensure_work_slots(asgfem_ctx* ctx, int need) {
     if ((int)ctx->slots.size() >= need) return 0;
     return asgfem_vec_alloc(ctx, need);
 }
 
-extern "C" int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax) {
+extern "C" int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, x && Ax, ASGFEM_EINVAL, "null host pointer");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -762,18 +797,20 @@ extern "C" int asgfem_apply_host(asgfem_ctx* ctx, const double* x, double* Ax) {
     if ((rc = apply_launch(ctx, ctx->slots[0], ctx->slots[1]))) return rc;
     return vec_to_host_layout(ctx, ctx->slots[1], Ax);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- preconditioner -----------------------------------------------------------------------------
-extern "C" int asgfem_precond_setup(asgfem_ctx* ctx) {
+extern "C" int asgfem_precond_setup(asgfem_ctx* ctx) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0 && ctx->M >= 0, ASGFEM_ESTATE, "precond_setup: K_0 not set");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return precond_setup(ctx);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_host_factor_solve(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val,
                                         const uint8_t* is_boundary, const double* coords, const double* b, double* x,
-                                        int64_t* lnz, char* err, int32_t errlen) {
+                                        int64_t* lnz, char* err, int32_t errlen) try {
     auto fail = [&](int rc, const std::string& msg) {
         if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", msg.c_str());
         return rc;
@@ -804,8 +841,9 @@ extern "C" int asgfem_host_factor_solve(int64_t n, const int64_t* rowptr, const 
     }
     return 0;
 }
+ASG_BOUNDARY_CATCH(nullptr)
 
-extern "C" int asgfem_precond_apply(asgfem_ctx* ctx, int32_t sr, int32_t sz) {
+extern "C" int asgfem_precond_apply(asgfem_ctx* ctx, int32_t sr, int32_t sz) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, sr) || check_slot(ctx, sz)) return ASGFEM_EINVAL;
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -818,8 +856,9 @@ extern "C" int asgfem_precond_apply(asgfem_ctx* ctx, int32_t sr, int32_t sz) {
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_precond_apply_host(asgfem_ctx* ctx, const double* b, double* y) {
+extern "C" int asgfem_precond_apply_host(asgfem_ctx* ctx, const double* b, double* y) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, b && y, ASGFEM_EINVAL, "null host pointer");
     ASG_CHECK(ctx, ctx->N > 0, ASGFEM_ESTATE, "multi-indices not set");
@@ -831,10 +870,11 @@ extern "C" int asgfem_precond_apply_host(asgfem_ctx* ctx, const double* b, doubl
     if ((rc = precond_apply(ctx, ctx->slots[0], ctx->slots[1]))) return rc;
     return vec_to_host_layout(ctx, ctx->slots[1], y);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- Krylov driver ------------------------------------------------------------------------------
 extern "C" int asgfem_pcg(asgfem_ctx* ctx, const double* b0, int32_t slot_x, double atol, double rtol, int64_t itmax,
-                          asgfem_stats* stats) {
+                          asgfem_stats* stats) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot_x)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, b0, ASGFEM_EINVAL, "null b0");
@@ -844,9 +884,10 @@ extern "C" int asgfem_pcg(asgfem_ctx* ctx, const double* b0, int32_t slot_x, dou
     if (!ctx->precond && !dist_has_global_precond(ctx) && (rc = precond_setup(ctx))) return rc;
     return pcg_solve(ctx, b0, ctx->slots[slot_x], atol, rtol, itmax, stats);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const double* b0, double atol, double rtol,
-                                        int64_t itmax, asgfem_stats* stats) {
+                                        int64_t itmax, asgfem_stats* stats) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, sol && b0, ASGFEM_EINVAL, "null host pointer");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -858,10 +899,11 @@ extern "C" int asgfem_solve_primal_host(asgfem_ctx* ctx, double* sol, const doub
     if ((rc = pcg_solve(ctx, b0, ctx->slots[0], atol, rtol, itmax, stats))) return rc;
     return vec_to_host_layout(ctx, ctx->slots[0], sol);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // out (n x nsamples, column s = solution of sample s): K(xi_s) u_s = b with u_s = 0 on the Dirichlet dofs
 extern "C" int asgfem_solve_samples_host(asgfem_ctx* ctx, double* out, const double* b, double atol, double rtol, int64_t itmax,
-                                         asgfem_stats* stats) {
+                                         asgfem_stats* stats) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->sample_mode, ASGFEM_ESTATE, "solve_samples: asgfem_set_samples first");
     ASG_CHECK(ctx, out && b, ASGFEM_EINVAL, "null host pointer");
@@ -875,11 +917,12 @@ extern "C" int asgfem_solve_samples_host(asgfem_ctx* ctx, double* out, const dou
     if ((rc = pcg_solve(ctx, b, ctx->slots[0], atol, rtol, itmax, stats))) return rc;
     return vec_to_host_layout(ctx, ctx->slots[0], out);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 
 // ---- log-transformed primal problem ----------------------------------------------------------------
 extern "C" int asgfem_set_precond_matrix_csc(asgfem_ctx* ctx, const int64_t* colptr, const int64_t* rowval,
-                                             const double* nzval) {
+                                             const double* nzval) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0 && ctx->nnz > 0, ASGFEM_ESTATE, "set_precond_matrix_csc: set_pattern_csc first");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -901,10 +944,11 @@ extern "C" int asgfem_set_precond_matrix_csc(asgfem_ctx* ctx, const int64_t* col
     ctx->h_precond_vals.swap(csr);
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // load vectors b[mu] = (lambda_mu f, phi_i) of the log-transformed primal problem into a device slot (logpoisson_primal.jl:108-127)
 extern "C" int asgfem_assemble_logprimal_rhs(asgfem_ctx* ctx, int32_t nq, const double* xref, const double* w, const double* f_at_qp,
-                                             int32_t ntrunc, int32_t slot_b) {
+                                             int32_t ntrunc, int32_t slot_b) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot_b)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, ctx->order > 0 && ctx->ncells > 0 && ctx->ndofs_space == ctx->n, ASGFEM_ESTATE, "assemble_logprimal_rhs: set_mesh / set_space first");
@@ -915,9 +959,10 @@ extern "C" int asgfem_assemble_logprimal_rhs(asgfem_ctx* ctx, int32_t nq, const 
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return assemble_logprimal_rhs(ctx, nq, xref, w, f_at_qp, ntrunc, ctx->slots[slot_b]);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_bicgstab(asgfem_ctx* ctx, int32_t slot_b, int32_t slot_x, double atol, double rtol, int64_t itmax,
-                               asgfem_stats* stats) {
+                               asgfem_stats* stats) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot_b) || check_slot(ctx, slot_x)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, slot_b != slot_x, ASGFEM_EINVAL, "bicgstab: b and x must be different slots");
@@ -927,9 +972,10 @@ extern "C" int asgfem_bicgstab(asgfem_ctx* ctx, int32_t slot_b, int32_t slot_x, 
     if (!ctx->precond && (rc = precond_setup(ctx))) return rc;
     return bicgstab_solve(ctx, ctx->slots[slot_b], ctx->slots[slot_x], atol, rtol, itmax, stats);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_solve_logprimal_host(asgfem_ctx* ctx, double* sol, const double* b, double atol, double rtol,
-                                           int64_t itmax, asgfem_stats* stats) {
+                                           int64_t itmax, asgfem_stats* stats) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, sol && b, ASGFEM_EINVAL, "null host pointer");
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -943,10 +989,11 @@ extern "C" int asgfem_solve_logprimal_host(asgfem_ctx* ctx, double* sol, const d
     if ((rc = bicgstab_solve(ctx, ctx->slots[1], ctx->slots[0], atol, rtol, itmax, stats))) return rc;
     return vec_to_host_layout(ctx, ctx->slots[0], sol);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- evaluation at samples ------------------------------------------------------------------------
 extern "C" int asgfem_evaluate_samples(asgfem_ctx* ctx, int32_t slot_u, int64_t nsamples, int64_t M_in, int32_t nvals,
-                                       const double* vals, double* out) {
+                                       const double* vals, double* out) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot_u)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, ctx->N > 0 && ctx->n > 0, ASGFEM_ESTATE, "evaluate_samples: multi-indices / pattern not set");
@@ -986,12 +1033,13 @@ extern "C" int asgfem_evaluate_samples(asgfem_ctx* ctx, int32_t slot_u, int64_t 
     if (e != cudaSuccess) return fail(ctx, ASGFEM_ECUDA, std::string("evaluate_samples: ") + cudaGetErrorString(e));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- estimator ----------------------------------------------------------------------------------
 extern "C" int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,
                                               const int64_t* mi_ext, int32_t nq, const double* xref, const double* w,
                                               const double* f_at_qp, int32_t nqf, const double* sf, const double* wf,
-                                              double* eta4cell, double* eta4modes) {
+                                              double* eta4cell, double* eta4modes) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot_u)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, ctx->order > 0 && ctx->ncells > 0, ASGFEM_ESTATE, "estimate: set_mesh / set_space first");
@@ -1005,12 +1053,13 @@ extern "C" int asgfem_estimate_poisson_primal(asgfem_ctx* ctx, int32_t slot_u, i
     return estimate_poisson_primal(ctx, ctx->slots[slot_u], N_ext, M_ext, mi_ext, nq, xref, w, f_at_qp, nqf, sf, wf,
                                    eta4cell, eta4modes);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // estimate(::Type{LogTransformedPoissonProblemPrimal}, ...) (src/estimate.jl:70-257)
 extern "C" int asgfem_estimate_logpoisson_primal(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext, const int64_t* mi_ext,
                                                  int32_t nq, const double* xref, const double* w, const double* f_at_qp,
                                                  const double* lam_at_qp, int32_t ntrunc, int32_t nqf, const double* sf,
-                                                 const double* wf, double* eta4cell, double* eta4modes, double* zeta3) {
+                                                 const double* wf, double* eta4cell, double* eta4modes, double* zeta3) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot_u)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, ctx->order > 0 && ctx->ncells > 0, ASGFEM_ESTATE, "estimate: set_mesh / set_space first");
@@ -1024,13 +1073,14 @@ extern "C" int asgfem_estimate_logpoisson_primal(asgfem_ctx* ctx, int32_t slot_u
     return estimate_poisson_primal(ctx, ctx->slots[slot_u], N_ext, M_ext, mi_ext, nq, xref, w, f_at_qp, nqf, sf, wf, eta4cell,
                                    eta4modes, -1, nullptr, nullptr, 1, lam_at_qp, ntrunc, zeta3);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // The outputs the adaptive loop consumes (scripts/poisson.jl:341-420): eta4modes and, for the spatial marking, the sum of
 // eta4cell over a set of columns (the active modes) - without the D2H of the ncells x N_ext matrix
 extern "C" int asgfem_estimate_poisson_primal_marking(asgfem_ctx* ctx, int32_t slot_u, int64_t N_ext, int64_t M_ext,
                                                       const int64_t* mi_ext, int32_t nq, const double* xref, const double* w,
                                                       const double* f_at_qp, int32_t nqf, const double* sf, const double* wf,
-                                                      int64_t nsel, const int64_t* sel, double* cellsum, double* eta4modes) {
+                                                      int64_t nsel, const int64_t* sel, double* cellsum, double* eta4modes) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot_u)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, ctx->order > 0 && ctx->ncells > 0, ASGFEM_ESTATE, "estimate: set_mesh / set_space first");
@@ -1045,65 +1095,73 @@ extern "C" int asgfem_estimate_poisson_primal_marking(asgfem_ctx* ctx, int32_t s
     return estimate_poisson_primal(ctx, ctx->slots[slot_u], N_ext, M_ext, mi_ext, nq, xref, w, f_at_qp, nqf, sf, wf, nullptr,
                                    eta4modes, nsel, sel, cellsum);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- multi-GPU: NCCL inside the library ------------------------------------------------------------
-extern "C" int asgfem_comm_unique_id(void* id128) {
+extern "C" int asgfem_comm_unique_id(void* id128) try {
     if (!id128) return ASGFEM_EINVAL;
     std::string err;
     int rc = dist_unique_id(id128, err);
     if (rc) g_create_error = err;
     return rc;
 }
+ASG_BOUNDARY_CATCH(nullptr)
 
-extern "C" int asgfem_comm_init(asgfem_ctx* ctx, int32_t nranks, int32_t rank, const void* id128) {
+extern "C" int asgfem_comm_init(asgfem_ctx* ctx, int32_t nranks, int32_t rank, const void* id128) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, nranks >= 1 && rank >= 0 && rank < nranks && id128, ASGFEM_EINVAL, "comm_init: bad arguments");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return dist_init(ctx, nranks, rank, id128);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_comm_destroy(asgfem_ctx* ctx) {
+extern "C" int asgfem_comm_destroy(asgfem_ctx* ctx) try {
     CTX_OR_FAIL(ctx);
     if (set_device(ctx)) return ASGFEM_ECUDA;
     cudaStreamSynchronize(ctx->stream);
     dist_free(ctx);
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_set_halo(asgfem_ctx* ctx, int32_t nneigh, const int32_t* ranks, const int64_t* send_ptr,
                                const int64_t* send_rows, const int64_t* recv_ptr, const int64_t* recv_rows,
-                               int64_t interior_row0, int64_t interior_row1) {
+                               int64_t interior_row0, int64_t interior_row1) try {
     CTX_OR_FAIL(ctx);
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return dist_set_halo(ctx, nneigh, ranks, send_ptr, send_rows, recv_ptr, recv_rows, interior_row0, interior_row1);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 extern "C" int asgfem_precond_setup_global(asgfem_ctx* ctx, int64_t n_global, const int64_t* colptr, const int64_t* rowval,
                                            const double* nzval, int64_t nb, const int64_t* bdofs, const double* coords,
-                                           const int64_t* row_offsets) {
+                                           const int64_t* row_offsets) try {
     CTX_OR_FAIL(ctx);
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return dist_precond_setup_global(ctx, n_global, colptr, rowval, nzval, nb, bdofs, coords, row_offsets);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_dot_global(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) {
+extern "C" int asgfem_vec_dot_global(asgfem_ctx* ctx, int32_t a, int32_t b, double* out) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, a) || check_slot(ctx, b)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, out, ASGFEM_EINVAL, "null output");
     if (set_device(ctx)) return ASGFEM_ECUDA;
     return dist_dot(ctx, ctx->slots[a], ctx->slots[b], out);
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 // ---- multi-GPU helpers --------------------------------------------------------------------------
-extern "C" int asgfem_set_owned_rows(asgfem_ctx* ctx, int64_t n_owned) {
+extern "C" int asgfem_set_owned_rows(asgfem_ctx* ctx, int64_t n_owned) try {
     CTX_OR_FAIL(ctx);
     ASG_CHECK(ctx, ctx->n > 0 && n_owned >= 1 && n_owned <= ctx->n, ASGFEM_EINVAL, "set_owned_rows: out of range");
     ctx->n_owned = n_owned;
     apply_free_plan(ctx);
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_halo_exchange(asgfem_ctx* ctx, int32_t slot) {
+extern "C" int asgfem_halo_exchange(asgfem_ctx* ctx, int32_t slot) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     if (set_device(ctx)) return ASGFEM_ECUDA;
@@ -1112,8 +1170,9 @@ extern "C" int asgfem_halo_exchange(asgfem_ctx* ctx, int32_t slot) {
     ASG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_set_owned_cells(asgfem_ctx* ctx, int64_t ncells, const uint8_t* owned) {
+extern "C" int asgfem_set_owned_cells(asgfem_ctx* ctx, int64_t ncells, const uint8_t* owned) try {
     CTX_OR_FAIL(ctx);
     if (!owned) {
         ctx->h_cell_owned.clear();
@@ -1123,8 +1182,9 @@ extern "C" int asgfem_set_owned_cells(asgfem_ctx* ctx, int64_t ncells, const uin
     ctx->h_cell_owned.assign(owned, owned + ncells);
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_vec_device_ptr(asgfem_ctx* ctx, int32_t slot, void** dptr, int64_t* ld) {
+extern "C" int asgfem_vec_device_ptr(asgfem_ctx* ctx, int32_t slot, void** dptr, int64_t* ld) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, dptr && ld, ASGFEM_EINVAL, "null output");
@@ -1132,6 +1192,7 @@ extern "C" int asgfem_vec_device_ptr(asgfem_ctx* ctx, int32_t slot, void** dptr,
     *ld = ctx->ld;
     return 0;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
 static int rows_to_device(asgfem_ctx* ctx, int64_t nrows, const int64_t* rows, int64_t** d_rows) {
     for (int64_t k = 0; k < nrows; ++k)
@@ -1141,7 +1202,7 @@ static int rows_to_device(asgfem_ctx* ctx, int64_t nrows, const int64_t* rows, i
     return 0;
 }
 
-extern "C" int asgfem_pack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t* rows, void* dbuf) {
+extern "C" int asgfem_pack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t* rows, void* dbuf) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, nrows >= 0 && (nrows == 0 || (rows && dbuf)), ASGFEM_EINVAL, "pack_rows: bad arguments");
@@ -1153,8 +1214,9 @@ extern "C" int asgfem_pack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, co
     if (d_rows) cudaFree(d_rows);
     return rc;
 }
+ASG_BOUNDARY_CATCH(ctx)
 
-extern "C" int asgfem_unpack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t* rows, const void* dbuf) {
+extern "C" int asgfem_unpack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, const int64_t* rows, const void* dbuf) try {
     CTX_OR_FAIL(ctx);
     if (check_slot(ctx, slot)) return ASGFEM_EINVAL;
     ASG_CHECK(ctx, nrows >= 0 && (nrows == 0 || (rows && dbuf)), ASGFEM_EINVAL, "unpack_rows: bad arguments");
@@ -1166,3 +1228,4 @@ extern "C" int asgfem_unpack_rows(asgfem_ctx* ctx, int32_t slot, int64_t nrows, 
     if (d_rows) cudaFree(d_rows);
     return rc;
 }
+ASG_BOUNDARY_CATCH(ctx)

@@ -7,6 +7,8 @@
 
 #include <cstdio>
 #include <array>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -175,6 +177,20 @@ inline int fail(asgfem_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     return code;
 }
+
+// Every exported function is a function-try-block closed by this macro: nothing throws or aborts across the C boundary
+// (a failed host allocation becomes ASGFEM_ENOMEM, anything else ASGFEM_EINTERNAL with the exception's message).
+inline int boundary_fail(asgfem_ctx* ctx, int code, const char* what) noexcept {
+    try {
+        if (ctx) ctx->err = what;
+    } catch (...) {
+    }
+    return code;
+}
+#define ASG_BOUNDARY_CATCH(ctxp)                                                                                       \
+    catch (const std::bad_alloc&) { return asgfem::boundary_fail((ctxp), ASGFEM_ENOMEM, "out of host memory"); }       \
+    catch (const std::exception& e) { return asgfem::boundary_fail((ctxp), ASGFEM_EINTERNAL, e.what()); }              \
+    catch (...) { return asgfem::boundary_fail((ctxp), ASGFEM_EINTERNAL, "unknown C++ exception"); }
 
 #define ASG_CUDA(ctx, call)                                                                             \
     do {                                                                                                \

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdlib>
+#include <exception>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -23,7 +24,7 @@ namespace asgfem {
 // ---- worker pool ---------------------------------------------------------------------------------------------------
 // Workers spin briefly between jobs (the top of the elimination tree issues thousands of short jobs back to back) and
 // sleep on a condition variable otherwise.  Every worker acknowledges every job, so the job record is never rewritten
-// while somebody still reads it.
+// while somebody still reads it.  An exception inside a task (e.g. std::bad_alloc) is carried to the thread that called run().
 class DensePool {
    public:
     explicit DensePool(int nthreads) : nthreads_(std::max(1, nthreads)) {
@@ -56,12 +57,28 @@ class DensePool {
         }
         work(0);
         while (acks_.load(std::memory_order_acquire) != nthreads_ - 1) _mm_pause();
+        if (failed_.load(std::memory_order_acquire)) {  // first exception of a task, rethrown on the calling thread
+            std::exception_ptr e = error_;
+            error_ = nullptr;
+            failed_.store(false, std::memory_order_release);
+            std::rethrow_exception(e);
+        }
     }
 
    private:
     void work(int th) {
-        for (int t = next_.fetch_add(1, std::memory_order_relaxed); t < ntask_; t = next_.fetch_add(1, std::memory_order_relaxed))
-            (*body_)(th, t);
+        for (int t = next_.fetch_add(1, std::memory_order_relaxed); t < ntask_; t = next_.fetch_add(1, std::memory_order_relaxed)) {
+            if (failed_.load(std::memory_order_relaxed)) continue;  // drain the remaining tasks after a failure
+            try {
+                (*body_)(th, t);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!failed_.load(std::memory_order_relaxed)) {
+                    error_ = std::current_exception();
+                    failed_.store(true, std::memory_order_release);
+                }
+            }
+        }
     }
     void worker(int th) {
         uint64_t seen = 0;
@@ -92,6 +109,8 @@ class DensePool {
     const std::function<void(int, int)>* body_ = nullptr;
     int ntask_ = 0;
     bool stop_ = false;
+    std::atomic<bool> failed_{false};
+    std::exception_ptr error_;
 };
 
 DensePool* dense_pool_create(int nthreads) { return new DensePool(nthreads); }

@@ -127,7 +127,7 @@ void build_coupling(const MultiIndexSet& S, int family, Coupling& C) {
 
 using namespace asgfem;
 
-extern "C" int asgfem_coupling_weights(int32_t family, int64_t maxdeg, double* gplus, double* gminus) {
+extern "C" int asgfem_coupling_weights(int32_t family, int64_t maxdeg, double* gplus, double* gminus) try {
     if (maxdeg < 0 || !gplus || !gminus || (family != ASGFEM_LEGENDRE && family != ASGFEM_HERMITE)) return ASGFEM_EINVAL;
     std::vector<double> gp, gm;
     coupling_weights(family, maxdeg, gp, gm);
@@ -135,10 +135,11 @@ extern "C" int asgfem_coupling_weights(int32_t family, int64_t maxdeg, double* g
     std::memcpy(gminus, gm.data(), sizeof(double) * gm.size());
     return 0;
 }
+ASG_BOUNDARY_CATCH(nullptr)
 
 extern "C" int asgfem_add_boundary_modes(int64_t N, int64_t M, const int64_t* mi, int64_t p_extension, int64_t tail1,
                                          int64_t tail2, int64_t* N_ext, int64_t* M_ext, int64_t* out,
-                                         int64_t out_capacity) {
+                                         int64_t out_capacity) try {
     if (N < 1 || M < 1 || !mi || !N_ext || !M_ext) return ASGFEM_EINVAL;
     // first loop (:65-73): j = 2..N, range of k frozen at loop entry, lowest qualifying nonzero wins
     int64_t last_nonzero = 0, maxdegree1 = 0;
@@ -193,8 +194,9 @@ extern "C" int asgfem_add_boundary_modes(int64_t N, int64_t M, const int64_t* mi
     }
     return 0;
 }
+ASG_BOUNDARY_CATCH(nullptr)
 
-extern "C" int asgfem_classify_modes(int64_t N_ext, int64_t M, const int64_t* mi_ext, int64_t N_active, int32_t* cls) {
+extern "C" int asgfem_classify_modes(int64_t N_ext, int64_t M, const int64_t* mi_ext, int64_t N_active, int32_t* cls) try {
     if (N_ext < 1 || M < 1 || !mi_ext || !cls || N_active < 0 || N_active > N_ext) return ASGFEM_EINVAL;
     MiSet act;
     std::vector<int64_t> v((size_t)M);
@@ -252,3 +254,4 @@ extern "C" int asgfem_classify_modes(int64_t N_ext, int64_t M, const int64_t* mi
     }
     return 0;
 }
+ASG_BOUNDARY_CATCH(nullptr)

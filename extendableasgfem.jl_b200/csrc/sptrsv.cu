@@ -571,6 +571,10 @@ void build_tasks_host(const CholFactor& F, std::vector<SmallBlk>& blk, RawVec<un
     if (const char* e = std::getenv("ASGFEM_CHOL_THREADS")) nthreads = std::max(1, atoi(e));
     if (F.n < 20000) nthreads = 1;
     DensePool* pool = dense_pool_create(nthreads);
+    struct PoolGuard {
+        DensePool* p;
+        ~PoolGuard() { dense_pool_destroy(p); }
+    } pool_guard{pool};
     const int32_t grain = 16, njobs = (nsubs + grain - 1) / grain;
     // ---- pass A: rows below every sub-block
     std::vector<std::vector<int32_t>> lists((size_t)nsubs);
@@ -683,7 +687,6 @@ void build_tasks_host(const CholFactor& F, std::vector<SmallBlk>& blk, RawVec<un
             }
         }
     });
-    dense_pool_destroy(pool);
     std::vector<int32_t> order(tasks.size());
     for (size_t k = 0; k < order.size(); ++k) order[k] = (int32_t)k;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {

@@ -34,7 +34,8 @@ enum {
     ASGFEM_ESTATE = -2,  /* call order violated (e.g. apply before set_multiindices)  */
     ASGFEM_ECUDA = -3,   /* CUDA runtime error (message in asgfem_last_error)         */
     ASGFEM_ENOMEM = -4,  /* host or device allocation failed                          */
-    ASGFEM_ENUMERIC = -5 /* factorisation broke down (matrix not SPD on interior dofs) */
+    ASGFEM_ENUMERIC = -5, /* factorisation broke down (matrix not SPD on interior dofs) */
+    ASGFEM_EINTERNAL = -6 /* unexpected C++ exception caught at the boundary (message in asgfem_last_error) */
 };
 
 enum { ASGFEM_LEGENDRE = 0, ASGFEM_HERMITE = 1 }; /* src/orthogonal_polynomials/{Legendre_uniform,Hermite_normal}.jl */

@@ -87,3 +87,17 @@ def test_host_mirrors_match_oracle():
     for order in (1, 2, 4):
         assert np.allclose(A.quadrature_rule(order)[0], ofem.quadrature_rule(order)[0])
         assert np.allclose(A.quadrature_rule(order)[1], ofem.quadrature_rule(order)[1])
+
+
+def test_cxx_exceptions_do_not_cross_the_boundary():
+    """include/asgfem.h: "nothing throws or aborts across the boundary".  An absurd tail extension makes the index code ask
+    for vectors of 2^58 and 2^62 entries: std::bad_alloc must come back as ASGFEM_ENOMEM (-4) and std::length_error as
+    ASGFEM_EINTERNAL (-6) instead of terminating the host process."""
+    import ctypes as C
+    lib = _lib.load()
+    mi = np.zeros(1, dtype=np.int64)
+    n_ext, m_ext = C.c_int64(), C.c_int64()
+    out = np.zeros(4, dtype=np.int64)
+    codes = [lib.asgfem_add_boundary_modes(1, 1, mi.ctypes.data_as(C.c_void_p), 1, tail, 2, C.byref(n_ext), C.byref(m_ext),
+                                           out.ctypes.data_as(C.c_void_p), 4) for tail in (2 ** 58, 2 ** 62)]
+    assert codes == [-4, -6]
