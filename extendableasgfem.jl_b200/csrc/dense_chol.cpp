@@ -50,8 +50,8 @@ class DensePool {
         ntask_ = ntask;
         next_.store(0, std::memory_order_relaxed);
         acks_.store(0, std::memory_order_relaxed);
-        gen_.fetch_add(1, std::memory_order_release);
-        if (sleepers_.load(std::memory_order_acquire) > 0) {
+        gen_.fetch_add(1);  // seq_cst with the sleepers_ / gen_ pair below: a worker about to sleep is either seen here or sees the job
+        if (sleepers_.load() > 0) {
             std::lock_guard<std::mutex> lk(mu_);
             cv_.notify_all();
         }
@@ -90,9 +90,9 @@ class DensePool {
                     continue;
                 }
                 std::unique_lock<std::mutex> lk(mu_);
-                sleepers_.fetch_add(1, std::memory_order_acq_rel);
-                cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
-                sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+                sleepers_.fetch_add(1);
+                cv_.wait(lk, [&]() { return gen_.load() != seen; });
+                sleepers_.fetch_sub(1);
             }
             seen = gen_.load(std::memory_order_acquire);
             if (stop_) return;

@@ -92,3 +92,15 @@ def test_dense_kernel_variants_agree(isa):
         "assert np.max(np.abs(x - ref)) <= 1e-9 * np.max(np.abs(ref)), np.max(np.abs(x - ref))\n" % (ROOT, os.path.join(ROOT, "tests")))
     env = dict(os.environ, ASGFEM_CHOL_ISA=isa)
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT, env=env, timeout=300)
+
+
+def test_factorisation_is_bit_reproducible_across_thread_counts(monkeypatch):
+    """Every entry of a front is updated by one register tile per panel, in panel order, and the extend-add visits the
+    children in tree order: the factor (hence the solve) does not depend on how the work was spread over the threads."""
+    space, indptr, indices, k0 = _mean_stiffness(omesh.uniform_refine(omesh.grid_unitsquare(), 8), 1)
+    b = np.cos(np.arange(space.ndofs) * 0.01)
+    xs = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("ASGFEM_CHOL_THREADS", threads)
+        xs.append(A.host_factor_solve(indptr, indices, k0, space.bdofs + 1, b, _dof_coords(space))[0])
+    assert np.array_equal(xs[0], xs[1]) and np.array_equal(xs[0], xs[2])
