@@ -104,3 +104,19 @@ def test_factorisation_is_bit_reproducible_across_thread_counts(monkeypatch):
         monkeypatch.setenv("ASGFEM_CHOL_THREADS", threads)
         xs.append(A.host_factor_solve(indptr, indices, k0, space.bdofs + 1, b, _dof_coords(space))[0])
     assert np.array_equal(xs[0], xs[1]) and np.array_equal(xs[0], xs[2])
+
+
+def test_multifrontal_and_task_builder_against_their_serial_references():
+    """tools/chol_bench.cpp (host functions of libasgfem_cuda.so, no GPU): the multifrontal factor has the patterns of
+    the scalar up-looking factorisation and its values to 1e-9 (observed 1e-14), and the parallel sweep-task builder
+    produces byte for byte the records, descriptors and launch list of the serial builder it replaced."""
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    env = dict(os.environ, ASGFEM_CHOL_VERBOSE="", TMPDIR=os.environ.get("TMPDIR", "/tmp"))
+    env.pop("ASGFEM_CHOL_UPLOOKING", None)
+    r = subprocess.run([os.path.join(ROOT, "tools", "chol_bench.sh"), "180", "check"], cwd=ROOT, env=env, timeout=600,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "patterns identical: yes" in r.stdout
+    assert r.stdout.count("identical: yes") == 3  # factor patterns + the task records of both factors

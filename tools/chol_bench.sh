@@ -6,4 +6,6 @@ CS=$ROOT/extendableasgfem.jl_b200/csrc
 OUT=${TMPDIR:-/tmp}/asgfem_chol_bench
 LIBDIR=$ROOT/extendableasgfem.jl_b200
 g++ -O2 -std=c++17 -pthread -I$CS -I$ROOT/include -I/usr/local/cuda/include $ROOT/tools/chol_bench.cpp -L$LIBDIR -l:libasgfem_cuda.so -Wl,-rpath,$LIBDIR -o $OUT
-ASGFEM_CHOL_VERBOSE=${ASGFEM_CHOL_VERBOSE-1} $OUT "$@"
+ASGFEM_CHOL_VERBOSE=${ASGFEM_CHOL_VERBOSE-1}
+if [ -z "$ASGFEM_CHOL_VERBOSE" ]; then unset ASGFEM_CHOL_VERBOSE; else export ASGFEM_CHOL_VERBOSE; fi
+$OUT "$@"
