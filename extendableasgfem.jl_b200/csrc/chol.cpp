@@ -573,23 +573,8 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         }
 
     chol_tick("elimination tree");
-    // ---- row patterns by row-subtree traversal (ereach); pass 1 counts, pass 2 factorises ------------
-    std::vector<int32_t> flag((size_t)n, -1), stack((size_t)n), rowlen((size_t)n, 0);
-    std::vector<int64_t> colcount((size_t)n, 1);  // diagonal
-    auto ereach = [&](int32_t k, int32_t& top) {
-        top = n;
-        flag[k] = k;
-        for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
-            int32_t i = Ci[p];
-            if (i > k) continue;
-            int32_t len = 0;
-            for (; flag[i] != k; i = parent[i]) {
-                stack[len++] = i;
-                flag[i] = k;
-            }
-            while (len > 0) stack[--top] = stack[--len];
-        }
-    };
+    std::vector<int32_t> rowlen((size_t)n, 0);
+    // ---- symbolic + numeric factorisation: multifrontal (default) ---------------------------------------------------------
     const bool uplooking = std::getenv("ASGFEM_CHOL_UPLOOKING") != nullptr;
     if (!uplooking) {
         // fronts of the multifrontal phase: the nodes of the dissection tree (chunks of one separator joined again)
@@ -743,6 +728,24 @@ int cholesky_reduced(int64_t n_full, const int64_t* rowptr, const int32_t* col, 
         for (int32_t k = 0; k < n; ++k) F.perm[k] = full[perm[k]];
         return 0;
     }
+    // ---- cross-check path (ASGFEM_CHOL_UPLOOKING=1): scalar up-looking factorisation -----------------------------------
+    // row patterns by row-subtree traversal (ereach); pass 1 counts, pass 2 factorises
+    std::vector<int32_t> flag((size_t)n, -1), stack((size_t)n);
+    std::vector<int64_t> colcount((size_t)n, 1);  // diagonal
+    auto ereach = [&](int32_t k, int32_t& top) {
+        top = n;
+        flag[k] = k;
+        for (int64_t p = Cp[k]; p < Cp[k + 1]; ++p) {
+            int32_t i = Ci[p];
+            if (i > k) continue;
+            int32_t len = 0;
+            for (; flag[i] != k; i = parent[i]) {
+                stack[len++] = i;
+                flag[i] = k;
+            }
+            while (len > 0) stack[--top] = stack[--len];
+        }
+    };
     int64_t lnz = 0;
     {
         F.node_lo.clear(), F.node_hi.clear();
