@@ -426,11 +426,23 @@ int32_t multifrontal_numeric(int32_t n, const std::vector<int64_t>& Cp, const st
     std::vector<int32_t> order(roots.size());
     std::iota(order.begin(), order.end(), 0);
     std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return fronts[(size_t)roots[(size_t)x]].subtree > fronts[(size_t)roots[(size_t)y]].subtree; });
+    const auto t_sub = std::chrono::steady_clock::now();
     dense_pool_run(pool, (int)order.size(), [&](int th, int g) {
         for (int32_t t : members[(size_t)order[(size_t)g]]) process(t, th, nullptr);
     });
+    const auto t_top = std::chrono::steady_clock::now();
+    int32_t ntop = 0;
     for (int32_t t = 0; t < nf; ++t)
-        if (group[(size_t)t] < 0) process(t, 0, pool);
+        if (group[(size_t)t] < 0) {
+            process(t, 0, pool);
+            ++ntop;
+        }
+    if (std::getenv("ASGFEM_CHOL_VERBOSE")) {
+        const double s_sub = std::chrono::duration<double>(t_top - t_sub).count();
+        const double s_top = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_top).count();
+        fprintf(stderr, "[chol] multifrontal: %d fronts, %.1f GFLOP (%s, %d threads): %zu subtrees %.3f s, %d top fronts %.3f s\n", nf,
+                total * 1.0e-9, dense_kernel_name(), nthreads, roots.size(), s_sub, ntop, s_top);
+    }
     return bad_pivot.load();
 }
 
